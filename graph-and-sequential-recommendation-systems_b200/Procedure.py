@@ -1,0 +1,145 @@
+"""Training and evaluation procedures with the reference's signatures (code/Procedure.py).
+
+BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=None) -> str
+Test(dataset, Recmodel, epoch, w=None, multicore=0) -> {'precision','recall','ndcg': np.ndarray}
+
+What changed underneath:
+  * training: the epoch's shuffled triples are moved to the device once (as in the reference,
+    code/Procedure.py:52-55) and every step is a device-side window move + one CUDA-graph replay;
+    the per-step loss is accumulated on the device and read once per epoch (the reference syncs
+    with loss.cpu().item() every step, code/utils.py:64).  The returned string and the CSV row are
+    the reference's: sum of step losses / (len//batch + 1).
+  * evaluation: propagation runs ONCE (the reference recomputes it for each of the 299 user
+    batches), scoring + train-item mask + top-k is one fused kernel, and precision/recall/NDCG are
+    reduced on the device.  Users are evaluated in testDict order; tiling is free because results
+    are per-user.
+"""
+import csv
+import os
+
+import numpy as np
+import torch
+
+from . import ops, utils, world
+from .utils import timer
+
+
+def _save_dir():
+    return world.config.get('path', world.config.get('checkpoint_dir', './checkpoints'))
+
+
+def _append_csv(name, header, row):
+    save_path = _save_dir()
+    os.makedirs(save_path, exist_ok=True)
+    path = os.path.join(save_path, name)
+    if not os.path.exists(path):
+        with open(path, 'w', newline='') as f:
+            csv.writer(f).writerow(header)
+    with open(path, 'a', newline='') as f:
+        csv.writer(f).writerow(row)
+
+
+def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=None):
+    Recmodel = recommend_model
+    Recmodel.train()
+    bpr = loss_class
+    with timer(name="Sample"):
+        S = utils.UniformSample_original(dataset)
+    bs = world.config['bpr_batch_size']
+    # int64 on the device directly (the reference's torch.Tensor(...).long() float32 round trip,
+    # code/Procedure.py:52-54, is exact only below 2^24 — SURVEY.md A16)
+    S_t = torch.from_numpy(np.ascontiguousarray(S[:, :3].T)).to(torch.int64)
+    perm = np.arange(S_t.shape[1])
+    np.random.shuffle(perm)                       # same RNG call as utils.shuffle (code/utils.py:148)
+    S_t = S_t[:, torch.from_numpy(perm)]
+    n = S_t.shape[1]
+    total_batch = n // bs + 1
+    if getattr(bpr, 'fused', False):
+        eng = Recmodel._engine
+        if eng.B_cap != bs:
+            eng._alloc_batch(bs)
+        eng.set_lr(bpr.opt.param_groups[0]['lr'])
+        eng.decay = float(bpr.weight_decay)
+        steps = eng.begin_epoch(S_t.to(world.device))
+        for batch_i in range(steps):
+            eng.epoch_step()
+            if world.tensorboard and w is not None:
+                w.add_scalar('BPRLoss/BPR', float(eng.loss_to_host()[2]), epoch * total_batch + batch_i)
+        aver_loss = float(eng.loss_to_host()[3])
+    else:
+        users, posItems, negItems = (S_t[i].to(world.device) for i in range(3))
+        aver_loss = 0.
+        for batch_i, (u, p, nn_) in enumerate(utils.minibatch(users, posItems, negItems, batch_size=bs)):
+            cri = bpr.stageOne(u, p, nn_)
+            aver_loss += cri
+            if world.tensorboard and w is not None:
+                w.add_scalar('BPRLoss/BPR', cri, epoch * total_batch + batch_i)
+    aver_loss = aver_loss / total_batch          # code/Procedure.py:57,68 (keeps the +1 quirk)
+    _append_csv('train_epoch_metrics.csv', ['epoch', 'loss'], [epoch, aver_loss])
+    time_info = timer.dict()
+    timer.zero()
+    return f"loss{aver_loss:.3f}-{time_info}"
+
+
+def test_one_batch(X):
+    """Host metric arithmetic for one user (code/Procedure.py:89-121); kept for API parity and as the
+    cross-check of the device metric kernel."""
+    sorted_items = X[0].cpu().numpy() if isinstance(X[0], torch.Tensor) else np.asarray(X[0])
+    groundTrue = X[1]
+    if not isinstance(groundTrue, (list, set, tuple, np.ndarray)):
+        groundTrue = [groundTrue]
+    test_data = [groundTrue]
+    r = np.expand_dims(utils.getLabel(groundTrue, sorted_items), axis=0)
+    pre, recall, ndcg = [], [], []
+    for k in world.topks:
+        ret = utils.RecallPrecision_ATk(test_data, r, k)
+        pre.append(ret['precision'])
+        recall.append(ret['recall'])
+        ndcg.append(utils.NDCGatK_r(test_data, r, k))
+    return {'precision': np.array(pre), 'recall': np.array(recall), 'ndcg': np.array(ndcg)}
+
+
+def rank_all(dataset, Recmodel, k, user_tile=8192):
+    """Top-k item ids for every user of testDict (key order) -> int64 device tensor [n_test_users, k]."""
+    users_dev, _, _ = dataset.test_csr()
+    out = []
+    for lo in range(0, users_dev.numel(), user_tile):
+        idx, _ = Recmodel.rank_topk(users_dev[lo:lo + user_tile], k)
+        out.append(idx)
+    return torch.cat(out, dim=0) if len(out) > 1 else out[0]
+
+
+def Test(dataset, Recmodel, epoch, w=None, multicore=0):
+    Recmodel = Recmodel.eval()
+    max_K = max(world.topks)
+    results = {m: np.zeros(len(world.topks)) for m in ['precision', 'recall', 'ndcg']}
+    with torch.no_grad():
+        users_dev, t_indptr, t_indices = dataset.test_csr()
+        n_users_eval = users_dev.numel()
+        if n_users_eval:
+            if hasattr(Recmodel, 'rank_topk'):
+                topk = rank_all(dataset, Recmodel, max_K, user_tile=max(int(world.config.get('test_u_batch_size', 100)), 8192))
+            else:   # a foreign model: the reference's unfused recipe, one user tile at a time
+                parts = []
+                u_bs = world.config['test_u_batch_size']
+                for lo in range(0, n_users_eval, u_bs):
+                    bu = users_dev[lo:lo + u_bs]
+                    rating = Recmodel.getUsersRating(bu)
+                    allPos = dataset.getUserPosItems(bu.cpu().tolist())
+                    ex_i = np.concatenate([np.full(len(it), i) for i, it in enumerate(allPos)])
+                    ex_j = np.concatenate([np.asarray(it) for it in allPos])
+                    rating[torch.from_numpy(ex_i).to(rating.device), torch.from_numpy(ex_j).long().to(rating.device)] = -(1 << 10)
+                    parts.append(torch.topk(rating, k=max_K)[1])
+                topk = torch.cat(parts, dim=0)
+            sums = ops.rank_metrics(topk.contiguous(), t_indptr, t_indices, world.topks).cpu().numpy()
+            results['precision'] = sums[:, 0] / n_users_eval
+            results['recall'] = sums[:, 1] / n_users_eval
+            results['ndcg'] = sums[:, 2] / n_users_eval
+    prec, rec, nd = float(results['precision'][0]), float(results['recall'][0]), float(results['ndcg'][0])
+    _append_csv('valid_epoch_metrics.csv', ['epoch', 'precision', 'recall', 'ndcg'], [epoch, prec, rec, nd])
+    if world.tensorboard and w is not None:
+        w.add_scalars(f'Test/Recall@{world.topks}', {str(world.topks[i]): results['recall'][i] for i in range(len(world.topks))}, epoch)
+        w.add_scalars(f'Test/Precision@{world.topks}', {str(world.topks[i]): results['precision'][i] for i in range(len(world.topks))}, epoch)
+        w.add_scalars(f'Test/NDCG@{world.topks}', {str(world.topks[i]): results['ndcg'][i] for i in range(len(world.topks))}, epoch)
+    print(results)
+    return results

@@ -1,0 +1,73 @@
+// adam.cu — torch.optim.Adam (defaults) as device kernels; replaces self.opt.step()
+// (reference code/utils.py:51,62).  The bias-correction scalars are computed on the device in
+// double precision — the same arithmetic torch does with Python floats — so a whole training step
+// can sit inside one CUDA graph with no host-side step counter.
+#include "common.cuh"
+
+namespace lgcn {
+
+__global__ void adam_init_kernel(lgcn_adam_scalars_t* s, float lr, float b1, float b2, float eps, int step) {
+    s->lr = lr; s->beta1 = b1; s->beta2 = b2; s->eps = eps; s->step = step; s->pad = 0;
+    const int t = step > 0 ? step : 1;
+    s->step_size = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
+    s->bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)t));
+}
+
+__global__ void adam_tick_kernel(lgcn_adam_scalars_t* s) {
+    const int t = s->step + 1;
+    s->step = t;
+    s->step_size = (float)((double)s->lr / (1.0 - pow((double)s->beta1, (double)t)));
+    s->bc2_sqrt = (float)sqrt(1.0 - pow((double)s->beta2, (double)t));
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, const float4* __restrict__ G,
+            long long n4, const lgcn_adam_scalars_t* __restrict__ sc) {
+    const float b1 = sc->beta1, b2 = sc->beta2, eps = sc->eps, step_size = sc->step_size, bc2s = sc->bc2_sqrt;
+    const float w1 = 1.f - b1, w2 = 1.f - b2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 p = P[i], m = M[i], v = V[i]; const float4 g = ld_once_f4(G + i);
+#define LGCN_ADAM1(c) \
+        m.c = m.c + w1 * (g.c - m.c); \
+        v.c = v.c * b2 + w2 * g.c * g.c; \
+        p.c = p.c - step_size * (m.c / (sqrtf(v.c) / bc2s + eps));
+        LGCN_ADAM1(x) LGCN_ADAM1(y) LGCN_ADAM1(z) LGCN_ADAM1(w)
+#undef LGCN_ADAM1
+        P[i] = p; M[i] = m; V[i] = v;
+    }
+}
+
+}  // namespace lgcn
+
+using namespace lgcn;
+
+extern "C" int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, float lr, float beta1, float beta2, float eps,
+                              int32_t step, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(scalars_dev, "adam_init: null scalars");
+    adam_init_kernel<<<1, 1, 0, as_stream(stream)>>>(scalars_dev, lr, beta1, beta2, eps, step);
+    LGCN_CHECK_LAUNCH("adam_init_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_adam_tick(lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(scalars_dev, "adam_tick: null scalars");
+    adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(scalars_dev);
+    LGCN_CHECK_LAUNCH("adam_tick_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_adam_f32(float* P, float* M, float* V, const float* G, int64_t n,
+                             const lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(P && M && V && G && scalars_dev, "adam: null argument");
+    LGCN_CHECK_ARG(n >= 0 && n % 4 == 0, "adam: n=%lld must be a multiple of 4", (long long)n);
+    LGCN_CHECK_ARG(((uintptr_t)P % 16) == 0 && ((uintptr_t)M % 16) == 0 && ((uintptr_t)V % 16) == 0 && ((uintptr_t)G % 16) == 0, "adam: 16-byte alignment required");
+    if (n == 0) return 0;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(P), reinterpret_cast<float4*>(M),
+        reinterpret_cast<float4*>(V), reinterpret_cast<const float4*>(G), n4, scalars_dev);
+    LGCN_CHECK_LAUNCH("adam_kernel");
+    return 0;
+}

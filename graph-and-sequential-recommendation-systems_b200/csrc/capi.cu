@@ -1,0 +1,80 @@
+// capi.cu — runtime glue behind the C ABI: error channel, device info, and the host-side negative
+// sampler that keeps the semantics of the reference's only native component
+// (code/sources/sampling.cpp:27-56, 88-91) so utils.UniformSample_original works unchanged.
+#include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+
+namespace lgcn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+int fail(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return 1;
+}
+
+static int g_sm_count = 0, g_smem_optin = 0;
+static void query_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { g_sm_count = 148; g_smem_optin = 227 * 1024; return; }
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+    if (g_smem_optin <= 0) g_smem_optin = 227 * 1024;
+}
+int sm_count() { if (!g_sm_count) query_device(); return g_sm_count; }
+int max_smem_optin() { if (!g_smem_optin) query_device(); return g_smem_optin; }
+
+}  // namespace lgcn
+
+using namespace lgcn;
+
+extern "C" int lgcn_abi_version(void) { return LGCN_ABI_VERSION; }
+extern "C" const char* lgcn_last_error(void) { return g_err; }
+
+extern "C" int lgcn_device_info(int32_t* out_host) {
+    LGCN_CHECK_ARG(out_host, "device_info: null output");
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail("device_info: %s", cudaGetErrorString(e));
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    out_host[0] = sm_count(); out_host[1] = max_smem_optin(); out_host[2] = major * 10 + minor;
+    return 0;
+}
+
+// ---- host sampler: glibc rand() stream, same draw order as sampling.cpp ---------------------
+extern "C" void lgcn_sampler_seed(uint32_t seed) { srand(seed); }
+
+extern "C" int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_num,
+                                        const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
+                                        int32_t neg_num, int32_t* out_host) {
+    if (user_num <= 0 || item_num <= 0 || neg_num < 1 || !allpos_indptr_host || !allpos_items_host || !out_host) {
+        set_error("sample_negative: bad arguments"); return -1;
+    }
+    const int64_t per_user = train_num / user_num;
+    const int row = neg_num + 2;
+    for (int32_t user = 0; user < user_num; ++user) {
+        const int32_t* pos = allpos_items_host + allpos_indptr_host[user];
+        const int64_t npos = allpos_indptr_host[user + 1] - allpos_indptr_host[user];
+        if (npos <= 0 && per_user > 0) { set_error("sample_negative: user %d has no positive item", user); return -2; }
+        if (npos >= item_num && per_user > 0) { set_error("sample_negative: user %d interacted with every item", user); return -3; }
+        for (int64_t pair = 0; pair < per_user; ++pair) {
+            int32_t* o = out_host + ((int64_t)user * per_user + pair) * row;
+            o[0] = user;
+            o[1] = pos[rand() % npos];
+            for (int idx = 2; idx < row; ++idx) {
+                int neg;
+                do { neg = rand() % item_num; } while (std::find(pos, pos + npos, neg) != pos + npos);
+                o[idx] = neg;
+            }
+        }
+    }
+    return (int64_t)user_num * per_user;
+}

@@ -1,0 +1,328 @@
+"""Propagation / training-step engine: owns the HBM-resident buffers and sequences the kernels.
+
+What the reference does with torch ops per step (code/utils.py:53-64 -> code/model.py:162-231):
+cat -> L x sparse.mm -> stack -> mean -> 3 gathers -> ~10 elementwise kernels -> autograd backward
+(L more sparse.mm on a transposed COO, index_put, stack/mean/cat backward) -> Adam.  Here a step is
+
+    K1 x (L-1)   X_k = A X_{k-1}
+    K1           out = (A X_{L-1} + X_0 + ... + X_{L-1}) / (L+1)        (layer mean fused)
+    K2           loss, reg, G = d(loss + decay*reg)/d(out)              (closed form, scatter-add)
+    K1 x (L-1)   g_{L-1} = s (G + A G);  g_k = s G + A g_{k+1}           (s = 1/(L+1); A symmetric)
+    K1 + Adam    g_0 = s G + A g_1  consumed by the Adam epilogue, never written
+    clear        the <= 3B rows of G the batch touched
+
+all on one stream, optionally captured in a CUDA graph.  Buffers: E0 (parameters, [users;items]),
+L-1 layer buffers (re-used as backward ping-pong), out, G, Adam M/V — (L+4) * N * d * 4 bytes.
+
+Multi-GPU (one process per GPU, torch.distributed):
+  mode 'dp'       graph replicated, batch sharded, G all-reduced  (weak scaling of the batch)
+  mode 'rowpart'  rows of A partitioned in contiguous nnz-balanced blocks; every layer's output block
+                  is all-gathered; K2 runs redundantly on the full batch so no gradient collective is
+                  needed; Adam only touches owned rows.
+"""
+import torch
+
+from . import ops
+
+
+def balanced_row_bounds(indptr_cpu, parts):
+    """Contiguous row blocks with ~equal nnz: returns parts+1 boundaries (host int list)."""
+    n_rows = indptr_cpu.numel() - 1
+    nnz = int(indptr_cpu[-1])
+    bounds = [0]
+    for p in range(1, parts):
+        target = nnz * p // parts
+        r = int(torch.searchsorted(indptr_cpu, torch.tensor(target, dtype=indptr_cpu.dtype), right=False))
+        r = max(bounds[-1], min(r, n_rows))
+        bounds.append(r)
+    bounds.append(n_rows)
+    return bounds
+
+
+def allgather_rows(buf, bounds, group=None):
+    """Uneven in-place all-gather: rank p broadcasts rows [bounds[p], bounds[p+1]) of `buf`.
+    Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    for p in range(world):
+        b0, b1 = bounds[p], bounds[p + 1]
+        if b1 > b0:
+            src = dist.get_global_rank(group, p) if group is not None else p
+            dist.broadcast(buf[b0:b1], src=src, group=group)
+    return buf
+
+
+def shard_batch(n, rank, world):
+    """Contiguous shard [lo,hi) of a batch of n triples for data-parallel rank `rank`."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+class Engine:
+    def __init__(self, csr, n_users, m_items, d, n_layers, device, *, lr=1e-3, decay=1e-4, B_cap=2048,
+                 deterministic=False, use_graph=True, dist_mode=None, group=None):
+        if n_layers > 8:
+            raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
+        self.csr = csr
+        self.nu, self.ni, self.N, self.d, self.L = n_users, m_items, n_users + m_items, d, n_layers
+        self.device = device
+        self.decay, self.lr = float(decay), float(lr)
+        self.deterministic = bool(deterministic)
+        self.B_cap = int(B_cap)
+        self.dist_mode = dist_mode
+        self.group = group
+        self.rank, self.world = 0, 1
+        if dist_mode is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.use_graph = bool(use_graph) and dist_mode is None
+        N, L = self.N, self.L
+        f32 = dict(dtype=torch.float32, device=device)
+        self.E0 = torch.zeros((N, d), **f32)
+        self.X = [torch.zeros((N, d), **f32) for _ in range(max(L - 1, 0))]
+        self.out = torch.zeros((N, d), **f32)
+        self.G = torch.zeros((N, d), **f32)
+        self.M = torch.zeros((N, d), **f32)
+        self.V = torch.zeros((N, d), **f32)
+        self._gradE0 = None
+        self._scratch = None
+        self.loss_out = torch.zeros(4, **f32)
+        self.scalars = ops.adam_scalars(device, self.lr)
+        self._host_step = 0
+        self.param_epoch = 0
+        # row partition
+        self.r0, self.r1 = 0, N
+        self.bounds = [0, N]
+        self.local = csr
+        if dist_mode == 'rowpart':
+            self.bounds = balanced_row_bounds(csr.indptr.cpu(), self.world)
+            self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+            self.local = csr.rows(self.r0, self.r1)
+        # batch staging: [ctl(4 x int32) | users | pos | neg] in one block so that a host batch is one H2D
+        self._alloc_batch(self.B_cap)
+        self._epoch = None          # (S tensor [3,cap], ctl) for epoch-resident mode
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ batch staging
+    def _alloc_batch(self, B_cap):
+        self.B_cap = int(B_cap)
+        self._blk = torch.zeros(2 + 3 * self.B_cap, dtype=torch.int64, device=self.device)
+        self.ctl = self._blk[:2].view(torch.int32)
+        self.bu = self._blk[2:2 + self.B_cap]
+        self.bp = self._blk[2 + self.B_cap:2 + 2 * self.B_cap]
+        self.bn = self._blk[2 + 2 * self.B_cap:2 + 3 * self.B_cap]
+        # two pinned staging buffers: a buffer is rewritten only after the H2D that read it has finished
+        self._stage = [[torch.zeros(2 + 3 * self.B_cap, dtype=torch.int64).pin_memory(), None] for _ in range(2)]
+        self._stage_i = 0
+        self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.bpr_ws = ops.bpr_workspace(self.B_cap, self.d, self.device)
+        self._graphs = {}
+
+    def _stage_batch(self, users, pos, neg, B_global=0):
+        B = int(users.numel())
+        if B > self.B_cap:
+            torch.cuda.current_stream().synchronize()
+            self._alloc_batch(B)
+        self._stage_i ^= 1
+        slot = self._stage[self._stage_i]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        h = slot[0]
+        if users.is_cuda:
+            self.bu[:B].copy_(users.to(torch.int64), non_blocking=True)
+            self.bp[:B].copy_(pos.to(torch.int64), non_blocking=True)
+            self.bn[:B].copy_(neg.to(torch.int64), non_blocking=True)
+            hc = h[:2].view(torch.int32)
+            hc[0], hc[1], hc[2], hc[3] = 0, B, B, B_global
+            self._blk[:2].copy_(h[:2], non_blocking=True)
+        else:
+            hc = h[:2].view(torch.int32)
+            hc[0], hc[1], hc[2], hc[3] = 0, B, B, B_global
+            cap = self.B_cap
+            h[2:2 + B].copy_(users)
+            h[2 + cap:2 + cap + B].copy_(pos)
+            h[2 + 2 * cap:2 + 2 * cap + B].copy_(neg)
+            if B == cap:
+                self._blk.copy_(h, non_blocking=True)                       # one H2D for the whole batch
+            else:
+                self._blk[:2 + B].copy_(h[:2 + B], non_blocking=True)
+                self._blk[2 + cap:2 + cap + B].copy_(h[2 + cap:2 + cap + B], non_blocking=True)
+                self._blk[2 + 2 * cap:2 + 2 * cap + B].copy_(h[2 + 2 * cap:2 + 2 * cap + B], non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return B
+
+    # ------------------------------------------------------------------ collectives
+    def _allgather_rows(self, buf):
+        """Every rank broadcasts its row block of `buf` (uneven all-gather, in place)."""
+        allgather_rows(buf, self.bounds, self.group)
+
+    def _layer(self, X, Y, alpha, beta, zs):
+        r0, r1 = self.r0, self.r1
+        if self.dist_mode == 'rowpart':
+            ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None)
+            self._allgather_rows(Y)
+        else:
+            ops.spmm(self.csr, X, Y, alpha, beta, zs)
+
+    # ------------------------------------------------------------------ propagation
+    def forward(self):
+        """out = mean_{k<=L} A^k E0  (reference code/model.py:201-222)."""
+        L, s = self.L, 1.0 / (self.L + 1)
+        if self.dist_mode == 'rowpart':
+            self._allgather_rows(self.E0)       # owners publish their updated parameter rows
+        if L == 0:
+            self.out.copy_(self.E0)
+            return self.out
+        cur = self.E0
+        for k in range(L - 1):
+            self._layer(cur, self.X[k], 1.0, 0.0, None)
+            cur = self.X[k]
+        self._layer(cur, self.out, s, s, [self.E0] + self.X[:L - 1])
+        return self.out
+
+    def _backward_chain(self, G, last):
+        """g_0 = dL/dE0 given G = dL/dout.  `last(X, alpha, beta, zs)` runs the final product."""
+        L, s = self.L, 1.0 / (self.L + 1)
+        if L == 1:
+            return last(G, s, s, [G])
+        bufs = self.X if L >= 3 else [self.X[0], None]
+        if L >= 3 and len(bufs) < 2:
+            raise RuntimeError("internal: missing ping-pong buffers")
+        cur = bufs[0]
+        self._layer(G, cur, s, s, [G])
+        for _ in range(L - 2):
+            nxt = bufs[1] if cur is bufs[0] else bufs[0]
+            self._layer(cur, nxt, 1.0, s, [G])
+            cur = nxt
+        return last(cur, 1.0, s, [G])
+
+    def backward_to(self, G, grad_out):
+        """grad_out (N,d) = dL/dE0 for an arbitrary dense G (generic autograd path)."""
+        if self.L == 0:
+            grad_out.copy_(G)
+            return grad_out
+        if self.dist_mode == 'rowpart':
+            r0, r1 = self.r0, self.r1
+
+            def last(X, alpha, beta, zs):
+                ops.spmm(self.local, X, grad_out[r0:r1], alpha, beta, [z[r0:r1] for z in zs])
+                self._allgather_rows(grad_out)
+        else:
+            def last(X, alpha, beta, zs):
+                ops.spmm(self.csr, X, grad_out, alpha, beta, zs)
+        self._backward_chain(G, last)
+        return grad_out
+
+    def grad_buffer(self):
+        if self._gradE0 is None:
+            self._gradE0 = torch.zeros((self.N, self.d), dtype=torch.float32, device=self.device)
+        return self._gradE0
+
+    def scratch(self):
+        if self._scratch is None:
+            self._scratch = torch.zeros((self.N, self.d), dtype=torch.float32, device=self.device)
+        return self._scratch
+
+    # ------------------------------------------------------------------ fused training step
+    def set_lr(self, lr):
+        if float(lr) != self.lr:
+            self.lr = float(lr)
+            ops.adam_reinit(self.scalars, self.lr, step=self._host_step)
+
+    def set_adam_step(self, step):
+        self._host_step = int(step)
+        ops.adam_reinit(self.scalars, self.lr, step=self._host_step)
+
+    def _enqueue_step(self, users, pos, neg, ctl):
+        """Everything between 'batch is on the device' and 'loss_out is written'."""
+        N, s = self.N, 1.0 / (self.L + 1)
+        ops.adam_tick(self.scalars)
+        self.forward()
+        if self.dist_mode == 'dp':
+            import torch.distributed as dist
+            ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
+                            self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
+            dist.all_reduce(self.G, group=self.group)
+            dist.all_reduce(self.loss_out[:3], group=self.group)
+        else:
+            ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
+                            self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
+        r0, r1 = self.r0, self.r1
+        if self.L == 0:
+            ops.adam(self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.G[r0:r1], self.scalars)
+        else:
+            g = self.local if self.dist_mode == 'rowpart' else self.csr
+
+            def last(X, alpha, beta, zs):
+                ops.spmm_adam(g, X, self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.scalars, alpha, beta,
+                              [z[r0:r1] for z in zs])
+            self._backward_chain(self.G, last)
+        if self.dist_mode == 'dp':
+            self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
+        else:
+            ops.bpr_clear_rows(self.G, users, pos, neg, self.B_cap, ctl, self.nu)
+
+    def _warm_kernels(self, users, pos, neg, ctl):
+        """Run the step once on throw-away state so every kernel is loaded before graph capture."""
+        state = (self.E0, self.M, self.V, self.scalars, self.loss_out, ctl)
+        saved = [t.clone() for t in state]
+        ctl.zero_()                                   # B = 0: the batch kernels touch nothing
+        self._enqueue_step(users, pos, neg, ctl)
+        for dst, src in zip(state, saved):
+            dst.copy_(src)
+        self.G.zero_()
+        torch.cuda.current_stream().synchronize()
+
+    def _run(self, key, users, pos, neg, ctl):
+        if not self.use_graph:
+            self._enqueue_step(users, pos, neg, ctl)
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            self._warm_kernels(users, pos, neg, ctl)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_step(users, pos, neg, ctl)
+            self._graphs[key] = g
+        g.replay()
+
+    def step(self, users, pos, neg, B_global=0):
+        """One BPR step on a batch given as host or device int64 tensors. Returns nothing; the loss is
+        in self.loss_out (device).  Host batches cost one H2D copy."""
+        self._stage_batch(users, pos, neg, B_global)
+        self._run('direct', self.bu, self.bp, self.bn, self.ctl)
+        self._host_step += 1
+        self.param_epoch += 1
+
+    def loss_to_host(self):
+        """D2H of {bpr, reg, total, running sum}; synchronises the stream."""
+        self._loss_host.copy_(self.loss_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._loss_host
+
+    # epoch-resident mode: the whole epoch's shuffled triples live on the device, each step only moves
+    # the device-side window (lgcn_batch_advance) and replays the graph.
+    def begin_epoch(self, S_dev):
+        """S_dev int64[3, n] on the device (users, pos, neg rows)."""
+        n = S_dev.shape[1]
+        if self._epoch is None or self._epoch[0].shape[1] < n:
+            cap = max(n, 1)
+            S = torch.zeros((3, cap), dtype=torch.int64, device=self.device)
+            ctl = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self._epoch = (S, ctl)
+            self._graphs.pop('epoch', None)
+        S, ctl = self._epoch
+        S[:, :n].copy_(S_dev)
+        ctl.copy_(torch.tensor([0, 0, n, 0], dtype=torch.int32), non_blocking=False)
+        self.loss_out.zero_()
+        return (n + self.B_cap - 1) // self.B_cap
+
+    def epoch_step(self):
+        S, ctl = self._epoch
+        ops.batch_advance(ctl, self.B_cap)
+        self._run('epoch', S[0], S[1], S[2], ctl)
+        self._host_step += 1
+        self.param_epoch += 1

@@ -1,0 +1,281 @@
+"""Tensor-level wrappers over the C ABI (include/lgcn_b200.h).
+
+torch is used for device memory and streams only; every computation below is a kernel of
+liblgcn_b200.so launched on torch's current CUDA stream.  Nothing here falls back to torch ops.
+"""
+import ctypes
+from ctypes import byref, c_void_p
+
+import torch
+
+from . import _lib
+
+DEFAULT_SEG_LEN = 512
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _need(t, dtype, name, dim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    if dim is not None and t.dim() != dim:
+        raise RuntimeError(f"{name}: expected {dim} dimensions, got {t.dim()}")
+    return t
+
+
+def device_info():
+    out = (ctypes.c_int32 * 3)()
+    _lib.check(_lib.load().lgcn_device_info(out), "device_info")
+    return {"sm_count": out[0], "max_smem_optin": out[1], "cc": out[2]}
+
+
+class CSRGraph:
+    """int32 CSR on the device + the SpMM segment plan for its long rows."""
+
+    def __init__(self, indptr, indices, vals, n_cols, deg=None, dinv=None, seg_len=DEFAULT_SEG_LEN, row_order=None):
+        self.indptr = _need(indptr, torch.int32, "indptr", 1)
+        self.indices = _need(indices, torch.int32, "indices", 1)
+        self.vals = _need(vals, torch.float32, "vals", 1)
+        self.n_rows = indptr.numel() - 1
+        self.n_cols = int(n_cols)
+        self.nnz = indices.numel()
+        self.deg, self.dinv = deg, dinv
+        self.device = indptr.device
+        self.row_order = None if row_order is None else _need(row_order, torch.int32, "row_order", 1)
+        self._build_plan(seg_len)
+
+    def _build_plan(self, seg_len):
+        lib = _lib.load()
+        self.seg_len = int(seg_len)
+        counts = torch.zeros(2, dtype=torch.int32, device=self.device)
+        _lib.check(lib.lgcn_spmm_plan_count(_p(self.indptr), self.n_rows, self.seg_len, _p(counts), _stream()), "spmm_plan_count")
+        n_long, n_segs = (int(v) for v in counts.cpu().tolist())      # one-time setup sync
+        self.n_long, self.n_segs = n_long, n_segs
+        self._segs = torch.zeros(max(n_segs, 1) * 8, dtype=torch.int32, device=self.device)
+        self._counters = torch.zeros(max(n_long, 1), dtype=torch.int32, device=self.device)
+        if n_segs:
+            cursor = torch.zeros(2, dtype=torch.int32, device=self.device)
+            _lib.check(lib.lgcn_spmm_plan_fill(_p(self.indptr), self.n_rows, self.seg_len, _p(self._segs), _p(cursor), _stream()), "spmm_plan_fill")
+        self._partials = None
+        self._plan = None
+
+    def plan(self, d):
+        if self._plan is None or self._plan.d_max < d:
+            self._partials = torch.empty(max(self.n_segs, 1) * d, dtype=torch.float32, device=self.device)
+            pl = _lib.SpmmPlan()
+            pl.seg_len, pl.n_long, pl.n_segs, pl.d_max = self.seg_len, self.n_long, self.n_segs, d
+            pl.segs = self._segs.data_ptr()
+            pl.counters = self._counters.data_ptr()
+            pl.partials = self._partials.data_ptr()
+            pl.row_order = None if self.row_order is None else self.row_order.data_ptr()
+            self._plan = pl
+        return self._plan
+
+    def set_row_order(self, row_order):
+        self.row_order = None if row_order is None else _need(row_order, torch.int32, "row_order", 1)
+        self._plan = None
+
+    def rows(self, begin, end, seg_len=None):
+        """Row block [begin,end) as its own CSRGraph (indptr rebased; shares indices/vals storage)."""
+        ip = (self.indptr[begin:end + 1] - self.indptr[begin]).contiguous()
+        lo, hi = int(self.indptr[begin]), int(self.indptr[end])
+        return CSRGraph(ip, self.indices[lo:hi], self.vals[lo:hi], self.n_cols,
+                        seg_len=self.seg_len if seg_len is None else seg_len)
+
+    def to_torch_sparse_csr(self):
+        return torch.sparse_csr_tensor(self.indptr, self.indices, self.vals, size=(self.n_rows, self.n_cols),
+                                       check_invariants=False)
+
+    def algorithmic_bytes(self, d):
+        """B_spmm = 8*nnz + 4*(N+1) + 8*N*d."""
+        return 8 * self.nnz + 4 * (self.n_rows + 1) + 8 * self.n_rows * d
+
+
+def csr_build(train_user, train_item, n_users, m_items, seg_len=DEFAULT_SEG_LEN):
+    """K4: (trainUser, trainItem) int64 device arrays -> normalised symmetric bipartite CSRGraph."""
+    lib = _lib.load()
+    tu = _need(train_user, torch.int64, "train_user", 1)
+    ti = _need(train_item, torch.int64, "train_item", 1)
+    E = tu.numel()
+    if ti.numel() != E:
+        raise RuntimeError("csr_build: trainUser and trainItem differ in length")
+    dev = tu.device
+    N = n_users + m_items
+    indptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(max(2 * E, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(2 * E, 1), dtype=torch.float32, device=dev)
+    deg = torch.empty(N, dtype=torch.float32, device=dev)
+    dinv = torch.empty(N, dtype=torch.float32, device=dev)
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.lgcn_csr_build_workspace_bytes(E, n_users, m_items)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    _lib.check(lib.lgcn_csr_build(_p(tu), _p(ti), E, n_users, m_items, _p(indptr), _p(indices), _p(vals),
+                                  _p(deg), _p(dinv), _p(nnz), _p(status), c_void_p(ws_ptr), ws_bytes, _stream()), "csr_build")
+    nnz_h, status_h = int(nnz.item()), int(status.item())
+    if status_h != 0:
+        raise RuntimeError("csr_build: a user or item id is outside [0,n_users) x [0,m_items)")
+    del ws
+    return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], N, deg=deg, dinv=dinv, seg_len=seg_len)
+
+
+def coo_to_csr(rows, cols, vals, n_rows, n_cols, seg_len=DEFAULT_SEG_LEN):
+    """Row-major-sorted COO (torch coalesced layout) -> CSRGraph."""
+    lib = _lib.load()
+    rows = _need(rows, torch.int64, "rows", 1)
+    cols = _need(cols, torch.int64, "cols", 1)
+    vals = _need(vals.to(torch.float32), torch.float32, "vals", 1)
+    nnz = rows.numel()
+    indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=rows.device)
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=rows.device)
+    _lib.check(lib.lgcn_coo_to_csr(_p(rows), _p(cols), nnz, n_rows, _p(indptr), _p(indices), _stream()), "coo_to_csr")
+    return CSRGraph(indptr, indices[:nnz], vals, n_cols, seg_len=seg_len)
+
+
+def _z_array(zs):
+    zs = list(zs or [])
+    if len(zs) > _lib.MAX_Z:
+        raise RuntimeError(f"spmm: at most {_lib.MAX_Z} own-row addends (n_layers <= {_lib.MAX_Z})")
+    arr = (c_void_p * max(len(zs), 1))()
+    for i, z in enumerate(zs):
+        arr[i] = z.data_ptr()
+    return arr, len(zs)
+
+
+def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None):
+    """Y = alpha * (A @ X) + beta * sum(zs)  — K1.  X is indexed by column id, Y/zs by local row."""
+    lib = _lib.load()
+    d = X.shape[1]
+    _need(X, torch.float32, "X", 2), _need(Y, torch.float32, "Y", 2)
+    if X.shape[0] < g.n_cols or Y.shape[0] < g.n_rows or Y.shape[1] != d:
+        raise RuntimeError(f"spmm: shape mismatch X{tuple(X.shape)} Y{tuple(Y.shape)} graph {g.n_rows}x{g.n_cols}")
+    if Y.data_ptr() == X.data_ptr():
+        raise RuntimeError("spmm: Y must not alias X")
+    arr, nz = _z_array(zs)
+    for z in (zs or []):
+        _need(z, torch.float32, "z", 2)
+    _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
+                                 float(alpha), float(beta), arr, nz, byref(g.plan(d)), _stream()), "spmm")
+    return Y
+
+
+def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None):
+    """K1 with the Adam epilogue: grad = alpha*(A@X) + beta*sum(zs); P,M,V updated in place."""
+    lib = _lib.load()
+    d = X.shape[1]
+    for t, n in ((X, "X"), (P, "P"), (M, "M"), (V, "V")):
+        _need(t, torch.float32, n, 2)
+    arr, nz = _z_array(zs)
+    _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
+                                      float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
+                                      byref(g.plan(d)), _stream()), "spmm_adam")
+
+
+def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
+    s = torch.zeros(ctypes.sizeof(_lib.AdamScalars) // 4, dtype=torch.int32, device=device)
+    _lib.check(_lib.load().lgcn_adam_init(_p(s), lr, beta1, beta2, eps, int(step), _stream()), "adam_init")
+    return s
+
+
+def adam_reinit(scalars, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
+    _lib.check(_lib.load().lgcn_adam_init(_p(scalars), lr, beta1, beta2, eps, int(step), _stream()), "adam_init")
+
+
+def adam_tick(scalars):
+    _lib.check(_lib.load().lgcn_adam_tick(_p(scalars), _stream()), "adam_tick")
+
+
+def adam_step_count(scalars):
+    return int(scalars[6].item())
+
+
+def adam(P, M, V, G, scalars):
+    _lib.check(_lib.load().lgcn_adam_f32(_p(P), _p(M), _p(V), _p(G), P.numel(), _p(scalars), _stream()), "adam")
+
+
+def bpr_workspace(B_cap, d, device):
+    nbytes = _lib.load().lgcn_bpr_workspace_bytes(B_cap, d)
+    return torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)
+
+
+def bpr_fwd_bwd(out, users, pos, neg, B_cap, ctl, n_users, m_items, inv_norm, decay, c_bpr, c_reg,
+                loss_out, G, workspace, own=(0, None), deterministic=False):
+    """K2: loss_out[0..2] = (bpr, reg, bpr+decay*reg); G += closed-form gradient (if G is not None)."""
+    lib = _lib.load()
+    d = out.shape[1]
+    _need(out, torch.float32, "out", 2)
+    for t, n in ((users, "users"), (pos, "pos"), (neg, "neg")):
+        _need(t, torch.int64, n, 1)
+    _need(ctl, torch.int32, "ctl", 1), _need(loss_out, torch.float32, "loss_out", 1)
+    own_end = out.shape[0] if own[1] is None else own[1]
+    _lib.check(lib.lgcn_bpr_fwd_bwd(_p(out), _p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users, m_items, d,
+                                    float(inv_norm), float(decay), float(c_bpr), float(c_reg), _p(loss_out), _p(G),
+                                    int(own[0]), int(own_end), int(bool(deterministic)), _p(workspace),
+                                    workspace.numel() * 4, _stream()), "bpr_fwd_bwd")
+
+
+def bpr_clear_rows(G, users, pos, neg, B_cap, ctl, n_users):
+    _lib.check(_lib.load().lgcn_bpr_clear_rows(_p(G), _p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users,
+                                               G.shape[1], _stream()), "bpr_clear_rows")
+
+
+def batch_advance(ctl, B_cap):
+    _lib.check(_lib.load().lgcn_batch_advance(_p(ctl), B_cap, _stream()), "batch_advance")
+
+
+def score_topk(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=None, mask_col_offset=0):
+    """K3: per-row top-k item ids/scores with train items masked to -1024 (lowest id wins ties)."""
+    lib = _lib.load()
+    _need(users_emb, torch.float32, "users_emb", 2), _need(items_emb, torch.float32, "items_emb", 2)
+    Bt = users_emb.shape[0] if users is None else users.numel()
+    m_items, d = items_emb.shape
+    dev = items_emb.device
+    if users is not None:
+        _need(users, torch.int64, "users", 1)
+    idx = torch.empty((Bt, k), dtype=torch.int64, device=dev)
+    val = torch.empty((Bt, k), dtype=torch.float32, device=dev)
+    if Bt == 0:
+        return idx, val
+    ws_bytes = lib.lgcn_score_topk_workspace_bytes(Bt, m_items, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.lgcn_score_topk(_p(users_emb), _p(items_emb), _p(users), Bt, m_items, d, _p(mask_indptr),
+                                   _p(mask_indices), int(mask_col_offset), int(k), _p(idx), _p(val), _p(ws),
+                                   ws_bytes, _stream()), "score_topk")
+    return idx, val
+
+
+def score_dense(users_emb, items_emb, users):
+    lib = _lib.load()
+    _need(users_emb, torch.float32, "users_emb", 2), _need(items_emb, torch.float32, "items_emb", 2)
+    Bt = users_emb.shape[0] if users is None else users.numel()
+    m_items, d = items_emb.shape
+    out = torch.empty((Bt, m_items), dtype=torch.float32, device=items_emb.device)
+    if Bt:
+        if users is not None:
+            _need(users, torch.int64, "users", 1)
+        _lib.check(lib.lgcn_score_dense(_p(users_emb), _p(items_emb), _p(users), Bt, m_items, d, _p(out), _stream()), "score_dense")
+    return out
+
+
+def rank_metrics(topk_idx, test_indptr, test_indices, ks):
+    """Sums over rows of precision/recall/ndcg at each k in ks -> float64 tensor [len(ks), 3]."""
+    lib = _lib.load()
+    _need(topk_idx, torch.int64, "topk_idx", 2)
+    Bt, k_max = topk_idx.shape
+    ks_t = torch.tensor(list(ks), dtype=torch.int32, device=topk_idx.device)
+    sums = torch.zeros(len(ks) * 3, dtype=torch.float64, device=topk_idx.device)
+    _lib.check(lib.lgcn_rank_metrics(_p(topk_idx), Bt, k_max, _p(_need(test_indptr, torch.int32, "test_indptr", 1)),
+                                     _p(_need(test_indices, torch.int32, "test_indices", 1)), _p(ks_t), len(ks),
+                                     _p(sums), _stream()), "rank_metrics")
+    return sums.view(len(ks), 3)

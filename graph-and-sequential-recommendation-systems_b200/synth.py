@@ -1,0 +1,83 @@
+"""Synthetic interaction graphs with the shapes BASELINE.json names.
+
+User degrees come from a discretised log-normal calibrated to each dataset's train-degree
+median/mean, items from a rank-popularity law, pairs are de-duplicated, every user keeps at least one
+train item, and ~20 % of each user's interactions are held out as test.  Deterministic in `seed`.
+"""
+import numpy as np
+
+# name: (n_users, m_items, train_edges, median_train_deg, mean_train_deg, max_train_deg, item_slope)
+SHAPES = {
+    'gowalla': (29858, 40981, 810128, 16, 27.1, 811, 0.55),
+    'yelp2018': (31668, 38048, 1237259, 27, 39.1, 1800, 0.45),
+    'amazon-book': (52643, 91599, 2380730, 28, 45.2, 10400, 0.49),
+    'tiny': (300, 500, 6000, 14, 20.0, 120, 0.5),
+}
+
+
+def make_graph(name='yelp2018', seed=2020, scale=1.0, test_frac=0.2):
+    """Returns dict(n_users, m_items, train_user, train_item, test_user, test_item) (int64 arrays)."""
+    nu, ni, e_train, med, mean, dmax, slope = SHAPES[name]
+    nu, ni = max(8, int(nu * scale)), max(16, int(ni * scale))
+    e_train = int(e_train * scale)
+    rng = np.random.default_rng(seed)
+    # total (train+test) degree per user: log-normal with mean/median = exp(sigma^2/2)
+    sigma = np.sqrt(2.0 * np.log(max(mean / med, 1.0001)))
+    mu = np.log(med / (1.0 - test_frac))
+    deg = np.exp(rng.normal(mu, sigma, nu))
+    deg = np.clip(np.rint(deg), 2, min(dmax / (1.0 - test_frac), 0.5 * ni)).astype(np.int64)
+    if name == 'amazon-book':                       # the real data has one hub user (~10.4 k train items)
+        deg[rng.integers(nu)] = int(min(dmax / (1.0 - test_frac), 0.5 * ni))
+    target_total = e_train / (1.0 - test_frac)
+    deg = np.maximum(2, np.rint(deg * (target_total / deg.sum()))).astype(np.int64)
+    # item popularity: p_r ~ (r + r0)^-a  (head slope ~ -0.45..-0.6 on log-log rank plots)
+    ranks = np.arange(ni, dtype=np.float64)
+    w = (ranks + 0.002 * ni + 1.0) ** (-(slope + 0.35))
+    w[rng.random(ni) < 0.02] *= 1e-4                # a few % of items are (almost) never seen in train
+    cdf = np.cumsum(w / w.sum())
+    perm = rng.permutation(ni)                      # popularity is not aligned with the item id
+    users = np.repeat(np.arange(nu, dtype=np.int64), (deg * 1.15 + 2).astype(np.int64))
+    items = perm[np.minimum(np.searchsorted(cdf, rng.random(users.size)), ni - 1)]
+    key = np.unique(users * ni + items)             # de-duplicate (u,i); sorted by user then item
+    users, items = key // ni, key % ni
+    # trim every user back to its target degree (random subset), then split train/test
+    order = np.lexsort((rng.random(users.size), users))
+    users, items = users[order], items[order]
+    start = np.concatenate([[0], np.cumsum(np.bincount(users, minlength=nu))])
+    rank_in_user = np.arange(users.size) - start[users]
+    keep = rank_in_user < deg[users]
+    users, items, rank_in_user = users[keep], items[keep], rank_in_user[keep]
+    have = np.bincount(users, minlength=nu)
+    n_test = np.minimum(np.floor(have * test_frac).astype(np.int64), np.maximum(have - 1, 0))
+    is_test = rank_in_user < n_test[users]
+    tr_u, tr_i, te_u, te_i = users[~is_test], items[~is_test], users[is_test], items[is_test]
+    # users that ended up with no interaction at all get one random train item (sampler needs >= 1)
+    missing = np.setdiff1d(np.arange(nu), tr_u, assume_unique=False)
+    if missing.size:
+        tr_u = np.concatenate([tr_u, missing])
+        tr_i = np.concatenate([tr_i, rng.integers(0, ni, missing.size)])
+    shuf = rng.permutation(tr_u.size)               # file order is not sorted order
+    return dict(name=name, n_users=nu, m_items=ni, train_user=tr_u[shuf].astype(np.int64), train_item=tr_i[shuf].astype(np.int64),
+                test_user=te_u.astype(np.int64), test_item=te_i.astype(np.int64))
+
+
+def make_dataset(name='yelp2018', seed=2020, scale=1.0, config=None):
+    from .dataloader import InteractionDataset
+    g = make_graph(name, seed, scale)
+    return InteractionDataset(g['n_users'], g['m_items'], g['train_user'], g['train_item'], g['test_user'], g['test_item'],
+                              config=config, name=f"{name}-shape")
+
+
+def write_txt(graph, path):
+    """Write train.txt / test.txt in the reference's format (one 'uid items...' line per user)."""
+    import os
+    os.makedirs(path, exist_ok=True)
+    for split in ('train', 'test'):
+        u, i = graph[f'{split}_user'], graph[f'{split}_item']
+        order = np.lexsort((i, u))
+        u, i = u[order], i[order]
+        with open(os.path.join(path, f'{split}.txt'), 'w') as f:
+            if u.size:
+                cuts = np.flatnonzero(np.diff(u)) + 1
+                for uu, its in zip(u[np.concatenate([[0], cuts])], np.split(i, cuts)):
+                    f.write(f"{uu} {' '.join(map(str, its.tolist()))}\n")

@@ -1,0 +1,247 @@
+"""Loss wrapper, sampler glue, batching and metric helpers with the reference's names and
+semantics (code/utils.py), minus its three breakages: `timer` is complete and
+`minibatch` has the single-tensor case that Procedure.Test relies on.
+"""
+import ctypes
+import os
+from time import time
+
+import numpy as np
+import torch
+from torch import optim
+
+from . import _lib, world
+
+
+# ---------------------------------------------------------------------------- BPR loss / optimiser
+class _AdamStateView(optim.Adam):
+    """torch.optim.Adam whose state tensors ALIAS the engine's fused-Adam buffers, so that
+    optimizer.state_dict()/load_state_dict() keep the reference checkpoint layout
+    (code/main.py:56-87: 'optimizer_state') while the update itself runs inside the kernels."""
+
+    def __init__(self, model, lr):
+        super().__init__(model.parameters(), lr=lr)
+        self._model = model
+        self._bind()
+
+    def _bind(self):
+        m = self._model
+        eng, nu = m._engine, m.n_users
+        for p, sl in ((m.embedding_user.weight, slice(0, nu)), (m.embedding_item.weight, slice(nu, None))):
+            st = self.state[p]
+            st['step'] = torch.tensor(float(eng._host_step))
+            st['exp_avg'] = eng.M[sl]
+            st['exp_avg_sq'] = eng.V[sl]
+
+    def state_dict(self):
+        for st in self.state.values():
+            st['step'] = torch.tensor(float(self._model._engine._host_step))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        m = self._model
+        eng, nu = m._engine, m.n_users
+        step = 0
+        for p, sl in ((m.embedding_user.weight, slice(0, nu)), (m.embedding_item.weight, slice(nu, None))):
+            st = self.state.get(p, {})
+            if 'exp_avg' in st:
+                eng.M[sl].copy_(st['exp_avg'])
+                eng.V[sl].copy_(st['exp_avg_sq'])
+                step = int(float(st['step']))
+        eng.set_lr(self.param_groups[0]['lr'])
+        eng.set_adam_step(step)
+        self._bind()
+
+
+class BPRLoss:
+    """Same constructor and `stageOne(users, pos, neg) -> float` as the reference (code/utils.py:38-64).
+    With this package's LightGCN the step is the fused kernel sequence (no autograd graph, no
+    materialised gradients); with any other nn.Module it is the reference's generic recipe."""
+
+    def __init__(self, recmodel, config):
+        self.model = recmodel
+        self.weight_decay = config['decay']
+        self.lr = config['lr']
+        self.fused = hasattr(recmodel, 'fused_train_step')
+        if self.fused:
+            recmodel._engine.decay = float(self.weight_decay)
+            recmodel._engine.set_lr(self.lr)
+            self.opt = _AdamStateView(recmodel, self.lr)
+        else:
+            self.opt = optim.Adam(recmodel.parameters(), lr=self.lr)
+
+    def stageOne_async(self, users, pos, neg):
+        """Enqueue one step; returns the device tensor {bpr, reg, total, running} without synchronising."""
+        if not self.fused:
+            raise RuntimeError("stageOne_async needs lgcn_b200.LightGCN")
+        eng = self.model.fused_train_step(users, pos, neg, lr=self.opt.param_groups[0]['lr'])
+        return eng.loss_out
+
+    def stageOne(self, users, pos, neg):
+        if self.fused:
+            eng = self.model.fused_train_step(users, pos, neg, lr=self.opt.param_groups[0]['lr'])
+            return float(eng.loss_to_host()[2])          # loss.cpu().item() (code/utils.py:64)
+        loss, reg_loss = self.model.bpr_loss(users, pos, neg)
+        loss = loss + reg_loss * self.weight_decay
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return loss.cpu().item()
+
+
+# ---------------------------------------------------------------------------- sampling
+sample_ext = True     # the C sampler ships inside liblgcn_b200.so
+
+
+def sampler_seed(seed):
+    _lib.load().lgcn_sampler_seed(ctypes.c_uint32(int(seed) & 0xffffffff))
+
+
+def UniformSample_original(dataset, neg_ratio=1):
+    """One epoch of (user, pos, neg) triples, int32 [n_users * (trainDataSize // n_users), 2+neg_ratio],
+    with the draw order of the reference's C++ sampler (code/sources/sampling.cpp:27-56)."""
+    if hasattr(dataset, 'allPos_csr'):
+        indptr, items = dataset.allPos_csr()
+    else:
+        ap = dataset.allPos
+        lens = np.fromiter((len(a) for a in ap), dtype=np.int64, count=len(ap))
+        indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        items = np.concatenate([np.asarray(a, dtype=np.int32) for a in ap]) if len(ap) else np.zeros(0, np.int32)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    items = np.ascontiguousarray(items, dtype=np.int32)
+    per_user = dataset.trainDataSize // dataset.n_users
+    out = np.empty((dataset.n_users * per_user, 2 + neg_ratio), dtype=np.int32)
+    rows = _lib.load().lgcn_sample_negative(dataset.n_users, dataset.m_items, dataset.trainDataSize,
+                                           indptr.ctypes.data_as(ctypes.c_void_p), items.ctypes.data_as(ctypes.c_void_p),
+                                           neg_ratio, out.ctypes.data_as(ctypes.c_void_p))
+    if rows < 0:
+        raise RuntimeError(_lib.load().lgcn_last_error().decode())
+    return out
+
+
+def UniformSample_original_python(dataset):
+    """The reference's numpy fallback (code/utils.py:84-110), kept for comparisons."""
+    user_num = dataset.trainDataSize
+    users = np.random.randint(0, dataset.n_users, user_num)
+    allPos = dataset.allPos
+    S = []
+    for user in users:
+        posForUser = allPos[user]
+        if len(posForUser) == 0:
+            continue
+        positem = np.random.choice(posForUser)
+        while True:
+            negitem = np.random.randint(0, dataset.m_items)
+            if negitem not in posForUser:
+                break
+        S.append([user, positem, negitem])
+    return np.array(S)
+
+
+# ---------------------------------------------------------------------------- helpers
+def set_seed(seed):
+    np.random.seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
+    torch.manual_seed(seed)
+
+
+def getFileName():
+    if world.model_name == 'mf':
+        file = f"mf-{world.dataset}-{world.config['latent_dim_rec']}.pth.tar"
+    else:
+        file = f"lgn-{world.dataset}-{world.config['lightGCN_n_layers']}-{world.config['latent_dim_rec']}.pth.tar"
+    return os.path.join(world.PATH, file)
+
+
+def minibatch(*tensors, **kwargs):
+    batch_size = kwargs.get('batch_size', world.config['bpr_batch_size'])
+    if len(tensors) == 1:
+        tensor = tensors[0]
+        for i in range(0, len(tensor), batch_size):
+            yield tensor[i:i + batch_size]
+    else:
+        for i in range(0, len(tensors[0]), batch_size):
+            yield tuple(x[i:i + batch_size] for x in tensors)
+
+
+def shuffle(*arrays, **kwargs):
+    """Same permutation stream as the reference: np.random.shuffle of arange(n) (code/utils.py:142-151)."""
+    require_indices = kwargs.get('indices', False)
+    if len(set(len(x) for x in arrays)) != 1:
+        raise ValueError("All inputs to shuffle must have the same length.")
+    shuffle_indices = np.arange(len(arrays[0]))
+    np.random.shuffle(shuffle_indices)
+    if len(arrays) == 1:
+        result = arrays[0][shuffle_indices]
+    else:
+        result = tuple(x[shuffle_indices] for x in arrays)
+    return (result, shuffle_indices) if require_indices else result
+
+
+class timer:
+    """Named accumulating timers: `with timer(name="Sample"): ...`; timer.dict() -> "|Sample:0.21|"."""
+    TAPE = [-1]
+    NAMED_TAPE = {}
+
+    @staticmethod
+    def get():
+        return timer.TAPE.pop() if len(timer.TAPE) > 1 else -1
+
+    @staticmethod
+    def dict(select_keys=None):
+        keys = timer.NAMED_TAPE.keys() if select_keys is None else select_keys
+        return "|" + "|".join(f"{k}:{timer.NAMED_TAPE[k]:.2f}" for k in keys) + "|" if len(timer.NAMED_TAPE) else "|"
+
+    @staticmethod
+    def zero(select_keys=None):
+        keys = list(timer.NAMED_TAPE.keys()) if select_keys is None else select_keys
+        for k in keys:
+            timer.NAMED_TAPE[k] = 0
+
+    def __init__(self, tape=None, **kwargs):
+        self.named = kwargs.get('name')
+        if self.named:
+            timer.NAMED_TAPE.setdefault(self.named, 0.)
+            self.tape = None
+        else:
+            self.tape = tape or timer.TAPE
+
+    def __enter__(self):
+        self.start = time()
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        if self.named:
+            timer.NAMED_TAPE[self.named] += time() - self.start
+        else:
+            self.tape.append(time() - self.start)
+
+
+# ---------------------------------------------------------------------------- metrics (host, numpy)
+def RecallPrecision_ATk(test_data, r, k):
+    right_pred = r[:, :k].sum(1)
+    recall_n = np.array([len(test_data[i]) for i in range(len(test_data))])
+    return {'recall': np.sum(right_pred / recall_n), 'precision': np.sum(right_pred) / k}
+
+
+def NDCGatK_r(test_data, r, k):
+    assert len(r) == len(test_data)
+    pred_data = r[:, :k]
+    test_matrix = np.zeros((len(pred_data), k))
+    for i, items in enumerate(test_data):
+        test_matrix[i, :min(k, len(items))] = 1
+    disc = 1. / np.log2(np.arange(2, k + 2))
+    idcg = np.sum(test_matrix * disc, axis=1)
+    dcg = np.sum(pred_data * disc, axis=1)
+    idcg[idcg == 0.] = 1.
+    return np.sum(dcg / idcg)
+
+
+def getLabel(groundTruth, predictTopK):
+    if not isinstance(groundTruth, (list, set, tuple, np.ndarray)):
+        groundTruth = [groundTruth]
+    gt = set(int(x) for x in groundTruth)
+    return np.array([1.0 if int(x) in gt else 0.0 for x in predictTopK], dtype=np.float32)

@@ -1,0 +1,119 @@
+"""Run-time configuration surface, mirroring the reference's global `world` module.
+
+The reference evaluates argparse at import time (code/world.py:26, code/parse.py:16-114) and every
+module does `import world`.  Here the same names exist (`config`, `topks`, `device`, `seed`, ...),
+with the reference's defaults, but nothing touches sys.argv on import: call `configure(...)` or
+`from_args(argv)` explicitly.  The hot path only reads config['latent_dim_rec'|'lightGCN_n_layers'|
+'bpr_batch_size'|'test_u_batch_size'|'decay'|'lr'], `topks` and `device`.
+"""
+import argparse
+import ast
+import multiprocessing
+import os
+
+import torch
+
+try:
+    CORES = multiprocessing.cpu_count() // 2
+except Exception:  # pragma: no cover
+    CORES = 4
+
+# defaults = code/parse.py:19-112
+config = {
+    'checkpoint_dir': './checkpoints',
+    'dataset': 'gowalla',
+    'lr': 0.001,
+    'decay': 1e-4,
+    'lightGCN_n_layers': 3,
+    'latent_dim_rec': 64,
+    'bpr_batch_size': 2048,
+    'test_u_batch_size': 100,
+    'dropout': 0,
+    'keep_prob': 0.6,
+    'A_split': False,
+    'A_n_fold': 100,
+    'epochs': 1000,
+    'multicore': 0,
+    'pretrain': 0,
+    'seed': 2020,
+    'model': 'lgn',
+    'use_scheduler': False,
+    'sched_gamma': 0.5,
+    'sched_milestones': [120, 240, 360, 480],
+    'use_pop_gate': False,
+    'use_item_item': False,
+    'i2i_path': None,
+    'i2i_alpha': 0.0,
+    # extras understood by this implementation only (all optional)
+    'deterministic': False,     # K2 owner-computes reduction instead of float atomics
+    'cuda_graph': True,         # capture the fused training step in a CUDA graph
+    'spmm_seg_len': 512,        # degree-binning threshold of K1
+}
+
+seed = 2020
+dataset = 'gowalla'
+comment = 'lgn'
+tensorboard = 0
+LOAD = 0
+model_name = 'lgn'
+TRAIN_epochs = 1000
+topks = [20]
+PATH = './checkpoints'
+ROOT_PATH = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA_PATH = os.path.join(ROOT_PATH, 'data')
+# The reference picks cuda when available (code/world.py:109).  This build has no CPU path: host-only
+# utilities still import, device work raises.
+device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+
+
+def cprint(*args, **kwargs):
+    print(*args, **kwargs)
+
+
+def configure(**overrides):
+    """Update `config` (and the mirrored module globals) in place."""
+    global seed, dataset, topks, model_name, TRAIN_epochs, PATH, tensorboard, comment, device
+    for k, v in overrides.items():
+        if k == 'topks':
+            topks = list(ast.literal_eval(v)) if isinstance(v, str) else list(v)
+        elif k == 'device':
+            device = torch.device(v)
+        elif k == 'tensorboard':
+            tensorboard = int(v)
+        elif k == 'comment':
+            comment = v
+        else:
+            config[k] = v
+    seed = config['seed']
+    dataset = config['dataset']
+    model_name = config['model']
+    TRAIN_epochs = config['epochs']
+    PATH = config['checkpoint_dir']
+    return config
+
+
+def from_args(argv=None):
+    """Same flags as the reference's parse.py (subset used by the hot path + driver)."""
+    p = argparse.ArgumentParser(description="LightGCN on B200")
+    p.add_argument('--bpr_batch', type=int, default=2048)
+    p.add_argument('--recdim', type=int, default=64)
+    p.add_argument('--layer', type=int, default=3)
+    p.add_argument('--lr', type=float, default=0.001)
+    p.add_argument('--decay', type=float, default=1e-4)
+    p.add_argument('--epochs', type=int, default=1000)
+    p.add_argument('--testbatch', type=int, default=100)
+    p.add_argument('--dataset', type=str, default='gowalla')
+    p.add_argument('--data_path', type=str, default=None)
+    p.add_argument('--checkpoint_dir', type=str, default='./checkpoints')
+    p.add_argument('--topks', type=str, default='[20]')
+    p.add_argument('--seed', type=int, default=2020)
+    p.add_argument('--model', type=str, default='lgn')
+    p.add_argument('--multicore', type=int, default=0)
+    p.add_argument('--deterministic', action='store_true')
+    p.add_argument('--save_every', type=int, default=10)
+    a = p.parse_args(argv)
+    configure(bpr_batch_size=a.bpr_batch, latent_dim_rec=a.recdim, lightGCN_n_layers=a.layer, lr=a.lr,
+              decay=a.decay, epochs=a.epochs, test_u_batch_size=a.testbatch, dataset=a.dataset,
+              checkpoint_dir=a.checkpoint_dir, topks=a.topks, seed=a.seed, model=a.model,
+              multicore=a.multicore, deterministic=a.deterministic)
+    return a

@@ -1,0 +1,210 @@
+/*
+ * lgcn_b200.h — C ABI of the B200-native LightGCN hot path (liblgcn_b200.so).
+ *
+ * The reference (saamiya225/Graph-and-sequential-recommendation-systems, LightGCN_work/code) has no
+ * C/FFI operator interface on this path: everything below replaces *library call sites* inside its
+ * Python files.  Each entry point cites the reference lines it stands in for.  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED DEVICE pointer unless the name ends in `_host`;
+ *   - nothing here allocates, frees or synchronises: scratch space is a caller-provided workspace
+ *     whose size comes from the matching *_workspace_bytes() query (host-side arithmetic only);
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *   - return value: 0 = enqueued, non-zero = rejected (bad argument / launch error); the message is
+ *     available from lgcn_last_error() on the calling thread;
+ *   - dense tables are row-major float32 with row stride d; node ids are users 0..n_users-1 followed
+ *     by items n_users..N-1 (code/model.py:209, code/dataloader.py:223-227);
+ *   - adjacency is CSR with int32 indptr/indices and float32 values.
+ */
+#ifndef LGCN_B200_H
+#define LGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGCN_ABI_VERSION 1
+#define LGCN_MAX_Z 8          /* max number of own-row addends in the SpMM epilogue (layers L <= 8) */
+#define LGCN_MAX_TOPK 128     /* max k of the fused score/top-k kernel */
+
+typedef void* lgcn_stream_t;  /* cudaStream_t */
+
+int lgcn_abi_version(void);
+const char* lgcn_last_error(void);
+/* Device properties the host side sizes grids with: out[0]=SM count, out[1]=max dyn smem per block,
+ * out[2]=compute capability major*10+minor.  Host-side query, no stream. */
+int lgcn_device_info(int32_t* out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  device CSR builder + degree normaliser
+ * replaces  code/dataloader.py:133-142 (UserItemNet, users_D/items_D) and :223-234
+ *           (dok/lil block assignment -> CSR, rowsum, power(-0.5), D.A.D)
+ *
+ * in : train_user/train_item  int64[E]   (code/dataloader.py:121-123 dtype)
+ * out: indptr int32[N+1], indices int32[<=2E] (sorted within a row), vals float32[<=2E],
+ *      deg float32[N] (weighted degree = row sum, duplicates counted, dataloader.py:133-136),
+ *      dinv float32[N] (deg^-1/2, 0 for deg 0), nnz_out int64[1] (number of stored entries)
+ * Duplicate (u,i) pairs are summed like scipy's csr_matrix((ones,(u,i))).
+ * -------------------------------------------------------------------------------------------*/
+size_t lgcn_csr_build_workspace_bytes(int64_t E, int32_t n_users, int32_t m_items);
+int lgcn_csr_build(const int64_t* train_user, const int64_t* train_item, int64_t E,
+                   int32_t n_users, int32_t m_items,
+                   int32_t* indptr, int32_t* indices, float* vals, float* deg, float* dinv,
+                   int64_t* nnz_out, int32_t* status_out /* int32[1]: !=0 -> id out of range */,
+                   void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+
+/* Row-major sorted COO (torch coalesced layout, code/dataloader.py:183-190,244) -> int32 CSR.
+ * rows/cols int64[nnz] sorted by (row,col); writes indptr int32[n_rows+1] and indices int32[nnz]. */
+int lgcn_coo_to_csr(const int64_t* rows, const int64_t* cols, int64_t nnz, int32_t n_rows,
+                    int32_t* indptr, int32_t* indices, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  CSR SpMM with fused epilogue
+ * replaces  torch.sparse.mm(g, x) per layer + stack/mean   code/model.py:216-222
+ *           and SparseAddmmBackward (loss.backward(), code/utils.py:61); A_hat is symmetric, so the
+ *           same CSR serves the transpose product.
+ *
+ *   acc[i,:] = sum_{j in row i} vals[j] * X[indices[j],:]            i in [0,n_rows)
+ *   g[i,:]   = alpha*acc[i,:] + beta * sum_{t<nz} Z_t[i,:]
+ *   plain    : Y[i,:] = g[i,:]
+ *   adam     : torch.optim.Adam update of P,M,V rows with gradient g (code/utils.py:51,62);
+ *              Y may be NULL.
+ * X is indexed by GLOBAL column id; Y, Z_t, P, M, V by LOCAL row i (callers pre-offset the
+ * pointers for a row partition).  d in {16,32,64,128,256}.
+ *
+ * Rows longer than seg_len are cut into segments by lgcn_spmm_plan_*; their partial sums meet in
+ * plan->partials and the last-arriving segment runs the epilogue (deterministic summation order).
+ * -------------------------------------------------------------------------------------------*/
+typedef struct {
+    int32_t seg_len;          /* rows with more non-zeros than this are segmented              */
+    int32_t n_long;           /* number of segmented rows                                       */
+    int32_t n_segs;           /* total number of segments                                       */
+    int32_t d_max;            /* partials holds n_segs*d_max floats                             */
+    const int32_t* segs;      /* int32[n_segs*8]: row,start,end,part,n_parts,slot_base,long_id,0 */
+    int32_t* counters;        /* int32[n_long], zero-initialised, self-resetting                */
+    float* partials;          /* float32[n_segs*d_max]                                          */
+    const int32_t* row_order; /* optional int32[n_rows] processing order (NULL = natural)       */
+} lgcn_spmm_plan_t;
+
+/* counts_out int32[2] = {n_long, n_segs} (device) */
+int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
+                         int32_t* counts_out, lgcn_stream_t stream);
+/* fills segs int32[n_segs*8]; cursor int32[2] must be zero on entry */
+int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
+                        int32_t* segs, int32_t* cursor, lgcn_stream_t stream);
+
+typedef struct {           /* device-resident Adam scalars, written by lgcn_adam_tick */
+    float step_size;       /* lr / (1 - beta1^t)                   */
+    float bc2_sqrt;        /* sqrt(1 - beta2^t)                    */
+    float beta1, beta2, eps;
+    float lr;
+    int32_t step;          /* t                                    */
+    int32_t pad;
+} lgcn_adam_scalars_t;
+
+int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
+                  int32_t n_rows, int32_t d, const float* X, float* Y,
+                  float alpha, float beta, const float* const* z_host, int32_t nz,
+                  const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream);
+
+int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
+                       int32_t n_rows, int32_t d, const float* X, float* Y /* may be NULL */,
+                       float alpha, float beta, const float* const* z_host, int32_t nz,
+                       float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
+                       const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Adam (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad)
+ * replaces  self.opt.step()  code/utils.py:51,62
+ * lgcn_adam_tick: step += 1 and refresh the bias-correction scalars on the device (double
+ * arithmetic, like torch's Python-side scalars).  lgcn_adam_f32: dense update of n floats.
+ * -------------------------------------------------------------------------------------------*/
+int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, float lr, float beta1, float beta2, float eps,
+                   int32_t step, lgcn_stream_t stream);
+int lgcn_adam_tick(lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream);
+int lgcn_adam_f32(float* P, float* M, float* V, const float* G, int64_t n,
+                  const lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  fused BPR forward + closed-form gradient
+ * replaces  getEmbedding gathers + bpr_loss arithmetic + their autograd backward
+ *           code/model.py:125-134, :162-173 ; code/utils.py:55-61
+ *
+ * out  float32[N,d] propagated embeddings (users then items)
+ * users/pos/neg int64[>= offset+B] (item ids are 0-based item indices, NOT offset by n_users)
+ * batch_ctl_dev int32[4] (device) = {offset, B, total, B_global}: the batch is entries [offset, offset+B)
+ *      of users/pos/neg, B <= B_cap.  Keeping it on the device lets ONE CUDA graph serve every batch
+ *      of an epoch (lgcn_batch_advance moves the window: offset += B; B = min(B_cap, total-offset)).
+ * inv_norm = 1/B_global (the means in code/model.py:170,173); pass <= 0 to take it from the batch
+ *      descriptor instead: 1/ctl[3] when ctl[3] > 0 (global batch of a sharded step), else 1/B
+ * loss_out float32[4]: {bpr = mean softplus(neg-pos), reg = 0.5*sum(|u|^2+|p|^2+|n|^2)/B,
+ *                       total = bpr + decay*reg, running sum of total (host resets it)}
+ * G float32[N,d]: += c_bpr*d(bpr)/d(out) + c_reg*d(reg)/d(out)   (scatter-add; G may be NULL for a
+ *      forward-only call).  own_begin/own_end restrict the scatter to rows in [own_begin,own_end)
+ *      (row partition); pass 0,N for all rows.
+ * deterministic != 0: rows are reduced in a fixed order (no float atomics).
+ * workspace must be zero-filled once after allocation (it holds a self-resetting arrival counter).
+ * -------------------------------------------------------------------------------------------*/
+size_t lgcn_bpr_workspace_bytes(int32_t B_cap, int32_t d);
+int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                     int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items,
+                     int32_t d, float inv_norm, float decay, float c_bpr, float c_reg,
+                     float* loss_out, float* G, int32_t own_begin, int32_t own_end,
+                     int32_t deterministic, void* workspace, size_t workspace_bytes,
+                     lgcn_stream_t stream);
+/* zero the rows of G a batch touched (cheaper than a full memset when B << N) */
+int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                        int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t d,
+                        lgcn_stream_t stream);
+int lgcn_batch_advance(int32_t* batch_ctl_dev, int32_t B_cap, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  user x item scores fused with the train-item mask and per-row top-k
+ * replaces  getUsersRating matmul (code/model.py:114-123), the -(1<<10) mask
+ *           (code/Procedure.py:177-181) and torch.topk (code/Procedure.py:183)
+ *
+ * users_emb float32[n_users,d], items_emb float32[m_items,d]; users int64[Bt] (NULL = 0..Bt-1)
+ * score(b,i) = fp32 FMA chain over k = 0..d-1 starting from 0 (exactly reproducible on a CPU)
+ * masked cells (i in the CSR row of user b; stored column = mask_col_offset + i) score -1024
+ * order: score descending, ties -> lowest item id first
+ * idx_out int64[Bt,k], val_out float32[Bt,k]
+ * -------------------------------------------------------------------------------------------*/
+size_t lgcn_score_topk_workspace_bytes(int32_t Bt, int32_t m_items, int32_t k);
+int lgcn_score_topk(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
+                    int32_t m_items, int32_t d, const int32_t* mask_indptr, const int32_t* mask_indices,
+                    int32_t mask_col_offset, int32_t k, int64_t* idx_out, float* val_out,
+                    void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+/* dense scores float32[Bt,m_items] for the unfused API (getUsersRating returns the matrix) */
+int lgcn_score_dense(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
+                     int32_t m_items, int32_t d, float* scores, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-device ranking metrics (precision/recall/NDCG sums over users)
+ * replaces  test_one_batch/getLabel/RecallPrecision_ATk/NDCGatK_r
+ *           code/Procedure.py:89-121 ; code/utils.py:173-200,212-217
+ * topk_idx int64[Bt,k_max]; test CSR over the same Bt rows (sorted item ids); ks int32[nk];
+ * sums_out float64[3*nk] += {precision, recall, ndcg} summed over rows.
+ * -------------------------------------------------------------------------------------------*/
+int lgcn_rank_metrics(const int64_t* topk_idx, int32_t Bt, int32_t k_max,
+                      const int32_t* test_indptr, const int32_t* test_indices,
+                      const int32_t* ks, int32_t nk, double* sums_out, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side negative sampler with the semantics of code/sources/sampling.cpp:27-56 (per user
+ * train_num/user_num triples, uniform positive, rejection-sampled negative, glibc rand()).
+ * All pointers are HOST pointers.  allpos CSR: indptr int64[user_num+1], items int32.
+ * out int32[user_num*(train_num/user_num)*(2+neg_num)].  Returns rows written or <0.
+ * -------------------------------------------------------------------------------------------*/
+void lgcn_sampler_seed(uint32_t seed);
+int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_num,
+                             const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
+                             int32_t neg_num, int32_t* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCN_B200_H */
