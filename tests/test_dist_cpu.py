@@ -1,0 +1,82 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path (row partition bounds,
+uneven in-place all-gather, batch sharding).  The SpMM itself is played by the numpy oracle — each
+output row is produced by exactly one rank, so the partitioned result must equal the unpartitioned one
+bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import lgcn_b200 as lg
+        from oracle import lightgcn_oracle as orc
+        g = lg.synth.make_graph('tiny', seed=1)
+        nu, ni = g['n_users'], g['m_items']
+        indptr, indices, vals, _, _ = orc.build_norm_adj(g['train_user'], g['train_item'], nu, ni)
+        N, d, L = nu + ni, 16, 3
+        rng = np.random.default_rng(0)
+        E0 = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+        bounds = lg.engine.balanced_row_bounds(torch.from_numpy(indptr), world)
+        assert bounds[0] == 0 and bounds[-1] == N and all(b0 <= b1 for b0, b1 in zip(bounds, bounds[1:]))
+        nnz_parts = [int(indptr[b1] - indptr[b0]) for b0, b1 in zip(bounds, bounds[1:])]
+        assert max(nnz_parts) - min(nnz_parts) <= 2 * int(np.diff(indptr).max())
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        lp = indptr[r0:r1 + 1] - indptr[r0]
+        li, lv = indices[indptr[r0]:indptr[r1]], vals[indptr[r0]:indptr[r1]]
+        # partitioned propagation: local rows, then the uneven all-gather
+        x = torch.from_numpy(E0.copy())
+        acc = x.clone()
+        for _ in range(L):
+            y = torch.zeros_like(x)
+            y[r0:r1] = torch.from_numpy(orc.spmm(lp, li, lv, x.numpy()))
+            lg.engine.allgather_rows(y, bounds)
+            acc += y
+            x = y
+        full = E0.copy(); acc_full = full.copy()
+        for _ in range(L):
+            full = orc.spmm(indptr, indices, vals, full); acc_full += full
+        ok_prop = np.array_equal(acc.numpy(), acc_full)
+        # batch sharding covers the batch exactly once
+        lo, hi = lg.engine.shard_batch(2049, rank, world)
+        cover = torch.zeros(2049); cover[lo:hi] = 1
+        dist.all_reduce(cover)
+        ok_shard = bool((cover == 1).all())
+        # data-parallel gradient: sum of per-shard closed-form gradients == full-batch gradient
+        users = rng.integers(0, nu, 64); pos = rng.integers(0, ni, 64); neg = rng.integers(0, ni, 64)
+        out = (acc_full / (L + 1)).astype(np.float64)
+        _, _, Gb, Gr = orc.bpr_loss(out, users, pos, neg, nu)
+        lo, hi = lg.engine.shard_batch(64, rank, world)
+        _, _, Gb_l, Gr_l = orc.bpr_loss(out, users[lo:hi], pos[lo:hi], neg[lo:hi], nu)
+        Gl = torch.from_numpy((Gb_l + 1e-4 * Gr_l) * (hi - lo) / 64.0)     # local mean -> global mean
+        dist.all_reduce(Gl)
+        ok_dp = np.allclose(Gl.numpy(), Gb + 1e-4 * Gr, rtol=1e-12, atol=1e-15)
+        q.put((rank, ok_prop, ok_shard, ok_dp))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_rowpart_and_dp_host_logic_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert res == [(0, True, True, True), (1, True, True, True)]

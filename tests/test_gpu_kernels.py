@@ -1,0 +1,376 @@
+"""GPU: every kernel of liblgcn_b200.so against the oracle, called through the C ABI wrappers.
+
+Tolerances: integer/index outputs bit-exact; fp32 outputs within 1e-5 norm-wise relative
+(rel_err = max |a-b| / (|b| + rms(b))) unless stated otherwise.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def lg():
+    import lgcn_b200
+    assert lgcn_b200.ops.device_info()['cc'] >= 100, "these kernels are built for sm_100a"
+    return lgcn_b200
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import lightgcn_oracle
+    return lightgcn_oracle
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build(lg, tu, ti, nu, ni, seg_len=512):
+    return lg.ops.csr_build(dev(np.asarray(tu, np.int64)), dev(np.asarray(ti, np.int64)), nu, ni, seg_len=seg_len)
+
+
+def random_edges(rng, nu, ni, E, dup=0):
+    u = rng.integers(0, nu, E); i = rng.integers(0, ni, E)
+    if dup:
+        u = np.concatenate([u, u[:dup]]); i = np.concatenate([i, i[:dup]])
+    return u.astype(np.int64), i.astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------ K4
+def test_csr_build_matches_reference_output(lg, orc, golden):
+    nu, ni = int(golden['n_users']), int(golden['m_items'])
+    g = build(lg, golden['train_user'], golden['train_item'], nu, ni)
+    N = nu + ni
+    ref_indptr = np.concatenate([[0], np.cumsum(np.bincount(golden['adj_row'], minlength=N))])
+    assert np.array_equal(g.indptr.cpu().numpy(), ref_indptr)                 # bit-exact vs the reference
+    assert np.array_equal(g.indices.cpu().numpy(), golden['adj_col'])
+    assert np.max(np.abs(g.vals.cpu().numpy() - golden['adj_val']) / golden['adj_val']) < 3e-7
+    o_indptr, o_indices, o_vals, o_deg, o_dinv = orc.build_norm_adj(golden['train_user'], golden['train_item'], nu, ni)
+    assert np.array_equal(g.vals.cpu().numpy(), o_vals)                       # bit-exact vs the oracle's rounding rule
+    assert np.array_equal(g.deg.cpu().numpy(), o_deg) and np.array_equal(g.dinv.cpu().numpy(), o_dinv)
+
+
+@pytest.mark.parametrize("nu,ni,E,dup", [(1, 1, 1, 0), (5, 7, 0, 0), (50, 30, 400, 40), (3000, 2000, 60000, 500), (70000, 300, 5000, 0)])
+def test_csr_build_random(lg, orc, nu, ni, E, dup):
+    rng = np.random.default_rng(nu * 7 + E)
+    tu, ti = random_edges(rng, nu, ni, E, dup)
+    g = build(lg, tu, ti, nu, ni)
+    o_indptr, o_indices, o_vals, o_deg, o_dinv = orc.build_norm_adj(tu, ti, nu, ni)
+    assert g.nnz == o_indices.size
+    assert np.array_equal(g.indptr.cpu().numpy(), o_indptr)
+    assert np.array_equal(g.indices.cpu().numpy(), o_indices)
+    assert np.array_equal(g.deg.cpu().numpy(), o_deg)
+    assert np.array_equal(g.vals.cpu().numpy(), o_vals)
+
+
+def test_csr_build_rejects_out_of_range_ids(lg):
+    with pytest.raises(RuntimeError):
+        build(lg, [0, 5], [0, 1], 3, 4)
+
+
+def test_csr_build_full_size_properties(lg, orc):
+    gr = lg.synth.make_graph('yelp2018')
+    nu, ni = gr['n_users'], gr['m_items']
+    g = build(lg, gr['train_user'], gr['train_item'], nu, ni)
+    indptr, indices = g.indptr.cpu().numpy().astype(np.int64), g.indices.cpu().numpy().astype(np.int64)
+    rows = np.repeat(np.arange(nu + ni), np.diff(indptr))
+    key = rows * (nu + ni) + indices
+    assert np.all(np.diff(key) > 0)                                           # sorted, duplicate-free
+    assert np.array_equal(np.sort(indices * (nu + ni) + rows), key)           # structurally symmetric
+    assert g.nnz == 2 * np.unique(gr['train_user'] * ni + gr['train_item']).size
+    o = orc.build_norm_adj(gr['train_user'], gr['train_item'], nu, ni)
+    assert np.array_equal(indptr, o[0]) and np.array_equal(indices, o[1]) and np.array_equal(g.vals.cpu().numpy(), o[2])
+    # bipartite: user rows only reference item columns and vice versa
+    assert indices[:indptr[nu]].min() >= nu and indices[indptr[nu]:].max() < nu
+
+
+def test_coo_to_csr(lg, orc):
+    g = load_golden('tiny')
+    N = int(g['n_users']) + int(g['m_items'])
+    c = lg.ops.coo_to_csr(dev(g['adj_row'].astype(np.int64)), dev(g['adj_col'].astype(np.int64)), dev(g['adj_val']), N, N)
+    ref_indptr = np.concatenate([[0], np.cumsum(np.bincount(g['adj_row'], minlength=N))])
+    assert np.array_equal(c.indptr.cpu().numpy(), ref_indptr) and np.array_equal(c.indices.cpu().numpy(), g['adj_col'])
+
+
+# ------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("seg_len", [512, 8])
+def test_spmm_vs_oracle(lg, orc, d, seg_len):
+    rng = np.random.default_rng(d + seg_len)
+    nu, ni = 700, 450
+    tu, ti = random_edges(rng, nu, ni, 9000, 100)
+    tu[:600] = 3; ti[:600] = rng.permutation(ni)[:600] if ni >= 600 else rng.integers(0, ni, 600)   # a hub row
+    g = build(lg, tu, ti, nu, ni, seg_len=seg_len)
+    if seg_len == 8:
+        assert g.n_segs > 0 and g.n_long > 0
+    N = nu + ni
+    X = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+    Z1 = rng.normal(0, 0.1, (N, d)).astype(np.float32); Z2 = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+    indptr, indices, vals = (t.cpu().numpy() for t in (g.indptr, g.indices, g.vals))
+    AX = orc.spmm_scipy(indptr, indices, vals.astype(np.float64), X.astype(np.float64))
+    Y = torch.empty((N, d), device='cuda')
+    lg.ops.spmm(g, dev(X), Y)
+    assert rel_err(Y.cpu().numpy(), AX) < TOL
+    lg.ops.spmm(g, dev(X), Y, alpha=0.25, beta=0.5, zs=[dev(Z1), dev(Z2)])
+    assert rel_err(Y.cpu().numpy(), 0.25 * AX + 0.5 * (Z1.astype(np.float64) + Z2)) < TOL
+    # second launch on the same plan: arrival counters must have reset themselves
+    lg.ops.spmm(g, dev(X), Y)
+    assert rel_err(Y.cpu().numpy(), AX) < TOL
+
+
+def test_spmm_empty_rows_and_zero_degree_nodes(lg, orc):
+    nu, ni, d = 40, 30, 64
+    tu = np.array([0, 0, 5], np.int64); ti = np.array([1, 2, 1], np.int64)
+    g = build(lg, tu, ti, nu, ni)
+    X = np.random.default_rng(0).normal(0, 1, (nu + ni, d)).astype(np.float32)
+    Y = torch.full((nu + ni, d), 7.0, device='cuda')
+    lg.ops.spmm(g, dev(X), Y)
+    indptr, indices, vals = (t.cpu().numpy() for t in (g.indptr, g.indices, g.vals))
+    exp = orc.spmm(indptr, indices, vals.astype(np.float64), X.astype(np.float64))
+    assert rel_err(Y.cpu().numpy(), exp) < TOL
+    assert float(Y[10].abs().max()) == 0.0                # empty row is written (zeros), not skipped
+
+
+def test_spmm_full_size_properties(lg):
+    """amazon-book shape (hub user ~10 k): linearity and symmetry <y, A x> = <A y, x>."""
+    gr = lg.synth.make_graph('amazon-book')
+    g = build(lg, gr['train_user'], gr['train_item'], gr['n_users'], gr['m_items'])
+    assert g.n_long > 0
+    N, d = g.n_rows, 64
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn((N, d), device='cuda', generator=gen); y = torch.randn((N, d), device='cuda', generator=gen)
+    Ax, Ay, Axy = (torch.empty_like(x) for _ in range(3))
+    lg.ops.spmm(g, x, Ax); lg.ops.spmm(g, y, Ay); lg.ops.spmm(g, (x + y).contiguous(), Axy)
+    assert rel_err(Axy.cpu().numpy(), (Ax + Ay).cpu().numpy()) < TOL
+    lhs = (y.double() * Ax.double()).sum().item(); rhs = (Ay.double() * x.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * (abs(lhs) + (y.double().norm() * Ax.double().norm()).item() * 1e-2)
+    # against torch's own CSR SpMM (cuSPARSE) on the same matrix
+    ref = torch.sparse.mm(g.to_torch_sparse_csr(), x)
+    assert rel_err(Ax.cpu().numpy(), ref.cpu().numpy()) < TOL
+    # row order hint only changes scheduling
+    order = torch.argsort(torch.diff(g.indptr), descending=True).to(torch.int32)
+    g.set_row_order(order)
+    Ax2 = torch.empty_like(x); lg.ops.spmm(g, x, Ax2)
+    g.set_row_order(None)
+    assert torch.equal(Ax, Ax2)
+
+
+# ------------------------------------------------------------------------------------ Adam
+def test_adam_matches_torch_and_oracle(lg, orc):
+    rng = np.random.default_rng(0)
+    n, d = 500, 64
+    p0 = rng.normal(0, 0.1, (n, d)).astype(np.float32)
+    P = dev(p0); M = torch.zeros_like(P); V = torch.zeros_like(P)
+    tp = torch.nn.Parameter(dev(p0).clone()); opt = torch.optim.Adam([tp], lr=1e-3)
+    sc = lg.ops.adam_scalars(P.device, 1e-3)
+    p64, m64, v64 = p0.astype(np.float64), np.zeros((n, d)), np.zeros((n, d))
+    for t in range(1, 6):
+        gnp = rng.normal(0, 1e-3, (n, d)).astype(np.float32); gnp[::7] = 0
+        G = dev(gnp)
+        lg.ops.adam_tick(sc); lg.ops.adam(P, M, V, G, sc)
+        tp.grad = G.clone(); opt.step()
+        p64, m64, v64 = orc.adam_step(p64, m64, v64, gnp.astype(np.float64), t)
+    assert lg.ops.adam_step_count(sc) == 5
+    assert rel_err(P.cpu().numpy(), tp.detach().cpu().numpy()) < 2e-6
+    assert rel_err(P.cpu().numpy(), p64) < 2e-6
+    assert rel_err(M.cpu().numpy(), m64) < TOL and rel_err(V.cpu().numpy(), v64) < TOL
+
+
+def test_spmm_adam_epilogue_equals_spmm_then_adam(lg):
+    rng = np.random.default_rng(2)
+    nu, ni, d = 300, 200, 64
+    tu, ti = random_edges(rng, nu, ni, 4000)
+    g = build(lg, tu, ti, nu, ni, seg_len=16)
+    N = nu + ni
+    X = dev(rng.normal(0, 1e-3, (N, d)).astype(np.float32)); Z = dev(rng.normal(0, 1e-3, (N, d)).astype(np.float32))
+    p0 = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+    m0 = rng.normal(0, 1e-3, (N, d)).astype(np.float32); v0 = np.abs(rng.normal(0, 1e-6, (N, d))).astype(np.float32)
+    sc = lg.ops.adam_scalars(X.device, 1e-3, step=3)
+    Pa, Ma, Va = dev(p0), dev(m0), dev(v0)
+    Ygrad = torch.empty((N, d), device='cuda')
+    lg.ops.spmm_adam(g, X, Pa, Ma, Va, sc, alpha=1.0, beta=0.25, zs=[Z], Y=Ygrad)
+    Pb, Mb, Vb = dev(p0), dev(m0), dev(v0)
+    Gd = torch.empty((N, d), device='cuda')
+    lg.ops.spmm(g, X, Gd, 1.0, 0.25, [Z]); lg.ops.adam(Pb, Mb, Vb, Gd, sc)
+    assert torch.equal(Ygrad, Gd)
+    assert torch.equal(Pa, Pb) and torch.equal(Ma, Mb) and torch.equal(Va, Vb)
+
+
+# ------------------------------------------------------------------------------------ K2
+def _bpr_case(rng, nu, ni, d, B):
+    out = rng.normal(0, 0.3, (nu + ni, d)).astype(np.float32)
+    users = rng.integers(0, nu, B); pos = rng.integers(0, ni, B); neg = rng.integers(0, ni, B)
+    users[: B // 8] = users[0]; pos[: B // 8] = pos[1]          # heavy row collisions (atomics / owner-computes)
+    return out, users.astype(np.int64), pos.astype(np.int64), neg.astype(np.int64)
+
+
+@pytest.mark.parametrize("d", [16, 64, 256])
+@pytest.mark.parametrize("B", [1, 37, 2048])
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_bpr_vs_oracle(lg, orc, d, B, deterministic):
+    rng = np.random.default_rng(d * B + deterministic)
+    nu, ni, decay = 500, 800, 1e-4
+    out, users, pos, neg = _bpr_case(rng, nu, ni, d, B)
+    bpr, reg, Gb, Gr = orc.bpr_loss(out, users, pos, neg, nu)
+    B_cap = 2048
+    ws = lg.ops.bpr_workspace(B_cap, d, 'cuda')
+    pad = lambda a: dev(np.concatenate([np.zeros(5, np.int64), a, np.zeros(B_cap, np.int64)]))   # window at offset 5
+    ctl = torch.tensor([5, B, 5 + B, 0], dtype=torch.int32, device='cuda')
+    loss = torch.zeros(4, device='cuda'); G = torch.zeros((nu + ni, d), device='cuda')
+    o = dev(out)
+    for rep in range(2):                                       # 2nd call: arrival counter reset, running sum
+        G.zero_()
+        lg.ops.bpr_fwd_bwd(o, pad(users), pad(pos), pad(neg), B_cap, ctl, nu, ni, 0.0, decay, 1.0, decay, loss, G, ws,
+                           deterministic=deterministic)
+    l = loss.cpu().numpy()
+    assert abs(l[0] - bpr) < TOL * abs(bpr) and abs(l[1] - reg) < TOL * abs(reg)
+    assert abs(l[2] - (bpr + decay * reg)) < TOL * abs(bpr) and abs(l[3] - 2 * l[2]) < 1e-6
+    assert rel_err(G.cpu().numpy(), Gb + decay * Gr) < TOL
+    # separate coefficients (generic autograd path) and forward-only call
+    G.zero_()
+    lg.ops.bpr_fwd_bwd(o, pad(users), pad(pos), pad(neg), B_cap, ctl, nu, ni, 1.0 / B, 0.0, 0.5, 2.0, loss, G, ws,
+                       deterministic=deterministic)
+    assert rel_err(G.cpu().numpy(), 0.5 * Gb + 2.0 * Gr) < TOL
+    lg.ops.bpr_fwd_bwd(o, pad(users), pad(pos), pad(neg), B_cap, ctl, nu, ni, 1.0 / B, 0.0, 0.0, 0.0, loss, None, ws)
+    assert abs(loss[0].item() - bpr) < TOL * abs(bpr)
+    # clear_rows zeroes exactly the touched rows
+    lg.ops.bpr_clear_rows(G, pad(users), pad(pos), pad(neg), B_cap, ctl, nu)
+    assert float(G.abs().max()) == 0.0
+
+
+def test_bpr_owner_range_and_global_norm(lg, orc):
+    """Row-partition filter (own_begin/own_end) and data-parallel normalisation via ctl[3]."""
+    rng = np.random.default_rng(9)
+    nu, ni, d, B = 300, 400, 64, 512
+    out, users, pos, neg = _bpr_case(rng, nu, ni, d, B)
+    _, _, Gb, Gr = orc.bpr_loss(out, users, pos, neg, nu)
+    ws = lg.ops.bpr_workspace(B, d, 'cuda')
+    o = dev(out); loss = torch.zeros(4, device='cuda')
+    G = torch.zeros((nu + ni, d), device='cuda')
+    ctl = torch.tensor([0, B, B, 0], dtype=torch.int32, device='cuda')
+    lg.ops.bpr_fwd_bwd(o, dev(users), dev(pos), dev(neg), B, ctl, nu, ni, 0.0, 0.0, 1.0, 0.0, loss, G, ws, own=(100, 450))
+    exp = Gb.copy(); exp[:100] = 0; exp[450:] = 0
+    assert rel_err(G.cpu().numpy(), exp) < TOL
+    # two shards normalised by the global batch add up to the full-batch gradient
+    G.zero_(); h = B // 2
+    for lo in (0, h):
+        ctl = torch.tensor([lo, h, B, B], dtype=torch.int32, device='cuda')
+        lg.ops.bpr_fwd_bwd(o, dev(users), dev(pos), dev(neg), B, ctl, nu, ni, 0.0, 0.0, 1.0, 0.0, loss, G, ws)
+    assert rel_err(G.cpu().numpy(), Gb) < TOL
+
+
+def test_bpr_deterministic_mode_is_bitwise_repeatable(lg):
+    rng = np.random.default_rng(4)
+    nu, ni, d, B = 200, 100, 64, 2048                        # tiny item set -> many collisions
+    out, users, pos, neg = _bpr_case(rng, nu, ni, d, B)
+    ws = lg.ops.bpr_workspace(B, d, 'cuda'); o = dev(out); loss = torch.zeros(4, device='cuda')
+    ctl = torch.tensor([0, B, B, 0], dtype=torch.int32, device='cuda')
+    outs = []
+    for _ in range(3):
+        G = torch.zeros((nu + ni, d), device='cuda')
+        lg.ops.bpr_fwd_bwd(o, dev(users), dev(pos), dev(neg), B, ctl, nu, ni, 0.0, 1e-4, 1.0, 1e-4, loss, G, ws, deterministic=True)
+        outs.append((G.clone(), loss[:3].clone()))
+    assert all(torch.equal(outs[0][0], x[0]) and torch.equal(outs[0][1], x[1]) for x in outs[1:])
+
+
+def test_batch_advance(lg):
+    ctl = torch.tensor([0, 0, 5000, 0], dtype=torch.int32, device='cuda')
+    seen = []
+    for _ in range(4):
+        lg.ops.batch_advance(ctl, 2048); seen.append(ctl.cpu().tolist()[:2])
+    assert seen == [[0, 2048], [2048, 2048], [4096, 904], [5000, 0]]
+
+
+# ------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+def test_score_topk_bit_exact(lg, orc, d):
+    rng = np.random.default_rng(d)
+    nu, ni, k = 333, 1301, 20
+    tu, ti = random_edges(rng, nu, ni, 12000)
+    tu[:900] = 7; ti[:900] = rng.permutation(ni)[:900]         # user 7 has 900 train items
+    g = build(lg, tu, ti, nu, ni)
+    out = rng.normal(0, 0.1, (nu + ni, d)).astype(np.float32)
+    out[nu + 5] = out[nu + 9]                                   # exact score ties between items 5 and 9
+    indptr, indices = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+    o = dev(out)
+    for users in (None, rng.permutation(nu)[:150].astype(np.int64), np.array([7, 7, 3], np.int64)):
+        exp_idx, exp_val = orc.score_topk_exact(out[:nu], out[nu:], users, k, indptr, indices, nu)
+        idx, val = lg.ops.score_topk(o[:nu], o[nu:], None if users is None else dev(users), k, g.indptr, g.indices, nu)
+        assert np.array_equal(idx.cpu().numpy(), exp_idx)
+        assert np.array_equal(val.cpu().numpy(), exp_val)       # scores are bit-identical too
+    exp_idx, exp_val = orc.score_topk_exact(out[:nu], out[nu:], None, k)
+    idx, val = lg.ops.score_topk(o[:nu], o[nu:], None, k)       # no mask
+    assert np.array_equal(idx.cpu().numpy(), exp_idx) and np.array_equal(val.cpu().numpy(), exp_val)
+
+
+def test_score_topk_k_exceeds_unmasked_items(lg, orc):
+    g0 = load_golden('edge')
+    nu, ni = int(g0['n_users']), int(g0['m_items'])
+    g = build(lg, g0['train_user'], g0['train_item'], nu, ni)
+    out = g0['out_after']; o = dev(out)
+    for k in (1, 5, 20, 60):
+        exp_idx, exp_val = orc.score_topk_exact(out[:nu], out[nu:], None, k, g.indptr.cpu().numpy(), g.indices.cpu().numpy(), nu)
+        idx, val = lg.ops.score_topk(o[:nu], o[nu:], None, k, g.indptr, g.indices, nu)
+        assert np.array_equal(idx.cpu().numpy(), exp_idx) and np.array_equal(val.cpu().numpy(), exp_val)
+    assert (val[0] == -1024.0).sum().item() == 45              # user 0: 45 masked train items among all 60
+    with pytest.raises(RuntimeError):
+        lg.ops.score_topk(o[:nu], o[nu:], None, 61)
+
+
+def test_score_dense_bit_exact(lg, orc):
+    rng = np.random.default_rng(3)
+    nu, ni, d = 130, 700, 64
+    out = rng.normal(0, 0.1, (nu + ni, d)).astype(np.float32); o = dev(out)
+    users = rng.integers(0, nu, 100).astype(np.int64)
+    got = lg.ops.score_dense(o[:nu], o[nu:], dev(users))
+    assert np.array_equal(got.cpu().numpy(), orc.score_dense_exact(out[:nu], out[nu:], users))
+
+
+def test_score_topk_full_size_against_fp64(lg):
+    """yelp2018 shape, all users: against fp64 scores the indices may differ only at near-ties."""
+    gr = lg.synth.make_graph('yelp2018')
+    nu, ni, d, k = gr['n_users'], gr['m_items'], 64, 20
+    g = build(lg, gr['train_user'], gr['train_item'], nu, ni)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    out = (0.1 * torch.randn((nu + ni, d), device='cuda', generator=gen)).contiguous()
+    idx, val = lg.ops.score_topk(out[:nu], out[nu:], None, k, g.indptr, g.indices, nu)
+    assert bool((val[:, :-1] >= val[:, 1:]).all())             # sorted descending
+    sub = torch.arange(0, nu, 37, device='cuda')
+    S = out[:nu][sub].double() @ out[nu:].double().T
+    indptr = g.indptr.cpu().numpy(); indices = g.indices.cpu().numpy()
+    for b, u in enumerate(sub.cpu().tolist()):
+        S[b, torch.from_numpy(indices[indptr[u]:indptr[u + 1]] - nu).cuda().long()] = -1024.0
+    ref_val, ref_idx = torch.topk(S, k, dim=1)
+    got = idx[sub]
+    mism = got != ref_idx
+    if mism.any():
+        a = torch.gather(S, 1, got)[mism]; b = ref_val[mism]
+        assert bool(((a - b).abs() <= 1e-6 * b.abs() + 1e-9).all())
+    assert mism.float().mean().item() < 1e-3
+    # masked items never appear
+    rows = sub.cpu().numpy()
+    for b in range(0, len(rows), 97):
+        u = rows[b]
+        assert np.intersect1d(got[b].cpu().numpy(), indices[indptr[u]:indptr[u + 1]] - nu).size == 0
+
+
+def test_rank_metrics_vs_oracle(lg, orc):
+    rng = np.random.default_rng(5)
+    n, m, kmax = 257, 400, 20
+    gts = [rng.choice(m, size=int(rng.integers(1, 40)), replace=False) for _ in range(n)]
+    topk = np.stack([rng.choice(m, size=kmax, replace=False) for _ in range(n)])
+    for b in range(0, n, 3):
+        topk[b, :3] = gts[b][:3] if len(gts[b]) >= 3 else topk[b, :3]
+    indptr = np.concatenate([[0], np.cumsum([len(x) for x in gts])]).astype(np.int32)
+    items = np.concatenate([np.sort(x) for x in gts]).astype(np.int32)
+    ks = [5, 10, 20]
+    sums = lg.ops.rank_metrics(dev(topk.astype(np.int64)), dev(indptr), dev(items), ks).cpu().numpy()
+    exp = orc.metrics_at_k(topk, [x.tolist() for x in gts], ks)
+    for j, name in enumerate(('precision', 'recall', 'ndcg')):
+        assert np.allclose(sums[:, j] / n, exp[name], rtol=1e-12, atol=1e-14)

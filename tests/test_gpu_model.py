@@ -1,0 +1,224 @@
+"""GPU: the reference-facing Python API (LightGCN / BPRLoss / Procedure) against outputs of the real
+reference (tests/golden/*.npz) and the gowalla known answer."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def lg():
+    import lgcn_b200
+    return lgcn_b200
+
+
+def make_model(lg, g, **over):
+    cfg = dict(lg.world.config)
+    cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), bpr_batch_size=len(g['users']),
+               decay=float(g['decay']), lr=float(g['lr']))
+    cfg.update(over)
+    ds = lg.InteractionDataset(int(g['n_users']), int(g['m_items']), g['train_user'], g['train_item'],
+                               g['test_user'], g['test_item'], config=cfg)
+    m = lg.LightGCN(cfg, ds)
+    nu = int(g['n_users'])
+    with torch.no_grad():
+        m.embedding_user.weight.copy_(torch.from_numpy(g['E0'][:nu]))
+        m.embedding_item.weight.copy_(torch.from_numpy(g['E0'][nu:]))
+    return cfg, ds, m
+
+
+def triples(g, shift=0):
+    return tuple(torch.from_numpy(np.roll(g[k], shift)).long() for k in ('users', 'pos', 'neg'))
+
+
+def params(m):
+    return torch.cat([m.embedding_user.weight, m.embedding_item.weight]).detach().cpu().numpy()
+
+
+def test_seeded_init_is_the_references(lg, golden):
+    """set_seed(2020) -> construct consumes the CPU RNG exactly like code/model.py:57-60."""
+    cfg = dict(lg.world.config); cfg.update(latent_dim_rec=int(golden['d']), lightGCN_n_layers=int(golden['L']))
+    ds = lg.InteractionDataset(int(golden['n_users']), int(golden['m_items']), golden['train_user'], golden['train_item'],
+                               golden['test_user'], golden['test_item'], config=cfg)
+    lg.utils.set_seed(2020)
+    m = lg.LightGCN(cfg, ds)
+    assert np.array_equal(params(m), golden['E0'])
+    assert set(m.state_dict().keys()) == {'embedding_user.weight', 'embedding_item.weight'}
+
+
+def test_computer_matches_reference(lg, golden):
+    _, ds, m = make_model(lg, golden)
+    with torch.no_grad():
+        u, i = m.computer()
+    out = torch.cat([u, i]).cpu().numpy()
+    assert rel_err(out, golden['out']) < TOL
+    # the dataset's graph is a torch sparse tensor usable exactly like the reference's
+    ref = torch.sparse.mm(ds.getSparseGraph(), torch.from_numpy(golden['E0']).cuda())
+    mine = torch.empty_like(ref); lg.ops.spmm(ds.getCSRGraph(), torch.from_numpy(golden['E0']).cuda(), mine)
+    assert rel_err(mine.cpu().numpy(), ref.cpu().numpy()) < TOL
+
+
+def test_bpr_loss_autograd_matches_reference(lg, golden):
+    """Generic path: bpr_loss -> (loss + decay*reg).backward(), as the reference's utils.BPRLoss drives it."""
+    _, _, m = make_model(lg, golden)
+    u, p, n = (t.cuda() for t in triples(golden))
+    loss, reg = m.bpr_loss(u, p, n)
+    assert abs(loss.item() - float(golden['loss'])) < TOL * abs(float(golden['loss']))
+    assert abs(reg.item() - float(golden['reg'])) < TOL * abs(float(golden['reg']))
+    (loss + reg * float(golden['decay'])).backward()
+    grad = torch.cat([m.embedding_user.weight.grad, m.embedding_item.weight.grad]).cpu().numpy()
+    assert rel_err(grad, golden['grad']) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager", "deterministic", "host_batch"])
+def test_fused_stageOne_matches_reference(lg, golden, mode):
+    over = dict(cuda_graph=(mode != "eager"), deterministic=(mode == "deterministic"))
+    cfg, _, m = make_model(lg, golden, **over)
+    bpr = lg.utils.BPRLoss(m, cfg)
+    B = len(golden['users'])
+    for s in range(3):
+        u, p, n = triples(golden, (s * 17) % B)
+        if mode != "host_batch":
+            u, p, n = u.cuda(), p.cuda(), n.cuda()
+        loss = bpr.stageOne(u, p, n)
+        assert abs(loss - golden['step_losses'][s]) < TOL * abs(golden['step_losses'][s])
+        assert rel_err(params(m), golden['params_after'][s]) < 1e-4
+    sd = bpr.opt.state_dict()
+    assert float(sd['state'][0]['step']) == 3.0
+    m_cat = np.concatenate([sd['state'][0]['exp_avg'].cpu().numpy(), sd['state'][1]['exp_avg'].cpu().numpy()])
+    v_cat = np.concatenate([sd['state'][0]['exp_avg_sq'].cpu().numpy(), sd['state'][1]['exp_avg_sq'].cpu().numpy()])
+    assert rel_err(m_cat, golden['exp_avg']) < 1e-4 and rel_err(v_cat, golden['exp_avg_sq']) < 1e-4
+    with torch.no_grad():
+        out = torch.cat(m.computer()).cpu().numpy()
+    assert rel_err(out, golden['out_after']) < 1e-4
+
+
+def test_reference_recipe_on_this_model(lg, golden):
+    """The reference's own BPRLoss recipe (zero_grad/backward/torch Adam) drives this model unchanged."""
+    cfg, _, m = make_model(lg, golden)
+    opt = torch.optim.Adam(m.parameters(), lr=cfg['lr'])
+    B = len(golden['users'])
+    for s in range(3):
+        u, p, n = (t.cuda() for t in triples(golden, (s * 17) % B))
+        loss, reg = m.bpr_loss(u, p, n)
+        total = loss + reg * cfg['decay']
+        opt.zero_grad(); total.backward(); opt.step()
+        assert abs(total.item() - golden['step_losses'][s]) < TOL * abs(golden['step_losses'][s])
+    assert rel_err(params(m), golden['params_after'][2]) < 1e-4
+
+
+def test_graph_replay_equals_eager_bitwise(lg, golden_tiny):
+    res = []
+    for use_graph in (True, False):
+        cfg, _, m = make_model(lg, golden_tiny, cuda_graph=use_graph, deterministic=True)
+        bpr = lg.utils.BPRLoss(m, cfg)
+        for s in range(4):
+            bpr.stageOne(*(t.cuda() for t in triples(golden_tiny, s * 5)))
+        res.append(params(m))
+    assert np.array_equal(res[0], res[1])
+
+
+def test_getUsersRating_and_Test_match_reference(lg, golden):
+    cfg, ds, m = make_model(lg, golden)
+    nu = int(golden['n_users'])
+    with torch.no_grad():
+        m.embedding_user.weight.copy_(torch.from_numpy(golden['params_after'][2][:nu]))
+        m.embedding_item.weight.copy_(torch.from_numpy(golden['params_after'][2][nu:]))
+    users = torch.from_numpy(golden['test_users']).long()
+    with torch.no_grad():
+        rating = m.getUsersRating(users.cuda()).cpu().numpy()
+    assert rating.shape == golden['rating'].shape
+    assert rel_err(rating, golden['rating']) < 2e-5
+    lg.world.configure(topks=[int(k) for k in golden['topks']], checkpoint_dir='/tmp/lgcn_b200_test_ckpt')
+    try:
+        res = lg.Procedure.Test(ds, m, 0)
+    finally:
+        lg.world.configure(topks=[20])
+    for name in ('precision', 'recall', 'ndcg'):
+        assert np.allclose(res[name], golden[name], rtol=0, atol=1e-4), (name, res[name], golden[name])
+    # top-k ids agree with the reference's torch.topk except at near-ties
+    idx, _ = m.rank_topk(users, int(max(golden['topks'])))
+    idx = idx.cpu().numpy()
+    frac = (idx != golden['topk']).mean()
+    assert frac < 0.02, frac
+
+
+def test_state_dict_and_optimizer_round_trip(lg, golden_tiny):
+    cfg, _, m = make_model(lg, golden_tiny)
+    bpr = lg.utils.BPRLoss(m, cfg)
+    for s in range(2):
+        bpr.stageOne(*(t.cuda() for t in triples(golden_tiny, s)))
+    sd, osd = {k: v.clone() for k, v in m.state_dict().items()}, bpr.opt.state_dict()
+    cfg2, _, m2 = make_model(lg, golden_tiny)
+    m2.load_state_dict(sd, strict=True)
+    bpr2 = lg.utils.BPRLoss(m2, cfg2)
+    bpr2.opt.load_state_dict(osd)
+    a = bpr.stageOne(*(t.cuda() for t in triples(golden_tiny, 9)))
+    b = bpr2.stageOne(*(t.cuda() for t in triples(golden_tiny, 9)))
+    assert abs(a - b) < 1e-6 * abs(a)
+    assert rel_err(params(m2), params(m)) < 1e-6
+    m3 = m2.to(lg.world.device)                       # the reference does Recmodel.to(world.device)
+    assert m3 is m2 and m2._params_packed()
+
+
+def test_epoch_training_and_eval_on_synthetic(lg, tmp_path):
+    lg.world.configure(checkpoint_dir=str(tmp_path), bpr_batch_size=256)
+    try:
+        cfg = dict(lg.world.config)
+        ds = lg.synth.make_dataset('tiny', config=cfg)
+        lg.utils.set_seed(2020); lg.utils.sampler_seed(2020)
+        m = lg.LightGCN(cfg, ds)
+        bpr = lg.utils.BPRLoss(m, cfg)
+        r0 = lg.Procedure.Test(ds, m, 0)
+        infos = [lg.Procedure.BPR_train_original(ds, m, bpr, e) for e in range(30)]
+        r1 = lg.Procedure.Test(ds, m, 30)
+        l0, l1 = float(infos[0].split('-')[0][4:]), float(infos[-1].split('-')[0][4:])
+        assert l1 < l0 and infos[0].endswith('|') and 'Sample' in infos[0]
+        assert r1['recall'][0] > r0['recall'][0]
+        assert (tmp_path / 'train_epoch_metrics.csv').read_text().count('\n') == 31
+    finally:
+        lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048)
+
+
+def test_epoch_mode_equals_step_mode(lg, golden_tiny):
+    """Device-resident epoch (window advance + graph replay) == explicit stageOne calls on the same batches."""
+    g = golden_tiny
+    S = np.stack([np.tile(g[k], 3)[:700] for k in ('users', 'pos', 'neg')])          # 700 triples, B=256 -> 3 steps
+    cfg, _, ma = make_model(lg, g, deterministic=True)
+    ea = ma._engine
+    steps = ea.begin_epoch(torch.from_numpy(S).cuda())
+    assert steps == 3
+    for _ in range(steps):
+        ea.epoch_step()
+    run_sum = float(ea.loss_to_host()[3])
+    cfg, _, mb = make_model(lg, g, deterministic=True)
+    bpr = lg.utils.BPRLoss(mb, cfg)
+    losses = [bpr.stageOne(*(torch.from_numpy(S[j, lo:lo + 256]).cuda() for j in range(3))) for lo in (0, 256, 512)]
+    assert np.array_equal(params(ma), params(mb))
+    assert abs(run_sum - sum(losses)) < 1e-5
+
+
+def test_gowalla_step0_known_answer_end_to_end(lg, gowalla, tmp_path):
+    """Reference run artefacts: seed 2020 -> LightGCN(L=3,d=64) -> Test on gowalla gives
+    Precision@20 0.0001875544, Recall@20 0.0005374941, NDCG@20 0.00040836."""
+    nu, ni = int(gowalla['n_users']), int(gowalla['m_items'])
+    tu = np.repeat(np.arange(nu), np.diff(gowalla['train_indptr'])).astype(np.int64)
+    ti = gowalla['train_items'].astype(np.int64)
+    su = np.repeat(gowalla['test_users'].astype(np.int64), np.diff(gowalla['test_indptr']))
+    si = gowalla['test_items'].astype(np.int64)
+    lg.world.configure(checkpoint_dir=str(tmp_path), topks=[20])
+    cfg = dict(lg.world.config)
+    ds = lg.InteractionDataset(nu, ni, tu, ti, su, si, config=cfg, name='gowalla')
+    g = ds.getCSRGraph()
+    assert g.nnz == 1620256
+    lg.utils.set_seed(2020)
+    m = lg.LightGCN(cfg, ds)
+    res = lg.Procedure.Test(ds, m, 0)
+    assert abs(res['precision'][0] - float(gowalla['kat_precision'])) < 2e-9
+    assert abs(res['recall'][0] - float(gowalla['kat_recall'])) < 2e-9
+    assert abs(res['ndcg'][0] - float(gowalla['kat_ndcg'])) < 2e-7

@@ -1,0 +1,159 @@
+"""CPU: host-side logic and the C-ABI boundary (no device compute)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    import lgcn_b200 as lg
+    header = open(os.path.join(ROOT, 'include', 'lgcn_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(lgcn_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    lib = lg._lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/lgcn_b200.h but not exported"
+    assert declared == set(lg._lib.EXPORTED_SYMBOLS), declared ^ set(lg._lib.EXPORTED_SYMBOLS)
+    assert lib.lgcn_abi_version() == 1
+
+
+def test_host_side_queries_without_gpu():
+    import lgcn_b200 as lg
+    lib = lg._lib.load()
+    assert lib.lgcn_csr_build_workspace_bytes(1000, 10, 20) > 2 * 8 * 2000
+    assert lib.lgcn_bpr_workspace_bytes(2048, 64) >= 16 + 2048 * 4
+    assert lib.lgcn_score_topk_workspace_bytes(100, 1000, 20) >= 100 * 32 * 20 * 8
+    # argument validation happens before any launch
+    assert lib.lgcn_spmm_f32(None, None, None, 1, 64, None, None, 1.0, 0.0, None, 0, None, None) != 0
+    assert b'null' in lib.lgcn_last_error()
+
+
+def test_sampler_matches_reference_cpp_bit_exact():
+    """Same glibc rand() stream and draw order as the reference's sources/sampling.cpp (golden made by
+    compiling that file, oracle/gen_golden.py::sampler_golden)."""
+    import ctypes
+    import lgcn_b200 as lg
+    g = load_golden('sampler')
+    lib = lg._lib.load()
+    lg.utils.sampler_seed(2020)
+    nu, ni, tn = int(g['n_users']), int(g['m_items']), int(g['train_num'])
+    out = np.empty(((tn // nu) * nu, 3), dtype=np.int32)
+    indptr, items = np.ascontiguousarray(g['indptr']), np.ascontiguousarray(g['items'])
+    rows = lib.lgcn_sample_negative(nu, ni, tn, indptr.ctypes.data_as(ctypes.c_void_p),
+                                    items.ctypes.data_as(ctypes.c_void_p), 1, out.ctypes.data_as(ctypes.c_void_p))
+    assert rows == out.shape[0]
+    assert np.array_equal(out, g['S'])
+
+
+def test_sampler_through_dataset_api():
+    import lgcn_b200 as lg
+    ds = lg.synth.make_dataset('tiny')
+    lg.utils.sampler_seed(7)
+    S = lg.utils.UniformSample_original(ds)
+    per = ds.trainDataSize // ds.n_users
+    assert S.shape == (ds.n_users * per, 3) and S.dtype == np.int32
+    assert np.array_equal(S[:, 0], np.repeat(np.arange(ds.n_users), per))
+    ap = ds.allPos
+    for u, p, n in S[::37]:
+        assert p in ap[u] and n not in ap[u] and 0 <= n < ds.m_items
+
+
+def test_loader_parses_reference_format(tmp_path):
+    import lgcn_b200 as lg
+    (tmp_path / 'train.txt').write_text("0 1 2 3\n1 0\n\n2\n3 4 4\n")
+    (tmp_path / 'test.txt').write_text("0 5\n1 2 3\n4\n")
+    ds = lg.Loader(lg.world.config, path=str(tmp_path))
+    assert (ds.n_users, ds.m_items) == (4, 6)            # max id over train+test, +1; item-less lines skipped
+    assert ds.trainDataSize == 6 and ds.testDataSize == 3
+    assert list(ds.testDict.keys()) == [0, 1] and ds.testDict[1] == [2, 3]
+    assert [a.tolist() for a in ds.allPos] == [[1, 2, 3], [0], [], [4]]
+    assert ds.users_D.tolist() == [3, 1, 1, 2] and ds.items_D[4] == 2     # duplicates counted, zero -> 1
+    assert ds.getUserItemFeedback([0, 1], [1, 1]).tolist() == [1, 0]
+
+
+def test_loader_round_trip_of_synthetic_graph(tmp_path):
+    import lgcn_b200 as lg
+    g = lg.synth.make_graph('tiny', seed=5)
+    lg.synth.write_txt(g, str(tmp_path))
+    ds = lg.Loader(lg.world.config, path=str(tmp_path))
+    a = lg.InteractionDataset(g['n_users'], g['m_items'], g['train_user'], g['train_item'], g['test_user'], g['test_item'])
+    assert ds.trainDataSize == a.trainDataSize
+    assert all(np.array_equal(x, y) for x, y in zip(ds.allPos, a.allPos))
+    assert {k: sorted(v) for k, v in ds.testDict.items()} == {k: sorted(v) for k, v in a.testDict.items()}
+
+
+def test_synthetic_shapes_match_calibration():
+    import lgcn_b200 as lg
+    g = lg.synth.make_graph('yelp2018')
+    assert (g['n_users'], g['m_items']) == (31668, 38048)
+    E = g['train_user'].size
+    assert abs(E - 1237259) / 1237259 < 0.03
+    du = np.bincount(g['train_user'], minlength=g['n_users'])
+    assert du.min() >= 1 and 24 <= np.median(du) <= 30
+    key = g['train_user'] * g['m_items'] + g['train_item']
+    assert np.unique(key).size == key.size                          # de-duplicated
+    tkey = g['test_user'] * g['m_items'] + g['test_item']
+    assert np.intersect1d(key, tkey).size == 0                      # train/test disjoint
+    g2 = lg.synth.make_graph('yelp2018')
+    assert np.array_equal(g['train_item'], g2['train_item'])        # deterministic in the seed
+
+
+def test_minibatch_shuffle_timer():
+    import lgcn_b200 as lg
+    u = lg.utils
+    assert [list(b) for b in u.minibatch(list(range(5)), batch_size=2)] == [[0, 1], [2, 3], [4]]
+    a, b = np.arange(10), np.arange(10) * 2
+    assert [tuple(x.tolist() for x in t) for t in u.minibatch(a, b, batch_size=6)][1] == ([6, 7, 8, 9], [12, 14, 16, 18])
+    np.random.seed(3); sa, sb = u.shuffle(a, b)
+    np.random.seed(3); perm = np.arange(10); np.random.shuffle(perm)
+    assert np.array_equal(sa, a[perm]) and np.array_equal(sb, b[perm])
+    with pytest.raises(ValueError):
+        u.shuffle(a, b[:3])
+    u.timer.zero()
+    with u.timer(name="Sample"):
+        pass
+    assert u.timer.dict().startswith("|Sample:")
+    u.timer.zero()
+    with u.timer():
+        pass
+    assert u.timer.get() >= 0
+
+
+def test_host_metrics_match_oracle():
+    import lgcn_b200 as lg
+    from oracle import lightgcn_oracle as orc
+    rng = np.random.default_rng(0)
+    lg.world.configure(topks=[5, 20])
+    try:
+        for _ in range(20):
+            gt = rng.choice(100, size=int(rng.integers(1, 30)), replace=False).tolist()
+            top = rng.choice(100, size=20, replace=False)
+            got = lg.Procedure.test_one_batch((top, gt))
+            exp = orc.metrics_at_k(top[None, :], [gt], [5, 20])
+            for k in ('precision', 'recall', 'ndcg'):
+                assert np.allclose(got[k], exp[k], atol=1e-7)
+    finally:
+        lg.world.configure(topks=[20])
+
+
+def test_device_paths_fail_loudly_without_gpu():
+    import torch
+    import lgcn_b200 as lg
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ds = lg.synth.make_dataset('tiny')
+    with pytest.raises(RuntimeError):
+        ds.getSparseGraph()
+    with pytest.raises(RuntimeError):
+        lg.ops.spmm(None, torch.zeros(4, 64), torch.zeros(4, 64))
+
+
+def test_world_has_reference_defaults():
+    import lgcn_b200 as lg
+    c = lg.world.config
+    assert (c['latent_dim_rec'], c['lightGCN_n_layers'], c['bpr_batch_size'], c['test_u_batch_size']) == (64, 3, 2048, 100)
+    assert (c['lr'], c['decay'], lg.world.topks, lg.world.seed) == (0.001, 1e-4, [20], 2020)
