@@ -16,15 +16,17 @@ MAX_TOPK = 128
 
 class SpmmPlan(Structure):
     _fields_ = [
-        ("seg_len", c_int32), ("n_long", c_int32), ("n_segs", c_int32), ("d_max", c_int32),
-        ("segs", c_void_p), ("counters", c_void_p), ("partials", c_void_p), ("row_order", c_void_p),
+        ("seg_len", c_int32), ("n_long", c_int32), ("n_segs", c_int32), ("n_items", c_int32),
+        ("d_max", c_int32), ("pad", c_int32),
+        ("items", c_void_p), ("seginfo", c_void_p), ("counters", c_void_p), ("partials", c_void_p),
     ]
 
 
 class AdamScalars(Structure):
     _fields_ = [
         ("step_size", c_float), ("bc2_sqrt", c_float), ("beta1", c_float), ("beta2", c_float),
-        ("eps", c_float), ("lr", c_float), ("step", c_int32), ("pad", c_int32),
+        ("w1", c_float), ("w2", c_float), ("eps", c_float), ("pad0", c_float),
+        ("step", c_int32), ("pad1", c_int32), ("lr_d", c_double), ("beta1_d", c_double), ("beta2_d", c_double),
     ]
 
 
@@ -37,12 +39,14 @@ _SIGNATURES = {
     "lgcn_csr_build": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "lgcn_coo_to_csr": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
     "lgcn_spmm_plan_count": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P]),
-    "lgcn_spmm_plan_fill": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P]),
+    "lgcn_spmm_plan_workspace_bytes": (c_size_t, [c_int32]),
+    "lgcn_spmm_plan_fill": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P, c_size_t, _P]),
     "lgcn_spmm_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                      POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P]),
     "lgcn_spmm_adam_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                           POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P]),
-    "lgcn_adam_init": (ctypes.c_int, [_P, c_float, c_float, c_float, c_float, c_int32, _P]),
+    "lgcn_debug_spmm_variant": (ctypes.c_int, [ctypes.c_int]),
+    "lgcn_adam_init": (ctypes.c_int, [_P, c_double, c_double, c_double, c_double, c_int32, _P]),
     "lgcn_adam_tick": (ctypes.c_int, [_P, _P]),
     "lgcn_adam_f32": (ctypes.c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "lgcn_bpr_workspace_bytes": (c_size_t, [c_int32, c_int32]),

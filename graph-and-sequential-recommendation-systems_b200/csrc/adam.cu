@@ -6,33 +6,35 @@
 
 namespace lgcn {
 
-__global__ void adam_init_kernel(lgcn_adam_scalars_t* s, float lr, float b1, float b2, float eps, int step) {
-    s->lr = lr; s->beta1 = b1; s->beta2 = b2; s->eps = eps; s->step = step; s->pad = 0;
-    const int t = step > 0 ? step : 1;
-    s->step_size = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
-    s->bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)t));
+__device__ void adam_refresh(lgcn_adam_scalars_t* s) {
+    const int t = s->step > 0 ? s->step : 1;
+    s->step_size = (float)(s->lr_d / (1.0 - pow(s->beta1_d, (double)t)));
+    s->bc2_sqrt = (float)sqrt(1.0 - pow(s->beta2_d, (double)t));
+}
+
+__global__ void adam_init_kernel(lgcn_adam_scalars_t* s, double lr, double b1, double b2, double eps, int step) {
+    s->lr_d = lr; s->beta1_d = b1; s->beta2_d = b2;
+    s->beta1 = (float)b1; s->beta2 = (float)b2; s->w1 = (float)(1.0 - b1); s->w2 = (float)(1.0 - b2);
+    s->eps = (float)eps; s->pad0 = 0.f; s->step = step; s->pad1 = 0;
+    adam_refresh(s);
 }
 
 __global__ void adam_tick_kernel(lgcn_adam_scalars_t* s) {
-    const int t = s->step + 1;
-    s->step = t;
-    s->step_size = (float)((double)s->lr / (1.0 - pow((double)s->beta1, (double)t)));
-    s->bc2_sqrt = (float)sqrt(1.0 - pow((double)s->beta2, (double)t));
+    s->step = s->step + 1;
+    adam_refresh(s);
 }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, const float4* __restrict__ G,
             long long n4, const lgcn_adam_scalars_t* __restrict__ sc) {
-    const float b1 = sc->beta1, b2 = sc->beta2, eps = sc->eps, step_size = sc->step_size, bc2s = sc->bc2_sqrt;
-    const float w1 = 1.f - b1, w2 = 1.f - b2;
+    const float b2 = sc->beta2, eps = sc->eps, step_size = sc->step_size, bc2s = sc->bc2_sqrt;
+    const float w1 = sc->w1, w2 = sc->w2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 p = P[i], m = M[i], v = V[i]; const float4 g = ld_once_f4(G + i);
-#define LGCN_ADAM1(c) \
-        m.c = m.c + w1 * (g.c - m.c); \
-        v.c = v.c * b2 + w2 * g.c * g.c; \
-        p.c = p.c - step_size * (m.c / (sqrtf(v.c) / bc2s + eps));
-        LGCN_ADAM1(x) LGCN_ADAM1(y) LGCN_ADAM1(z) LGCN_ADAM1(w)
-#undef LGCN_ADAM1
+        adam_update1(p.x, m.x, v.x, g.x, b2, w1, w2, step_size, bc2s, eps);
+        adam_update1(p.y, m.y, v.y, g.y, b2, w1, w2, step_size, bc2s, eps);
+        adam_update1(p.z, m.z, v.z, g.z, b2, w1, w2, step_size, bc2s, eps);
+        adam_update1(p.w, m.w, v.w, g.w, b2, w1, w2, step_size, bc2s, eps);
         P[i] = p; M[i] = m; V[i] = v;
     }
 }
@@ -41,7 +43,7 @@ adam_kernel(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__
 
 using namespace lgcn;
 
-extern "C" int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, float lr, float beta1, float beta2, float eps,
+extern "C" int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, double lr, double beta1, double beta2, double eps,
                               int32_t step, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(scalars_dev, "adam_init: null scalars");
     adam_init_kernel<<<1, 1, 0, as_stream(stream)>>>(scalars_dev, lr, beta1, beta2, eps, step);

@@ -82,6 +82,16 @@ __device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
     return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
 
+// torch.optim.Adam (defaults) element update with the rounding points pinned: exp_avg.lerp_(g, 1-b1);
+// exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2); denom = sqrt(v)/bc2_sqrt + eps; p.addcdiv_(m, denom, -step)
+__device__ __forceinline__ void adam_update1(float& p, float& m, float& v, float g, float b2, float w1, float w2,
+                                             float step_size, float bc2s, float eps) {
+    m = __fmaf_rn(w1, __fsub_rn(g, m), m);
+    v = __fmaf_rn(__fmul_rn(w2, g), g, __fmul_rn(v, b2));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), eps);
+    p = __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace lgcn

@@ -5,17 +5,23 @@
 // symmetric so the same CSR is used) and, in the last backward layer, torch.optim.Adam.step()
 // (code/utils.py:62).
 //
-// Schedule
-//   * one GROUP of LANES = min(32, d/4) lanes owns one output row; every lane holds d/4/LANES
-//     float4 accumulators, so one embedding row (d=64: 256 B) is one 16-byte load per lane;
-//   * the row's (col,val) pairs are read LANES at a time with one coalesced streaming load each and
-//     handed round the group with shuffles (register staging of the row segment); the next chunk is
-//     prefetched while the current one is being gathered;
-//   * UNROLL independent 16-byte gathers are in flight per lane before the first FMA;
-//   * degree binning: rows with more than plan.seg_len non-zeros are cut into equal segments that
-//     are scheduled as independent groups (appended after the n_rows short-row groups).  Each
-//     segment writes its partial row to plan.partials; the segment that arrives last (atomic
-//     counter) adds the partials in part order — a fixed summation order — and runs the epilogue.
+// Schedule (round-1 measurements in profiles/README.md drove every choice below)
+//   * WORK ITEMS.  A plan (lgcn_spmm_plan_*) turns the rows into items {row, start, end}: a row with at
+//     most seg_len non-zeros is one item, a longer row is cut into equal segments.  Items are binned
+//     by exact length and laid out in DESCENDING length (degree-binned load balancing): the groups
+//     that share a warp/CTA do the same amount of work, the long items start first, and the item
+//     descriptor is ONE coalesced 16-byte load instead of the row_order -> indptr -> indptr chain.
+//   * one GROUP of LANES lanes owns one item; every lane holds d/4/LANES float4 accumulators
+//     (d=64, LANES=16: one 256-B embedding row is one 16-byte load per lane, two items per warp);
+//   * the item's (col,val) pairs are read LANES at a time with one coalesced streaming load each and
+//     handed round the group with shuffles; lanes past the end re-read the last valid column with
+//     weight 0, so the gather loop has no predicates; the next chunk is prefetched;
+//   * UNROLL independent 16-byte gathers are in flight per lane before the first FMA; registers are
+//     capped at 64 so that 32 warps/SM are resident (the kernel is latency-, not bandwidth-bound:
+//     ncu showed L2 at 16 % of peak with 16 resident warps);
+//   * segments write their partial row to plan.partials; the segment that arrives last (atomic
+//     counter, self-resetting) adds the partials in part order — a fixed summation order — and runs
+//     the epilogue.  No float atomics, one launch, results independent of scheduling.
 //
 // HBM roofline: B_spmm = 8*nnz + 4*(N+1) + 8*N*d bytes per layer.
 #include "common.cuh"
@@ -23,55 +29,54 @@
 namespace lgcn {
 
 struct SpmmArgs {
+    const int4* items; int n_items;            // sorted work items {row, start, end, seg_ref}; NULL -> rows of indptr
+    const int4* seginfo;                       // {part, n_parts, slot_base, long_id}
     const int* indptr; const int* indices; const float* vals;
-    int n_rows;
     const float4* X; float4* Y;
     float alpha, beta;
     int nz;
     const float4* z[LGCN_MAX_Z];
-    // plan
-    int seg_len; int n_segs;
-    const int4* segs; int* counters; float4* partials; const int* row_order;
-    // adam epilogue
-    float4* P; float4* M; float4* V; const lgcn_adam_scalars_t* sc;
+    int* counters; float4* partials;
+    float4* P; float4* M; float4* V; const lgcn_adam_scalars_t* sc;   // adam epilogue
 };
 
-template <int D> struct Geo {
-    static constexpr int VEC = D / 4;
-    static constexpr int LANES = VEC < 32 ? VEC : 32;
-    static constexpr int VPL = VEC / LANES;
-    static_assert(D % 16 == 0 && VPL >= 1, "d must be a multiple of 16");
-};
+static int g_variant = 0;      // tuning variant of the d=64 kernels (lgcn_debug_spmm_variant, profiling hook)
 
-constexpr int kThreads = 256;
+__device__ __forceinline__ float4 gather_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
-template <int D, int UNROLL>
-__device__ __forceinline__ void accumulate_segment(const SpmmArgs& a, int start, int end, int lane,
-                                                   unsigned gmask, float4 (&acc)[Geo<D>::VPL]) {
-    constexpr int LANES = Geo<D>::LANES, VPL = Geo<D>::VPL, VEC = Geo<D>::VEC;
+template <int D, int LANES, int UNROLL>
+__device__ __forceinline__ void accumulate_item(const SpmmArgs& a, int start, int end, int lane,
+                                                unsigned gmask, float4 (&acc)[D / 4 / LANES]) {
+    constexpr int VEC = D / 4, VPL = VEC / LANES;
     static_assert(LANES % UNROLL == 0, "UNROLL must divide the group width");
-    int c_nxt = 0; float v_nxt = 0.f;
-    if (start + lane < end) { c_nxt = ld_stream_i32(a.indices + start + lane); v_nxt = ld_stream_f32(a.vals + start + lane); }
+    if (start >= end) return;
+    int cnt = min(LANES, end - start);
+    int j = start + min(lane, cnt - 1);                     // lanes past the end: last valid entry, weight 0
+    int c_nxt = ld_stream_i32(a.indices + j);
+    float v_nxt = lane < cnt ? ld_stream_f32(a.vals + j) : 0.f;
     for (int base = start; base < end; base += LANES) {
         const int c = c_nxt; const float v = v_nxt;
-        const int jn = base + LANES + lane;
-        c_nxt = 0; v_nxt = 0.f;
-        if (jn < end) { c_nxt = ld_stream_i32(a.indices + jn); v_nxt = ld_stream_f32(a.vals + jn); }
-        const int cnt = min(LANES, end - base);
-        for (int t = 0; t < cnt; t += UNROLL) {
+        const int cur = cnt;
+        if (base + LANES < end) {
+            cnt = min(LANES, end - base - LANES);
+            j = base + LANES + min(lane, cnt - 1);
+            c_nxt = ld_stream_i32(a.indices + j);
+            v_nxt = lane < cnt ? ld_stream_f32(a.vals + j) : 0.f;
+        }
+#pragma unroll 1
+        for (int t = 0; t < cur; t += UNROLL) {
             float4 x[UNROLL][VPL]; float w[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int cc = __shfl_sync(gmask, c, t + u, LANES);
                 w[u] = __shfl_sync(gmask, v, t + u, LANES);
-                if (t + u < cnt) {
-                    const float4* src = a.X + (size_t)cc * VEC + lane;
+                const float4* src = a.X + (size_t)cc * VEC + lane;
 #pragma unroll
-                    for (int p = 0; p < VPL; ++p) x[u][p] = ld_gather_f4(src + p * LANES);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < VPL; ++p) x[u][p] = f4_zero();
-                }
+                for (int p = 0; p < VPL; ++p) x[u][p] = gather_f4(src + p * LANES);
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
@@ -81,30 +86,28 @@ __device__ __forceinline__ void accumulate_segment(const SpmmArgs& a, int start,
     }
 }
 
-template <int D, bool ADAM>
-__device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, const float4 (&acc)[Geo<D>::VPL]) {
-    constexpr int LANES = Geo<D>::LANES, VPL = Geo<D>::VPL, VEC = Geo<D>::VEC;
+template <int D, int LANES, bool ADAM>
+__device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, const float4 (&acc)[D / 4 / LANES]) {
+    constexpr int VEC = D / 4, VPL = VEC / LANES;
 #pragma unroll
     for (int p = 0; p < VPL; ++p) {
         const size_t off = (size_t)row * VEC + lane + p * LANES;
         float4 g = make_float4(a.alpha * acc[p].x, a.alpha * acc[p].y, a.alpha * acc[p].z, a.alpha * acc[p].w);
         if (a.nz > 0) {
             float4 zs = ld_once_f4(a.z[0] + off);
+#pragma unroll 1
             for (int t = 1; t < a.nz; ++t) f4_add(zs, ld_once_f4(a.z[t] + off));
             f4_fma(g, a.beta, zs);
         }
         if constexpr (ADAM) {
             // torch.optim.Adam single-tensor arithmetic (betas/eps/step scalars live on the device)
-            const float b1 = a.sc->beta1, b2 = a.sc->beta2, eps = a.sc->eps;
+            const float b2 = a.sc->beta2, eps = a.sc->eps, w1 = a.sc->w1, w2 = a.sc->w2;
             const float step_size = a.sc->step_size, bc2s = a.sc->bc2_sqrt;
             float4 pw = a.P[off], m = a.M[off], vv = a.V[off];
-            const float w1 = 1.f - b1, w2 = 1.f - b2;
-#define LGCN_ADAM1(c) \
-            m.c = m.c + w1 * (g.c - m.c); \
-            vv.c = vv.c * b2 + w2 * g.c * g.c; \
-            pw.c = pw.c - step_size * (m.c / (sqrtf(vv.c) / bc2s + eps));
-            LGCN_ADAM1(x) LGCN_ADAM1(y) LGCN_ADAM1(z) LGCN_ADAM1(w)
-#undef LGCN_ADAM1
+            adam_update1(pw.x, m.x, vv.x, g.x, b2, w1, w2, step_size, bc2s, eps);
+            adam_update1(pw.y, m.y, vv.y, g.y, b2, w1, w2, step_size, bc2s, eps);
+            adam_update1(pw.z, m.z, vv.z, g.z, b2, w1, w2, step_size, bc2s, eps);
+            adam_update1(pw.w, m.w, vv.w, g.w, b2, w1, w2, step_size, bc2s, eps);
             a.P[off] = pw; a.M[off] = m; a.V[off] = vv;
             if (a.Y != nullptr) st_stream_f4(a.Y + off, g);
         } else {
@@ -113,35 +116,34 @@ __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, c
     }
 }
 
-template <int D, int UNROLL, bool ADAM>
-__global__ void __launch_bounds__(kThreads)
+template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 spmm_kernel(const __grid_constant__ SpmmArgs a) {
-    constexpr int LANES = Geo<D>::LANES, VPL = Geo<D>::VPL, VEC = Geo<D>::VEC;
-    constexpr int GROUPS = kThreads / LANES;
+    constexpr int VEC = D / 4, VPL = VEC / LANES;
+    constexpr int GROUPS = THREADS / LANES;
+    static_assert(VEC % LANES == 0 && LANES <= 32 && VPL >= 1, "bad group width");
     const int lane = threadIdx.x % LANES;
-    const int group_in_cta = threadIdx.x / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                          : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
-    const long long gidx = (long long)blockIdx.x * GROUPS + group_in_cta;
-
+    const long long gidx = (long long)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    if (gidx >= a.n_items) return;
+    int row, start, end, seg_ref;
+    if (a.items != nullptr) {
+        const int4 it = __ldg(a.items + gidx);
+        row = it.x; start = it.y; end = it.z; seg_ref = it.w;
+    } else {
+        row = (int)gidx; start = __ldg(a.indptr + row); end = __ldg(a.indptr + row + 1); seg_ref = -1;
+    }
     float4 acc[VPL];
 #pragma unroll
     for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
-
-    if (gidx < a.n_rows) {
-        const int row = a.row_order ? __ldg(a.row_order + gidx) : (int)gidx;
-        const int s = __ldg(a.indptr + row), e = __ldg(a.indptr + row + 1);
-        if (e - s > a.seg_len) return;                       // handled by its segments
-        accumulate_segment<D, UNROLL>(a, s, e, lane, gmask, acc);
-        epilogue<D, ADAM>(a, row, lane, acc);
+    accumulate_item<D, LANES, UNROLL>(a, start, end, lane, gmask, acc);
+    if (seg_ref < 0) {
+        epilogue<D, LANES, ADAM>(a, row, lane, acc);
         return;
     }
-    const long long seg = gidx - a.n_rows;
-    if (seg >= a.n_segs) return;
-    const int4 s0 = __ldg(a.segs + 2 * seg), s1 = __ldg(a.segs + 2 * seg + 1);
-    const int row = s0.x, start = s0.y, end = s0.z, part = s0.w;
-    const int n_parts = s1.x, slot_base = s1.y, long_id = s1.z;
-    accumulate_segment<D, UNROLL>(a, start, end, lane, gmask, acc);
+    const int4 si = __ldg(a.seginfo + seg_ref);
+    const int part = si.x, n_parts = si.y, slot_base = si.z, long_id = si.w;
     float4* mine = a.partials + (size_t)(slot_base + part) * VEC + lane;
 #pragma unroll
     for (int p = 0; p < VPL; ++p) mine[p * LANES] = acc[p];
@@ -154,16 +156,18 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
     __threadfence();
 #pragma unroll
     for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+#pragma unroll 1
     for (int q = 0; q < n_parts; ++q) {
         const float4* src = a.partials + (size_t)(slot_base + q) * VEC + lane;
 #pragma unroll
         for (int p = 0; p < VPL; ++p) f4_add(acc[p], ld_cg_f4(src + p * LANES));
     }
-    epilogue<D, ADAM>(a, row, lane, acc);
+    epilogue<D, LANES, ADAM>(a, row, lane, acc);
     if (lane == 0) a.counters[long_id] = 0;                  // ready for the next launch
 }
 
 // ---- plan kernels -------------------------------------------------------------------------
+// ws ints: [0]=long cursor, [1]=segment cursor, then bins[seg_len+1], offsets[seg_len+1], cursors[seg_len+1]
 __global__ void plan_count_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* counts) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
@@ -174,33 +178,58 @@ __global__ void plan_count_kernel(const int* __restrict__ indptr, int n_rows, in
     }
 }
 
-__global__ void plan_fill_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* segs, int* cursor) {
+__device__ __forceinline__ void split_row(int deg, int seg_len, int& n_parts, int& len) {
+    n_parts = (deg + seg_len - 1) / seg_len;
+    len = (deg + n_parts - 1) / n_parts;                     // equal-length parts, never empty
+}
+
+__global__ void plan_hist_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* bins) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    const int s = indptr[r], deg = indptr[r + 1] - s;
-    if (deg <= seg_len) return;
-    const int n_parts = (deg + seg_len - 1) / seg_len;
-    const int len = (deg + n_parts - 1) / n_parts;          // equal-length parts
-    const int long_id = atomicAdd(cursor + 0, 1);
-    const int slot_base = atomicAdd(cursor + 1, n_parts);
+    const int deg = indptr[r + 1] - indptr[r];
+    if (deg <= seg_len) { atomicAdd(bins + deg, 1); return; }
+    int n_parts, len; split_row(deg, seg_len, n_parts, len);
     for (int p = 0; p < n_parts; ++p) {
-        int* o = segs + (size_t)(slot_base + p) * 8;
-        const int b = s + p * len;
-        int e = b + len; if (e > s + deg) e = s + deg;
-        o[0] = r; o[1] = b; o[2] = e; o[3] = p; o[4] = n_parts; o[5] = slot_base; o[6] = long_id; o[7] = 0;
+        const int l = min(len, deg - p * len);
+        atomicAdd(bins + l, 1);
     }
 }
 
-template <int D, bool ADAM>
-static int launch_spmm(const SpmmArgs& a, cudaStream_t st) {
-    constexpr int LANES = Geo<D>::LANES;
-    constexpr int GROUPS = kThreads / LANES;
-    constexpr int UNROLL = (LANES >= 8) ? 8 : 4;
-    const long long groups = (long long)a.n_rows + a.n_segs;
-    if (groups == 0) return 0;
-    const long long blocks = (groups + GROUPS - 1) / GROUPS;
+// offsets[l] = number of items longer than l  (descending-length layout)
+__global__ void plan_offsets_kernel(const int* __restrict__ bins, int seg_len, int* offsets) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int run = 0;
+    for (int l = seg_len; l >= 0; --l) { offsets[l] = run; run += bins[l]; }
+}
+
+__global__ void plan_scatter_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, const int* __restrict__ offsets,
+                                    int* cursors, int* long_cursor, int4* items, int4* seginfo) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int s = indptr[r], deg = indptr[r + 1] - s;
+    if (deg <= seg_len) {
+        const int pos = offsets[deg] + atomicAdd(cursors + deg, 1);
+        items[pos] = make_int4(r, s, s + deg, -1);
+        return;
+    }
+    int n_parts, len; split_row(deg, seg_len, n_parts, len);
+    const int long_id = atomicAdd(long_cursor + 0, 1);
+    const int slot_base = atomicAdd(long_cursor + 1, n_parts);
+    for (int p = 0; p < n_parts; ++p) {
+        const int b = s + p * len, l = min(len, deg - p * len);
+        seginfo[slot_base + p] = make_int4(p, n_parts, slot_base, long_id);
+        const int pos = offsets[l] + atomicAdd(cursors + l, 1);
+        items[pos] = make_int4(r, b, b + l, slot_base + p);
+    }
+}
+
+template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB>
+static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
+    constexpr int GROUPS = THREADS / LANES;
+    if (a.n_items == 0) return 0;
+    const long long blocks = ((long long)a.n_items + GROUPS - 1) / GROUPS;
     if (blocks > 0x7fffffffLL) return fail("spmm: grid too large");
-    spmm_kernel<D, UNROLL, ADAM><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+    spmm_kernel<D, LANES, UNROLL, ADAM, THREADS, MINB><<<(unsigned)blocks, THREADS, 0, st>>>(a);
     LGCN_CHECK_LAUNCH("spmm_kernel");
     return 0;
 }
@@ -208,11 +237,30 @@ static int launch_spmm(const SpmmArgs& a, cudaStream_t st) {
 template <bool ADAM>
 static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
     switch (d) {
-        case 16:  return launch_spmm<16, ADAM>(a, st);
-        case 32:  return launch_spmm<32, ADAM>(a, st);
-        case 64:  return launch_spmm<64, ADAM>(a, st);
-        case 128: return launch_spmm<128, ADAM>(a, st);
-        case 256: return launch_spmm<256, ADAM>(a, st);
+        case 16:  return launch_cfg<16, 4, 4, ADAM, 128, 8>(a, st);
+        case 32:  return launch_cfg<32, 4, 4, ADAM, 128, 8>(a, st);
+        case 64:
+            if (!ADAM) switch (g_variant) {                       // tuning variants, same results
+                case 1:  return launch_cfg<64, 16, 8, false, 128, 8>(a, st);
+                case 2:  return launch_cfg<64, 16, 4, false, 128, 8>(a, st);
+                case 3:  return launch_cfg<64, 8, 4, false, 64, 16>(a, st);
+                case 4:  return launch_cfg<64, 8, 4, false, 256, 4>(a, st);
+                case 5:  return launch_cfg<64, 4, 2, false, 128, 8>(a, st);
+                case 6:  return launch_cfg<64, 4, 4, false, 128, 4>(a, st);
+                case 7:  return launch_cfg<64, 8, 2, false, 128, 10>(a, st);
+                case 8:  return launch_cfg<64, 4, 2, false, 64, 16>(a, st);
+                case 9:  return launch_cfg<64, 8, 8, false, 128, 4>(a, st);
+                default: break;
+            }
+            return launch_cfg<64, 8, 4, ADAM, 128, 8>(a, st);
+        case 128:
+            if (!ADAM && g_variant == 1) return launch_cfg<128, 32, 8, false, 128, 8>(a, st);
+            if (!ADAM && g_variant == 2) return launch_cfg<128, 8, 2, false, 128, 8>(a, st);
+            return launch_cfg<128, 16, 4, ADAM, 128, 8>(a, st);
+        case 256:
+            if (!ADAM && g_variant == 1) return launch_cfg<256, 16, 2, false, 128, 8>(a, st);
+            if (!ADAM && g_variant == 2) return launch_cfg<256, 32, 2, false, 128, 8>(a, st);
+            return launch_cfg<256, 32, 4, ADAM, 128, 8>(a, st);
         default:  return fail("spmm: d=%d unsupported (16,32,64,128,256)", d);
     }
 }
@@ -220,12 +268,12 @@ static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
 static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices, const float* vals,
                      int32_t n_rows, int32_t d, const float* X, float* Y, float alpha, float beta,
                      const float* const* z_host, int32_t nz, const lgcn_spmm_plan_t* plan) {
-    LGCN_CHECK_ARG(indptr && X, "spmm: null indptr/X");
+    LGCN_CHECK_ARG(X, "spmm: null X");
     LGCN_CHECK_ARG(n_rows >= 0, "spmm: n_rows < 0");
     LGCN_CHECK_ARG(nz >= 0 && nz <= LGCN_MAX_Z, "spmm: nz=%d out of range (max %d)", nz, LGCN_MAX_Z);
     LGCN_CHECK_ARG(nz == 0 || z_host, "spmm: nz>0 but z_host is null");
     LGCN_CHECK_ARG(((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0, "spmm: X/Y must be 16-byte aligned");
-    a.indptr = indptr; a.indices = indices; a.vals = vals; a.n_rows = n_rows;
+    a.indptr = indptr; a.indices = indices; a.vals = vals;
     a.X = reinterpret_cast<const float4*>(X); a.Y = reinterpret_cast<float4*>(Y);
     a.alpha = alpha; a.beta = beta; a.nz = nz;
     for (int t = 0; t < LGCN_MAX_Z; ++t) {
@@ -233,14 +281,16 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
         LGCN_CHECK_ARG(t >= nz || (z_host[t] && ((uintptr_t)z_host[t] % 16) == 0), "spmm: z[%d] null or misaligned", t);
     }
     if (plan) {
-        LGCN_CHECK_ARG(plan->seg_len > 0, "spmm: plan.seg_len must be > 0");
-        LGCN_CHECK_ARG(plan->n_segs == 0 || (plan->segs && plan->counters && plan->partials), "spmm: plan buffers missing");
+        LGCN_CHECK_ARG(plan->n_items >= 0 && (plan->n_items == 0 || plan->items), "spmm: plan.items missing");
+        LGCN_CHECK_ARG(((uintptr_t)plan->items % 16) == 0 && ((uintptr_t)plan->seginfo % 16) == 0, "spmm: plan arrays must be 16-byte aligned");
+        LGCN_CHECK_ARG(plan->n_segs == 0 || (plan->seginfo && plan->counters && plan->partials), "spmm: plan segment buffers missing");
         LGCN_CHECK_ARG(plan->n_segs == 0 || plan->d_max >= d, "spmm: plan.d_max=%d < d=%d", plan->d_max, d);
-        a.seg_len = plan->seg_len; a.n_segs = plan->n_segs;
-        a.segs = reinterpret_cast<const int4*>(plan->segs); a.counters = plan->counters;
-        a.partials = reinterpret_cast<float4*>(plan->partials); a.row_order = plan->row_order;
+        a.items = reinterpret_cast<const int4*>(plan->items); a.n_items = plan->n_items;
+        a.seginfo = reinterpret_cast<const int4*>(plan->seginfo);
+        a.counters = plan->counters; a.partials = reinterpret_cast<float4*>(plan->partials);
     } else {
-        a.seg_len = 0x7fffffff; a.n_segs = 0; a.segs = nullptr; a.counters = nullptr; a.partials = nullptr; a.row_order = nullptr;
+        LGCN_CHECK_ARG(indptr || n_rows == 0, "spmm: indptr is null and no plan was given");
+        a.items = nullptr; a.n_items = n_rows; a.seginfo = nullptr; a.counters = nullptr; a.partials = nullptr;
     }
     a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr;
     return 0;
@@ -249,6 +299,8 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
 }  // namespace lgcn
 
 using namespace lgcn;
+
+extern "C" int lgcn_debug_spmm_variant(int variant) { const int old = g_variant; g_variant = variant; return old; }
 
 extern "C" int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
                                     int32_t* counts_out, lgcn_stream_t stream) {
@@ -260,13 +312,31 @@ extern "C" int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32
     return 0;
 }
 
+extern "C" size_t lgcn_spmm_plan_workspace_bytes(int32_t seg_len) {
+    if (seg_len <= 0) return 0;
+    return sizeof(int32_t) * (4 + 3 * ((size_t)seg_len + 1));
+}
+
 extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
-                                   int32_t* segs, int32_t* cursor, lgcn_stream_t stream) {
-    LGCN_CHECK_ARG(indptr && segs && cursor && seg_len > 0 && n_rows >= 0, "spmm_plan_fill: bad arguments");
-    LGCN_CHECK_ARG(((uintptr_t)segs % 16) == 0, "spmm_plan_fill: segs must be 16-byte aligned");
+                                   int32_t* items_out, int32_t* seginfo_out,
+                                   void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(indptr && items_out && seg_len > 0 && n_rows >= 0, "spmm_plan_fill: bad arguments");
+    LGCN_CHECK_ARG(seg_len <= (1 << 20), "spmm_plan_fill: seg_len too large");
+    LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_spmm_plan_workspace_bytes(seg_len), "spmm_plan_fill: workspace too small");
+    LGCN_CHECK_ARG(((uintptr_t)items_out % 16) == 0 && ((uintptr_t)seginfo_out % 16) == 0, "spmm_plan_fill: outputs must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    if (n_rows > 0) plan_fill_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(indptr, n_rows, seg_len, segs, cursor);
-    LGCN_CHECK_LAUNCH("plan_fill_kernel");
+    int* ws = static_cast<int*>(workspace);
+    int* long_cursor = ws; int* bins = ws + 4; int* offsets = bins + seg_len + 1; int* cursors = offsets + seg_len + 1;
+    cudaMemsetAsync(workspace, 0, lgcn_spmm_plan_workspace_bytes(seg_len), st);
+    if (n_rows == 0) return 0;
+    const unsigned nb = (n_rows + 255) / 256;
+    plan_hist_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, bins);
+    LGCN_CHECK_LAUNCH("plan_hist_kernel");
+    plan_offsets_kernel<<<1, 32, 0, st>>>(bins, seg_len, offsets);
+    LGCN_CHECK_LAUNCH("plan_offsets_kernel");
+    plan_scatter_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, offsets, cursors, long_cursor,
+                                            reinterpret_cast<int4*>(items_out), reinterpret_cast<int4*>(seginfo_out));
+    LGCN_CHECK_LAUNCH("plan_scatter_kernel");
     return 0;
 }
 

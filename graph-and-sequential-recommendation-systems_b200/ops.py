@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-DEFAULT_SEG_LEN = 512
+DEFAULT_SEG_LEN = 128
 
 
 def _stream():
@@ -42,7 +42,7 @@ def device_info():
 class CSRGraph:
     """int32 CSR on the device + the SpMM segment plan for its long rows."""
 
-    def __init__(self, indptr, indices, vals, n_cols, deg=None, dinv=None, seg_len=DEFAULT_SEG_LEN, row_order=None):
+    def __init__(self, indptr, indices, vals, n_cols, deg=None, dinv=None, seg_len=DEFAULT_SEG_LEN):
         self.indptr = _need(indptr, torch.int32, "indptr", 1)
         self.indices = _need(indices, torch.int32, "indices", 1)
         self.vals = _need(vals, torch.float32, "vals", 1)
@@ -51,39 +51,45 @@ class CSRGraph:
         self.nnz = indices.numel()
         self.deg, self.dinv = deg, dinv
         self.device = indptr.device
-        self.row_order = None if row_order is None else _need(row_order, torch.int32, "row_order", 1)
         self._build_plan(seg_len)
 
     def _build_plan(self, seg_len):
+        """Degree-binned work items (descending length) + segments of the long rows."""
         lib = _lib.load()
         self.seg_len = int(seg_len)
         counts = torch.zeros(2, dtype=torch.int32, device=self.device)
         _lib.check(lib.lgcn_spmm_plan_count(_p(self.indptr), self.n_rows, self.seg_len, _p(counts), _stream()), "spmm_plan_count")
         n_long, n_segs = (int(v) for v in counts.cpu().tolist())      # one-time setup sync
         self.n_long, self.n_segs = n_long, n_segs
-        self._segs = torch.zeros(max(n_segs, 1) * 8, dtype=torch.int32, device=self.device)
+        self.n_items = self.n_rows - n_long + n_segs
+        self._items = torch.zeros(max(self.n_items, 1) * 4, dtype=torch.int32, device=self.device)
+        self._seginfo = torch.zeros(max(n_segs, 1) * 4, dtype=torch.int32, device=self.device)
         self._counters = torch.zeros(max(n_long, 1), dtype=torch.int32, device=self.device)
-        if n_segs:
-            cursor = torch.zeros(2, dtype=torch.int32, device=self.device)
-            _lib.check(lib.lgcn_spmm_plan_fill(_p(self.indptr), self.n_rows, self.seg_len, _p(self._segs), _p(cursor), _stream()), "spmm_plan_fill")
+        ws_bytes = lib.lgcn_spmm_plan_workspace_bytes(self.seg_len)
+        ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.int32, device=self.device)
+        _lib.check(lib.lgcn_spmm_plan_fill(_p(self.indptr), self.n_rows, self.seg_len, _p(self._items), _p(self._seginfo),
+                                           _p(ws), ws.numel() * 4, _stream()), "spmm_plan_fill")
         self._partials = None
         self._plan = None
+        self.use_plan = True
 
     def plan(self, d):
+        if not self.use_plan:
+            return None
         if self._plan is None or self._plan.d_max < d:
             self._partials = torch.empty(max(self.n_segs, 1) * d, dtype=torch.float32, device=self.device)
             pl = _lib.SpmmPlan()
-            pl.seg_len, pl.n_long, pl.n_segs, pl.d_max = self.seg_len, self.n_long, self.n_segs, d
-            pl.segs = self._segs.data_ptr()
+            pl.seg_len, pl.n_long, pl.n_segs, pl.n_items, pl.d_max = self.seg_len, self.n_long, self.n_segs, self.n_items, d
+            pl.items = self._items.data_ptr()
+            pl.seginfo = self._seginfo.data_ptr()
             pl.counters = self._counters.data_ptr()
             pl.partials = self._partials.data_ptr()
-            pl.row_order = None if self.row_order is None else self.row_order.data_ptr()
             self._plan = pl
         return self._plan
 
-    def set_row_order(self, row_order):
-        self.row_order = None if row_order is None else _need(row_order, torch.int32, "row_order", 1)
-        self._plan = None
+    def _plan_ref(self, d):
+        pl = self.plan(d)
+        return None if pl is None else byref(pl)
 
     def rows(self, begin, end, seg_len=None):
         """Row block [begin,end) as its own CSRGraph (indptr rebased; shares indices/vals storage)."""
@@ -166,7 +172,7 @@ def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None):
     for z in (zs or []):
         _need(z, torch.float32, "z", 2)
     _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
-                                 float(alpha), float(beta), arr, nz, byref(g.plan(d)), _stream()), "spmm")
+                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _stream()), "spmm")
     return Y
 
 
@@ -179,7 +185,7 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None):
     arr, nz = _z_array(zs)
     _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                       float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
-                                      byref(g.plan(d)), _stream()), "spmm_adam")
+                                      g._plan_ref(d), _stream()), "spmm_adam")
 
 
 def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
@@ -197,7 +203,7 @@ def adam_tick(scalars):
 
 
 def adam_step_count(scalars):
-    return int(scalars[6].item())
+    return int(scalars[8].item())
 
 
 def adam(P, M, V, G, scalars):

@@ -47,7 +47,7 @@ config = {
     # extras understood by this implementation only (all optional)
     'deterministic': False,     # K2 owner-computes reduction instead of float atomics
     'cuda_graph': True,         # capture the fused training step in a CUDA graph
-    'spmm_seg_len': 512,        # degree-binning threshold of K1
+    'spmm_seg_len': 128,        # degree-binning threshold of K1
 }
 
 seed = 2020

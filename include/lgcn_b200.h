@@ -76,40 +76,54 @@ int lgcn_coo_to_csr(const int64_t* rows, const int64_t* cols, int64_t nnz, int32
  * X is indexed by GLOBAL column id; Y, Z_t, P, M, V by LOCAL row i (callers pre-offset the
  * pointers for a row partition).  d in {16,32,64,128,256}.
  *
- * Rows longer than seg_len are cut into segments by lgcn_spmm_plan_*; their partial sums meet in
- * plan->partials and the last-arriving segment runs the epilogue (deterministic summation order).
+ * Scheduling plan (degree-binned load balancing).  lgcn_spmm_plan_* turn the rows into WORK ITEMS
+ * {row, start, end, seg_ref}: a row with at most seg_len non-zeros is one item, a longer row is cut into
+ * equal segments whose partial sums meet in plan->partials (the last-arriving segment adds them in part
+ * order and runs the epilogue: deterministic, no float atomics).  Items are laid out by DESCENDING
+ * length.  plan_host == NULL runs one item per row in natural order without segmentation.
  * -------------------------------------------------------------------------------------------*/
 typedef struct {
-    int32_t seg_len;          /* rows with more non-zeros than this are segmented              */
-    int32_t n_long;           /* number of segmented rows                                       */
-    int32_t n_segs;           /* total number of segments                                       */
-    int32_t d_max;            /* partials holds n_segs*d_max floats                             */
-    const int32_t* segs;      /* int32[n_segs*8]: row,start,end,part,n_parts,slot_base,long_id,0 */
-    int32_t* counters;        /* int32[n_long], zero-initialised, self-resetting                */
-    float* partials;          /* float32[n_segs*d_max]                                          */
-    const int32_t* row_order; /* optional int32[n_rows] processing order (NULL = natural)       */
+    int32_t seg_len;          /* rows with more non-zeros than this are segmented                 */
+    int32_t n_long;           /* number of segmented rows                                          */
+    int32_t n_segs;           /* total number of segments                                          */
+    int32_t n_items;          /* n_rows - n_long + n_segs                                          */
+    int32_t d_max;            /* partials holds n_segs*d_max floats                                */
+    int32_t pad;
+    const int32_t* items;     /* int32[4*n_items]: row,start,end,seg_ref(-1 = whole row), 16-B aligned */
+    const int32_t* seginfo;   /* int32[4*n_segs]: part,n_parts,slot_base,long_id                    */
+    int32_t* counters;        /* int32[n_long], zero-initialised, self-resetting                   */
+    float* partials;          /* float32[n_segs*d_max]                                             */
 } lgcn_spmm_plan_t;
 
 /* counts_out int32[2] = {n_long, n_segs} (device) */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
                          int32_t* counts_out, lgcn_stream_t stream);
-/* fills segs int32[n_segs*8]; cursor int32[2] must be zero on entry */
+size_t lgcn_spmm_plan_workspace_bytes(int32_t seg_len);
+/* fills items_out int32[4*n_items] and seginfo_out int32[4*n_segs] */
 int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
-                        int32_t* segs, int32_t* cursor, lgcn_stream_t stream);
+                        int32_t* items_out, int32_t* seginfo_out,
+                        void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 
-typedef struct {           /* device-resident Adam scalars, written by lgcn_adam_tick */
-    float step_size;       /* lr / (1 - beta1^t)                   */
-    float bc2_sqrt;        /* sqrt(1 - beta2^t)                    */
-    float beta1, beta2, eps;
-    float lr;
-    int32_t step;          /* t                                    */
-    int32_t pad;
+typedef struct {           /* device-resident Adam scalars, written by lgcn_adam_init / lgcn_adam_tick */
+    float step_size;       /* (float)(lr / (1 - beta1^t)), computed in double like torch's Python scalars */
+    float bc2_sqrt;        /* (float)sqrt(1 - beta2^t)                                                  */
+    float beta1, beta2;    /* (float)beta                                                               */
+    float w1, w2;          /* (float)(1 - beta) with the subtraction done in double                     */
+    float eps;
+    float pad0;
+    int32_t step;          /* t */
+    int32_t pad1;
+    double lr_d, beta1_d, beta2_d;
 } lgcn_adam_scalars_t;
 
 int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                   int32_t n_rows, int32_t d, const float* X, float* Y,
                   float alpha, float beta, const float* const* z_host, int32_t nz,
                   const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream);
+
+/* profiling hook: selects a tuning variant (unroll / CTA size / occupancy cap / L1 policy) of the d=64
+ * plain kernel; 0 = shipped configuration.  Returns the previous value.  Results are identical. */
+int lgcn_debug_spmm_variant(int variant);
 
 int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                        int32_t n_rows, int32_t d, const float* X, float* Y /* may be NULL */,
@@ -123,7 +137,7 @@ int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const floa
  * lgcn_adam_tick: step += 1 and refresh the bias-correction scalars on the device (double
  * arithmetic, like torch's Python-side scalars).  lgcn_adam_f32: dense update of n floats.
  * -------------------------------------------------------------------------------------------*/
-int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, float lr, float beta1, float beta2, float eps,
+int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, double lr, double beta1, double beta2, double eps,
                    int32_t step, lgcn_stream_t stream);
 int lgcn_adam_tick(lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream);
 int lgcn_adam_f32(float* P, float* M, float* V, const float* G, int64_t n,

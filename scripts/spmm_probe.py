@@ -1,0 +1,115 @@
+"""GPU probe: times K1 variants (and cuSPARSE via torch.sparse.mm as the library bar), K3 and K4 with CUDA
+events, cold L2 (read-flush of a 512 MiB buffer between launches).  Writes gpurun_out/probe.jsonl."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lgcn_b200 as lg   # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out", "probe.jsonl")
+os.makedirs(os.path.dirname(OUT), exist_ok=True)
+flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+lib = lg._lib.load()
+
+
+def flush():
+    flush_buf.view(torch.int64).sum()          # read-flush: leaves clean lines, evicts everything else
+
+
+def time_fn(fn, reps=15, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def emit(**kw):
+    with open(OUT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+    print(kw, flush=True)
+
+
+def probe_spmm(name, variants, ds=(64,), seg_lens=(64,)):
+    gr = lg.synth.make_graph(name)
+    tu = torch.from_numpy(gr['train_user']).cuda(); ti = torch.from_numpy(gr['train_item']).cuda()
+    for seg_len in seg_lens:
+        g = lg.ops.csr_build(tu, ti, gr['n_users'], gr['m_items'], seg_len=seg_len)
+        N = g.n_rows
+        for d in ds:
+            X = (0.1 * torch.randn((N, d), device="cuda")).contiguous(); Y = torch.empty_like(X)
+            alg = g.algorithmic_bytes(d); gather = 8 * g.nnz + 4 * (N + 1) + 4 * g.nnz * d + 4 * N * d
+            for v in (variants if d == 64 else [0, 1, 2]):
+                lib.lgcn_debug_spmm_variant(v)
+                med, best = time_fn(lambda: lg.ops.spmm(g, X, Y))
+                emit(kind="spmm", graph=name, d=d, seg_len=seg_len, variant=v, order="plan", us=med, us_best=best,
+                     alg_gbs=alg / med / 1e3, gather_gbs=gather / med / 1e3, n_long=g.n_long, n_segs=g.n_segs)
+            lib.lgcn_debug_spmm_variant(0)
+            if seg_len == seg_lens[0]:
+                g.use_plan = False
+                med, best = time_fn(lambda: lg.ops.spmm(g, X, Y))
+                emit(kind="spmm", graph=name, d=d, seg_len=seg_len, variant=0, order="noplan", us=med, us_best=best,
+                     alg_gbs=alg / med / 1e3, gather_gbs=gather / med / 1e3)
+                g.use_plan = True
+                A = g.to_torch_sparse_csr()
+                med, best = time_fn(lambda: torch.sparse.mm(A, X))
+                emit(kind="cusparse_csr", graph=name, d=d, us=med, us_best=best, alg_gbs=alg / med / 1e3)
+                for _ in range(3):
+                    lg.ops.spmm(g, X, Y)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    lg.ops.spmm(g, X, Y)
+                e1.record(); torch.cuda.synchronize()
+                emit(kind="spmm_warm", graph=name, d=d, us=e0.elapsed_time(e1) * 1e3 / 20)
+    return gr, g
+
+
+def probe_eval_and_build(name):
+    gr = lg.synth.make_graph(name)
+    tu = torch.from_numpy(gr['train_user']).cuda(); ti = torch.from_numpy(gr['train_item']).cuda()
+    med, best = time_fn(lambda: lg.ops.csr_build(tu, ti, gr['n_users'], gr['m_items']), reps=5, warm=1)
+    emit(kind="csr_build_incl_alloc_and_sync", graph=name, us=med, us_best=best, E=int(tu.numel()))
+    g = lg.ops.csr_build(tu, ti, gr['n_users'], gr['m_items'])
+    nu, ni = gr['n_users'], gr['m_items']
+    out = (0.1 * torch.randn((nu + ni, 64), device="cuda")).contiguous()
+    for Bt in (100, 2048, nu):
+        users = torch.arange(Bt, device="cuda")
+        med, best = time_fn(lambda: lg.ops.score_topk(out[:nu], out[nu:], users, 20, g.indptr, g.indices, nu), reps=5, warm=1)
+        fl = 2.0 * Bt * ni * 64
+        emit(kind="score_topk", graph=name, Bt=Bt, us=med, tflops=fl / med / 1e6)
+    users = torch.arange(2048, device="cuda")
+    med, best = time_fn(lambda: torch.topk(out[:nu][users] @ out[nu:].T, 20), reps=5, warm=1)
+    emit(kind="torch_matmul_topk_nomask", graph=name, Bt=2048, us=med)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "spmm"):
+        probe_spmm("yelp2018", list(range(0, 10)), seg_lens=(128, 64, 256))
+        probe_spmm("amazon-book", [0, 3, 5, 7], ds=(64, 128, 256), seg_lens=(128, 256))
+        probe_spmm("gowalla", [0, 5])
+    if which in ("all", "eval"):
+        probe_eval_and_build("yelp2018")
+        probe_eval_and_build("amazon-book")
+    if which == "ncu":
+        # short run for `ncu -k regex:spmm_kernel`: 3 cold launches of the shipped kernel on yelp2018
+        gr = lg.synth.make_graph("yelp2018")
+        g = lg.ops.csr_build(torch.from_numpy(gr['train_user']).cuda(), torch.from_numpy(gr['train_item']).cuda(), gr['n_users'], gr['m_items'])
+        X = (0.1 * torch.randn((g.n_rows, 64), device="cuda")).contiguous(); Y = torch.empty_like(X)
+        v = int(os.environ.get("SPMM_VARIANT", "0")); lib.lgcn_debug_spmm_variant(v)
+        for _ in range(3):
+            flush(); lg.ops.spmm(g, X, Y)
+        torch.cuda.synchronize()
+        print("ncu target done")

@@ -31,7 +31,7 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def build(lg, tu, ti, nu, ni, seg_len=512):
+def build(lg, tu, ti, nu, ni, seg_len=128):
     return lg.ops.csr_build(dev(np.asarray(tu, np.int64)), dev(np.asarray(ti, np.int64)), nu, ni, seg_len=seg_len)
 
 
@@ -100,7 +100,7 @@ def test_coo_to_csr(lg, orc):
 
 # ------------------------------------------------------------------------------------ K1
 @pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
-@pytest.mark.parametrize("seg_len", [512, 8])
+@pytest.mark.parametrize("seg_len", [128, 8])
 def test_spmm_vs_oracle(lg, orc, d, seg_len):
     rng = np.random.default_rng(d + seg_len)
     nu, ni = 700, 450
@@ -153,12 +153,21 @@ def test_spmm_full_size_properties(lg):
     # against torch's own CSR SpMM (cuSPARSE) on the same matrix
     ref = torch.sparse.mm(g.to_torch_sparse_csr(), x)
     assert rel_err(Ax.cpu().numpy(), ref.cpu().numpy()) < TOL
-    # row order hint only changes scheduling
-    order = torch.argsort(torch.diff(g.indptr), descending=True).to(torch.int32)
-    g.set_row_order(order)
+    # the plan only changes scheduling: without it (one item per row, natural order) every row that was
+    # not segmented is bit-identical, segmented rows agree to rounding
+    g.use_plan = False
     Ax2 = torch.empty_like(x); lg.ops.spmm(g, x, Ax2)
-    g.set_row_order(None)
-    assert torch.equal(Ax, Ax2)
+    g.use_plan = True
+    short = (torch.diff(g.indptr) <= g.seg_len)
+    assert torch.equal(Ax[short], Ax2[short])
+    assert rel_err(Ax.cpu().numpy(), Ax2.cpu().numpy()) < TOL
+    # every tuning variant of the d=64 kernel computes the same thing
+    lib = lg._lib.load()
+    for v in range(1, 10):
+        lib.lgcn_debug_spmm_variant(v)
+        Av = torch.empty_like(x); lg.ops.spmm(g, x, Av)
+        lib.lgcn_debug_spmm_variant(0)
+        assert rel_err(Av.cpu().numpy(), Ax.cpu().numpy()) < 1e-6, v
 
 
 # ------------------------------------------------------------------------------------ Adam
@@ -206,7 +215,7 @@ def test_spmm_adam_epilogue_equals_spmm_then_adam(lg):
 def _bpr_case(rng, nu, ni, d, B):
     out = rng.normal(0, 0.3, (nu + ni, d)).astype(np.float32)
     users = rng.integers(0, nu, B); pos = rng.integers(0, ni, B); neg = rng.integers(0, ni, B)
-    users[: B // 8] = users[0]; pos[: B // 8] = pos[1]          # heavy row collisions (atomics / owner-computes)
+    users[: B // 8] = users[0]; pos[: B // 8] = pos[min(1, B - 1)]          # heavy row collisions (atomics / owner-computes)
     return out, users.astype(np.int64), pos.astype(np.int64), neg.astype(np.int64)
 
 
