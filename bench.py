@@ -59,7 +59,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -176,7 +176,12 @@ def run_ours(args):
     perm = np.arange(S.shape[0]); np.random.shuffle(perm)
     S_host = torch.from_numpy(np.ascontiguousarray(S[perm, :3].T)).to(torch.int64).pin_memory()
     n_batches = S_host.shape[1] // B
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda").view(torch.int64)
+
+    def flush_l2():
+        # read 512 MiB (4x the 126 MB L2): everything the step touched is evicted and the lines left behind are
+        # clean, so the timed kernels neither hit stale data nor pay for write-backs of the flush itself
+        flush.sum()
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -190,7 +195,7 @@ def run_ours(args):
         barrier()
         wall0 = time.perf_counter()
         for i in range(K):
-            flush.zero_()
+            flush_l2()
             evs[i][0].record()
             step_fn(i)
             evs[i][1].record()
@@ -247,7 +252,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}-shape synthetic graph ({ds.n_users} users x {ds.m_items} items, "
                                    f"{ds.trainDataSize} train edges, nnz {csr.nnz}), LightGCN L=3 d=64, BPR batch {B} per step"
                                    + (f" per rank ({mode})" if mode else ""),
-                       "l2": "flushed between timed steps (256 MiB write outside the event brackets)",
+                       "l2": "flushed between timed steps (512 MiB read outside the event brackets)",
                        "parallelism": mode or "single", "cuda_graph": bool(eng.use_graph)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 + 3 * B * 8, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / K, "wall_ms_per_step": 1e3 * wall_e2e / K},
@@ -270,7 +275,7 @@ def run_ours(args):
         use_graph = eng.use_graph
         eng.use_graph = False
         for i in range(min(K, 20)):
-            flush.zero_()
+            flush_l2()
             lo = (i % n_batches) * B
             eng.step(S_host[0, lo:lo + B], S_host[1, lo:lo + B], S_host[2, lo:lo + B])
         torch.cuda.synchronize()
