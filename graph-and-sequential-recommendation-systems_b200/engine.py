@@ -292,6 +292,8 @@ class Engine:
     def step(self, users, pos, neg, B_global=0):
         """One BPR step on a batch given as host or device int64 tensors. Returns nothing; the loss is
         in self.loss_out (device).  Host batches cost one H2D copy."""
+        if self.dist_mode == 'dp' and not B_global:
+            B_global = int(users.numel()) * self.world          # equal shards unless the caller says otherwise
         self._stage_batch(users, pos, neg, B_global)
         self._run('direct', self.bu, self.bp, self.bn, self.ctl)
         self._host_step += 1
