@@ -170,9 +170,9 @@ def run_ours(args):
     model = lg.LightGCN(cfg, ds)
     bpr = lg.utils.BPRLoss(model, cfg)
     eng = model._engine
-    lg.utils.sampler_seed(2020 + (rank if mode == 'dp' else 0))
+    lg.utils.sampler_seed(2020 + (rank if mode in ('dp', 'dp_idx') else 0))
     S = lg.utils.UniformSample_original(ds)
-    np.random.seed(2020 + (rank if mode == 'dp' else 0))
+    np.random.seed(2020 + (rank if mode in ('dp', 'dp_idx') else 0))
     perm = np.arange(S.shape[0]); np.random.shuffle(perm)
     S_host = torch.from_numpy(np.ascontiguousarray(S[perm, :3].T)).to(torch.int64).pin_memory()
     n_batches = S_host.shape[1] // B
@@ -228,7 +228,7 @@ def run_ours(args):
         clocks.start()
     ms_dev, _ = timed_loop(step1)
     clk = clocks.stop() if rank == 0 else None
-    samples_per_step = B * (world if mode == 'dp' else 1)
+    samples_per_step = B * (world if mode in ('dp', 'dp_idx') else 1)
     value = samples_per_step * K / (ms_dev * 1e-3)
 
     # ---- leg 2: end to end through utils.BPRLoss.stageOne with pinned host batches ---------------------
@@ -296,6 +296,7 @@ def run_ours(args):
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "kernel": "spmm_kernel<64>", "algorithmic_bytes_per_launch": alg_bytes,
                             "mean_launch_us": 1e3 * mean_ms, "launches_timed": len(t_ms), "peak_source": peak_src,
+                            "per_launch_us_by_position": [round(1e3 * sum(t_ms[i::6]) / len(t_ms[i::6]), 1) for i in range(6)] if len(t_ms) % 6 == 0 else None,
                             "spmm_share_of_step": (6 * mean_ms) / (ms_dev / K),
                             "l2_gather_gbs": gather_bytes / (mean_ms * 1e-3) / 1e9}
         # ---- evaluation (K3) timing, reported beside the headline -----------------------------------------
@@ -322,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="yelp2018", choices=["gowalla", "yelp2018", "amazon-book", "tiny"])
-    ap.add_argument("--parallel", default="dp", choices=["dp", "rowpart"])
+    ap.add_argument("--parallel", default="dp_idx", choices=["dp_idx", "dp", "rowpart"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

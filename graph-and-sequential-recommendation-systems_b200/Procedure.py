@@ -56,6 +56,8 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
     total_batch = n // bs + 1
     if getattr(bpr, 'fused', False):
         eng = Recmodel._engine
+        if eng.dist_mode is not None:
+            raise NotImplementedError("BPR_train_original drives one GPU; use Engine.step per rank for dist_mode")
         if eng.B_cap != bs:
             eng._alloc_batch(bs)
         eng.set_lr(bpr.opt.param_groups[0]['lr'])

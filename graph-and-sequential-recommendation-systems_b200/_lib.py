@@ -44,7 +44,7 @@ _SIGNATURES = {
     "lgcn_spmm_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                      POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P]),
     "lgcn_spmm_adam_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
-                                          POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P]),
+                                          POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, _P]),
     "lgcn_debug_spmm_variant": (ctypes.c_int, [ctypes.c_int]),
     "lgcn_adam_init": (ctypes.c_int, [_P, c_double, c_double, c_double, c_double, c_int32, _P]),
     "lgcn_adam_tick": (ctypes.c_int, [_P, _P]),
@@ -55,9 +55,14 @@ _SIGNATURES = {
                                         c_int32, _P, c_size_t, _P]),
     "lgcn_bpr_clear_rows": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "lgcn_batch_advance": (ctypes.c_int, [_P, c_int32, _P]),
+    "lgcn_batch_masks": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "lgcn_score_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "lgcn_score_topk": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32,
                                        _P, _P, _P, c_size_t, _P]),
+    "lgcn_score_topk_tc_supported": (ctypes.c_int, [c_int32, c_int32]),
+    "lgcn_score_topk_tc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "lgcn_score_topk_tc": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32,
+                                          _P, _P, _P, _P, _P, c_size_t, _P]),
     "lgcn_score_dense": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_rank_metrics": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P, c_int32, _P, _P]),
     "lgcn_sampler_seed": (None, [c_uint32]),

@@ -234,6 +234,23 @@ __global__ void batch_advance_kernel(int* ctl, int B_cap) {
     ctl[0] = off; ctl[1] = B;
 }
 
+// Row sets a training step can be restricted to (engine.py: dead-row pruning).  One warp per batch entry:
+//   m0 = rows the loss reads (the 3B batch rows), m1 = m0 + their neighbours (rows of X_{L-1} that
+//   out[m0] depends on; also the non-zero rows of the first backward product).
+__global__ void __launch_bounds__(256)
+batch_masks_kernel(const long long* users, const long long* pos, const long long* neg, int B_cap, const int* ctl,
+                   int n_users, const int* __restrict__ indptr, const int* __restrict__ indices, unsigned* m0, unsigned* m1) {
+    const int off = ctl[0];
+    const int B = min(ctl[1], B_cap);
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= 3 * B) return;
+    const int row = (int)(e < B ? users[off + e] : (e < 2 * B ? pos[off + e - B] + n_users : neg[off + e - 2 * B] + n_users));
+    if (lane == 0) { atomicOr(m0 + (row >> 5), 1u << (row & 31)); if (m1) atomicOr(m1 + (row >> 5), 1u << (row & 31)); }
+    if (m1 == nullptr) return;
+    const int s = indptr[row], t = indptr[row + 1];
+    for (int j = s + lane; j < t; j += 32) { const int c = indices[j]; atomicOr(m1 + (c >> 5), 1u << (c & 31)); }
+}
+
 static size_t bpr_blocks(int B_cap, int d) {
     const int vec = d / 4, lanes = vec < 32 ? vec : 32, groups = kBprThreads / lanes;
     return (size_t)(B_cap + groups - 1) / groups;
@@ -323,5 +340,22 @@ extern "C" int lgcn_batch_advance(int32_t* batch_ctl_dev, int32_t B_cap, lgcn_st
     LGCN_CHECK_ARG(batch_ctl_dev && B_cap > 0, "batch_advance: bad arguments");
     batch_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(batch_ctl_dev, B_cap);
     LGCN_CHECK_LAUNCH("batch_advance_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_batch_masks(const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t B_cap,
+                                const int32_t* batch_ctl_dev, int32_t n_users, int32_t n_nodes,
+                                const int32_t* indptr, const int32_t* indices, uint32_t* m0, uint32_t* m1,
+                                lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(users && pos && neg && batch_ctl_dev && m0 && B_cap > 0 && n_nodes > 0, "batch_masks: bad arguments");
+    LGCN_CHECK_ARG(m1 == nullptr || (indptr && indices), "batch_masks: m1 needs the CSR");
+    cudaStream_t st = as_stream(stream);
+    const size_t words = ((size_t)n_nodes + 31) / 32;
+    cudaMemsetAsync(m0, 0, words * 4, st);
+    if (m1) cudaMemsetAsync(m1, 0, words * 4, st);
+    const unsigned blocks = (unsigned)((3LL * B_cap * 32 + 255) / 256);
+    batch_masks_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(users), reinterpret_cast<const long long*>(pos),
+                                               reinterpret_cast<const long long*>(neg), B_cap, batch_ctl_dev, n_users, indptr, indices, m0, m1);
+    LGCN_CHECK_LAUNCH("batch_masks_kernel");
     return 0;
 }

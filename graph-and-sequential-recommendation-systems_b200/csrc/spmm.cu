@@ -38,7 +38,11 @@ struct SpmmArgs {
     const float4* z[LGCN_MAX_Z];
     int* counters; float4* partials;
     float4* P; float4* M; float4* V; const lgcn_adam_scalars_t* sc;   // adam epilogue
+    const unsigned* row_mask;   // optional bitmap: items whose row bit is 0 are skipped (output not written)
+    const unsigned* col_mask;   // optional bitmap: columns whose bit is 0 are known-zero rows of X (never read)
 };
+
+__device__ __forceinline__ bool mask_bit(const unsigned* m, int i) { return (__ldg(m + (i >> 5)) >> (i & 31)) & 1u; }
 
 static int g_variant = 0;      // tuning variant of the d=64 kernels (lgcn_debug_spmm_variant, profiling hook)
 
@@ -86,6 +90,46 @@ __device__ __forceinline__ void accumulate_item(const SpmmArgs& a, int start, in
     }
 }
 
+// Same product when most rows of X are known to be zero (first backward layer: X = G has at most 3B
+// non-zero rows): every lane tests the bitmap for its own column once per chunk, the group ballots, and
+// only the surviving entries are gathered.  Skipped entries contribute exact zeros, so the result is
+// bit-identical to the unmasked kernel.
+template <int D, int LANES, int UNROLL>
+__device__ __forceinline__ void accumulate_item_masked(const SpmmArgs& a, int start, int end, int lane,
+                                                       unsigned gmask, int gshift, float4 (&acc)[D / 4 / LANES]) {
+    constexpr int VEC = D / 4, VPL = VEC / LANES;
+    for (int base = start; base < end; base += LANES) {
+        const int j = base + lane;
+        int c = 0; float v = 0.f; bool keep = false;
+        if (j < end) {
+            c = ld_stream_i32(a.indices + j);
+            keep = mask_bit(a.col_mask, c);
+            if (keep) v = ld_stream_f32(a.vals + j);
+        }
+        unsigned km = __ballot_sync(gmask, keep) >> gshift;
+        if (LANES < 32) km &= (1u << LANES) - 1u;
+        while (km) {
+            float4 x[UNROLL][VPL]; float w[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const bool on = km != 0;
+                const int idx = on ? __ffs(km) - 1 : 0;
+                km &= km - 1;                                   // 0 stays 0
+                const int cc = __shfl_sync(gmask, c, idx, LANES);
+                const float ww = __shfl_sync(gmask, v, idx, LANES);
+                w[u] = on ? ww : 0.f;
+                const float4* src = a.X + (size_t)cc * VEC + lane;
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) x[u][p] = on ? gather_f4(src + p * LANES) : f4_zero();
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) f4_fma(acc[p], w[u], x[u][p]);
+        }
+    }
+}
+
 template <int D, int LANES, bool ADAM>
 __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, const float4 (&acc)[D / 4 / LANES]) {
     constexpr int VEC = D / 4, VPL = VEC / LANES;
@@ -116,7 +160,7 @@ __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, c
     }
 }
 
-template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB>
+template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB, bool MASKED = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_kernel(const __grid_constant__ SpmmArgs a) {
     constexpr int VEC = D / 4, VPL = VEC / LANES;
@@ -134,10 +178,12 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
     } else {
         row = (int)gidx; start = __ldg(a.indptr + row); end = __ldg(a.indptr + row + 1); seg_ref = -1;
     }
+    if (a.row_mask != nullptr && !mask_bit(a.row_mask, row)) return;     // dead row: nobody reads it this step
     float4 acc[VPL];
 #pragma unroll
     for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
-    accumulate_item<D, LANES, UNROLL>(a, start, end, lane, gmask, acc);
+    if constexpr (MASKED) accumulate_item_masked<D, LANES, UNROLL>(a, start, end, lane, gmask, (threadIdx.x & 31) / LANES * LANES, acc);
+    else accumulate_item<D, LANES, UNROLL>(a, start, end, lane, gmask, acc);
     if (seg_ref < 0) {
         epilogue<D, LANES, ADAM>(a, row, lane, acc);
         return;
@@ -229,6 +275,12 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
     if (a.n_items == 0) return 0;
     const long long blocks = ((long long)a.n_items + GROUPS - 1) / GROUPS;
     if (blocks > 0x7fffffffLL) return fail("spmm: grid too large");
+    if (a.col_mask != nullptr) {
+        constexpr int UM = UNROLL < 4 ? UNROLL : 4;
+        spmm_kernel<D, LANES, UM, ADAM, THREADS, MINB, true><<<(unsigned)blocks, THREADS, 0, st>>>(a);
+        LGCN_CHECK_LAUNCH("spmm_kernel<masked>");
+        return 0;
+    }
     spmm_kernel<D, LANES, UNROLL, ADAM, THREADS, MINB><<<(unsigned)blocks, THREADS, 0, st>>>(a);
     LGCN_CHECK_LAUNCH("spmm_kernel");
     return 0;
@@ -267,7 +319,8 @@ static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
 
 static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices, const float* vals,
                      int32_t n_rows, int32_t d, const float* X, float* Y, float alpha, float beta,
-                     const float* const* z_host, int32_t nz, const lgcn_spmm_plan_t* plan) {
+                     const float* const* z_host, int32_t nz, const lgcn_spmm_plan_t* plan,
+                     const uint32_t* row_mask, const uint32_t* col_mask) {
     LGCN_CHECK_ARG(X, "spmm: null X");
     LGCN_CHECK_ARG(n_rows >= 0, "spmm: n_rows < 0");
     LGCN_CHECK_ARG(nz >= 0 && nz <= LGCN_MAX_Z, "spmm: nz=%d out of range (max %d)", nz, LGCN_MAX_Z);
@@ -293,6 +346,7 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
         a.items = nullptr; a.n_items = n_rows; a.seginfo = nullptr; a.counters = nullptr; a.partials = nullptr;
     }
     a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr;
+    a.row_mask = row_mask; a.col_mask = col_mask;
     return 0;
 }
 
@@ -343,9 +397,10 @@ extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_
 extern "C" int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                              int32_t n_rows, int32_t d, const float* X, float* Y,
                              float alpha, float beta, const float* const* z_host, int32_t nz,
-                             const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream) {
+                             const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
+                             lgcn_stream_t stream) {
     SpmmArgs a;
-    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host)) return rc;
+    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask)) return rc;
     LGCN_CHECK_ARG(Y, "spmm: Y is null");
     return dispatch_spmm<false>(d, a, as_stream(stream));
 }
@@ -354,9 +409,10 @@ extern "C" int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices,
                                   int32_t n_rows, int32_t d, const float* X, float* Y,
                                   float alpha, float beta, const float* const* z_host, int32_t nz,
                                   float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
-                                  const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream) {
+                                  const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
+                                  lgcn_stream_t stream) {
     SpmmArgs a;
-    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host)) return rc;
+    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask)) return rc;
     LGCN_CHECK_ARG(P && M && V && scalars_dev, "spmm_adam: null P/M/V/scalars");
     LGCN_CHECK_ARG(((uintptr_t)P % 16) == 0 && ((uintptr_t)M % 16) == 0 && ((uintptr_t)V % 16) == 0, "spmm_adam: P/M/V must be 16-byte aligned");
     a.P = reinterpret_cast<float4*>(P); a.M = reinterpret_cast<float4*>(M); a.V = reinterpret_cast<float4*>(V);

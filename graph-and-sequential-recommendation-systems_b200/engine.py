@@ -16,6 +16,10 @@ L-1 layer buffers (re-used as backward ping-pong), out, G, Adam M/V — (L+4) * 
 
 Multi-GPU (one process per GPU, torch.distributed):
   mode 'dp'       graph replicated, batch sharded, G all-reduced  (weak scaling of the batch)
+  mode 'dp_idx'   same replicas, but the ranks all-gather their 49 KB index batches instead of
+                  all-reducing the 18 MB gradient: G is a function of (out, indices) and out is replicated,
+                  so every rank scatters the global batch itself (K2 is ~10 us).  Same result, and the
+                  compute part stays inside the single-GPU CUDA graph.
   mode 'rowpart'  rows of A partitioned in contiguous nnz-balanced blocks; every layer's output block
                   is all-gathered; K2 runs redundantly on the full batch so no gradient collective is
                   needed; Adam only touches owned rows.
@@ -61,7 +65,7 @@ def shard_batch(n, rank, world):
 
 class Engine:
     def __init__(self, csr, n_users, m_items, d, n_layers, device, *, lr=1e-3, decay=1e-4, B_cap=2048,
-                 deterministic=False, use_graph=True, dist_mode=None, group=None):
+                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True):
         if n_layers > 8:
             raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
         self.csr = csr
@@ -76,7 +80,9 @@ class Engine:
         if dist_mode is not None:
             import torch.distributed as dist
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.use_graph = bool(use_graph) and dist_mode is None
+        self.use_graph = bool(use_graph) and dist_mode in (None, 'dp_idx')
+        if dist_mode == 'dp_idx':
+            self.B_cap = self.B_cap * self.world          # the static batch buffers hold the GLOBAL batch
         N, L = self.N, self.L
         f32 = dict(dtype=torch.float32, device=device)
         self.E0 = torch.zeros((N, d), **f32)
@@ -91,6 +97,10 @@ class Engine:
         self.scalars = ops.adam_scalars(device, self.lr)
         self._host_step = 0
         self.param_epoch = 0
+        # dead-row pruning of the training step (see _enqueue_step): bitmaps over the N nodes
+        self.prune = bool(prune) and dist_mode in (None, 'dp_idx')
+        words = (N + 31) // 32
+        self.m0 = torch.zeros(words, dtype=torch.int32, device=device)
         # row partition
         self.r0, self.r1 = 0, N
         self.bounds = [0, N]
@@ -159,17 +169,19 @@ class Engine:
         """Every rank broadcasts its row block of `buf` (uneven all-gather, in place)."""
         allgather_rows(buf, self.bounds, self.group)
 
-    def _layer(self, X, Y, alpha, beta, zs):
+    def _layer(self, X, Y, alpha, beta, zs, row_mask=None, col_mask=None):
         r0, r1 = self.r0, self.r1
         if self.dist_mode == 'rowpart':
             ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None)
             self._allgather_rows(Y)
         else:
-            ops.spmm(self.csr, X, Y, alpha, beta, zs)
+            ops.spmm(self.csr, X, Y, alpha, beta, zs, row_mask=row_mask, col_mask=col_mask)
 
     # ------------------------------------------------------------------ propagation
-    def forward(self):
-        """out = mean_{k<=L} A^k E0  (reference code/model.py:201-222)."""
+    def forward(self, masks=None):
+        """out = mean_{k<=L} A^k E0  (reference code/model.py:201-222).
+        masks=(m0, m1): only the rows a training step reads are produced — `out` on the batch rows m0, X_{L-1}
+        on m0 + neighbours m1; earlier layers are complete.  The skipped rows are simply not written."""
         L, s = self.L, 1.0 / (self.L + 1)
         if self.dist_mode == 'rowpart':
             self._allgather_rows(self.E0)       # owners publish their updated parameter rows
@@ -178,26 +190,27 @@ class Engine:
             return self.out
         cur = self.E0
         for k in range(L - 1):
-            self._layer(cur, self.X[k], 1.0, 0.0, None)
+            self._layer(cur, self.X[k], 1.0, 0.0, None, row_mask=masks[1] if (masks and masks[1] is not None and k == L - 2) else None)
             cur = self.X[k]
-        self._layer(cur, self.out, s, s, [self.E0] + self.X[:L - 1])
+        self._layer(cur, self.out, s, s, [self.E0] + self.X[:L - 1], row_mask=masks[0] if masks else None)
         return self.out
 
-    def _backward_chain(self, G, last):
-        """g_0 = dL/dE0 given G = dL/dout.  `last(X, alpha, beta, zs)` runs the final product."""
+    def _backward_chain(self, G, last, g_rows=None):
+        """g_0 = dL/dE0 given G = dL/dout.  `last(X, alpha, beta, zs, col_mask)` runs the final product.
+        g_rows: bitmap of the rows of G that can be non-zero (the first product never reads the others)."""
         L, s = self.L, 1.0 / (self.L + 1)
         if L == 1:
-            return last(G, s, s, [G])
+            return last(G, s, s, [G], g_rows)
         bufs = self.X if L >= 3 else [self.X[0], None]
         if L >= 3 and len(bufs) < 2:
             raise RuntimeError("internal: missing ping-pong buffers")
         cur = bufs[0]
-        self._layer(G, cur, s, s, [G])
+        self._layer(G, cur, s, s, [G], col_mask=g_rows)
         for _ in range(L - 2):
             nxt = bufs[1] if cur is bufs[0] else bufs[0]
             self._layer(cur, nxt, 1.0, s, [G])
             cur = nxt
-        return last(cur, 1.0, s, [G])
+        return last(cur, 1.0, s, [G], None)
 
     def backward_to(self, G, grad_out):
         """grad_out (N,d) = dL/dE0 for an arbitrary dense G (generic autograd path)."""
@@ -207,12 +220,12 @@ class Engine:
         if self.dist_mode == 'rowpart':
             r0, r1 = self.r0, self.r1
 
-            def last(X, alpha, beta, zs):
+            def last(X, alpha, beta, zs, col_mask):
                 ops.spmm(self.local, X, grad_out[r0:r1], alpha, beta, [z[r0:r1] for z in zs])
                 self._allgather_rows(grad_out)
         else:
-            def last(X, alpha, beta, zs):
-                ops.spmm(self.csr, X, grad_out, alpha, beta, zs)
+            def last(X, alpha, beta, zs, col_mask):
+                ops.spmm(self.csr, X, grad_out, alpha, beta, zs, col_mask=col_mask)
         self._backward_chain(G, last)
         return grad_out
 
@@ -238,9 +251,18 @@ class Engine:
 
     def _enqueue_step(self, users, pos, neg, ctl):
         """Everything between 'batch is on the device' and 'loss_out is written'."""
-        N, s = self.N, 1.0 / (self.L + 1)
         ops.adam_tick(self.scalars)
-        self.forward()
+        masks = None
+        if self.prune:
+            # Dead-row pruning: the loss reads `out` only on the <= 3B batch rows (bitmap m0), so the last forward
+            # layer is evaluated there and nowhere else.  Same values as the full pass on every row that is read;
+            # the other rows of `out` are not consumed before the next step overwrites them.  (Measured on the
+            # yelp2018 shape: the batch rows hold ~60 % of the non-zeros because positives are popularity-biased,
+            # so this saves ~15 us of the 44 us layer; pruning X_{L-1} to the 1-hop set m1 (90 % of the rows) and
+            # masking the first backward product by m0 did not pay and are not used — profiles/README.md.)
+            ops.batch_masks(users, pos, neg, self.B_cap, ctl, self.nu, self.csr, self.m0, None)
+            masks = (self.m0, None)
+        self.forward(masks)
         if self.dist_mode == 'dp':
             import torch.distributed as dist
             ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
@@ -256,9 +278,9 @@ class Engine:
         else:
             g = self.local if self.dist_mode == 'rowpart' else self.csr
 
-            def last(X, alpha, beta, zs):
+            def last(X, alpha, beta, zs, col_mask):
                 ops.spmm_adam(g, X, self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.scalars, alpha, beta,
-                              [z[r0:r1] for z in zs])
+                              [z[r0:r1] for z in zs], col_mask=col_mask)
             self._backward_chain(self.G, last)
         if self.dist_mode == 'dp':
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
@@ -294,10 +316,24 @@ class Engine:
         in self.loss_out (device).  Host batches cost one H2D copy."""
         if self.dist_mode == 'dp' and not B_global:
             B_global = int(users.numel()) * self.world          # equal shards unless the caller says otherwise
+        if self.dist_mode == 'dp_idx':
+            users, pos, neg = self._gather_indices(users, pos, neg)
+            B_global = 0
         self._stage_batch(users, pos, neg, B_global)
         self._run('direct', self.bu, self.bp, self.bn, self.ctl)
         self._host_step += 1
         self.param_epoch += 1
+
+    def _gather_indices(self, users, pos, neg):
+        """dp_idx: all-gather every rank's (users,pos,neg) shard -> the global batch on every rank."""
+        import torch.distributed as dist
+        Bl = int(users.numel())
+        loc = torch.stack([users.to(self.device, torch.int64, non_blocking=True), pos.to(self.device, torch.int64, non_blocking=True),
+                           neg.to(self.device, torch.int64, non_blocking=True)])                     # [3, Bl]
+        allb = torch.empty((self.world, 3, Bl), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allb, loc, group=self.group)
+        g = allb.permute(1, 0, 2).reshape(3, self.world * Bl)
+        return g[0], g[1], g[2]
 
     def loss_to_host(self):
         """D2H of {bpr, reg, total, running sum}; synchronises the stream."""

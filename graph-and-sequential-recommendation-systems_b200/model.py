@@ -129,7 +129,7 @@ class LightGCN(nn.Module):
                               B_cap=config.get('bpr_batch_size', 2048),
                               deterministic=config.get('deterministic', False),
                               use_graph=config.get('cuda_graph', True),
-                              dist_mode=config.get('dist_mode', None))
+                              dist_mode=config.get('dist_mode', None), prune=config.get('prune_dead_rows', True))
         self._cache_key = None
         self._pack_params()
 
@@ -206,9 +206,11 @@ class LightGCN(nn.Module):
             all_users, all_items = self.computer()
             users = users.to(self.device, dtype=torch.int64).contiguous()
             g = self._csr
-            if mask:
-                return ops.score_topk(all_users, all_items, users, k, g.indptr, g.indices, self.n_users)
-            return ops.score_topk(all_users, all_items, users, k)
+            mi, mx = (g.indptr, g.indices) if mask else (None, None)
+            if self.config.get('score_tensor_core', True):
+                idx, val, self.last_rank_redone = ops.score_topk_tc(all_users, all_items, users, k, mi, mx, self.n_users)
+                return idx, val
+            return ops.score_topk(all_users, all_items, users, k, mi, mx, self.n_users)
 
     def getEmbedding(self, users, pos_items, neg_items):
         all_users, all_items = self.computer()

@@ -159,7 +159,7 @@ def _z_array(zs):
     return arr, len(zs)
 
 
-def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None):
+def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None):
     """Y = alpha * (A @ X) + beta * sum(zs)  — K1.  X is indexed by column id, Y/zs by local row."""
     lib = _lib.load()
     d = X.shape[1]
@@ -172,11 +172,11 @@ def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None):
     for z in (zs or []):
         _need(z, torch.float32, "z", 2)
     _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
-                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _stream()), "spmm")
+                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _p(row_mask), _p(col_mask), _stream()), "spmm")
     return Y
 
 
-def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None):
+def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None):
     """K1 with the Adam epilogue: grad = alpha*(A@X) + beta*sum(zs); P,M,V updated in place."""
     lib = _lib.load()
     d = X.shape[1]
@@ -185,7 +185,7 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None):
     arr, nz = _z_array(zs)
     _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                       float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
-                                      g._plan_ref(d), _stream()), "spmm_adam")
+                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _stream()), "spmm_adam")
 
 
 def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
@@ -236,6 +236,12 @@ def bpr_clear_rows(G, users, pos, neg, B_cap, ctl, n_users):
                                                G.shape[1], _stream()), "bpr_clear_rows")
 
 
+def batch_masks(users, pos, neg, B_cap, ctl, n_users, g, m0, m1):
+    """Bitmaps of the rows a step needs: m0 = batch rows, m1 (optional) = m0 + their neighbours."""
+    _lib.check(_lib.load().lgcn_batch_masks(_p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users, g.n_rows, _p(g.indptr),
+                                            _p(g.indices), _p(m0), _p(m1), _stream()), "batch_masks")
+
+
 def batch_advance(ctl, B_cap):
     _lib.check(_lib.load().lgcn_batch_advance(_p(ctl), B_cap, _stream()), "batch_advance")
 
@@ -259,6 +265,38 @@ def score_topk(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=No
                                    _p(mask_indices), int(mask_col_offset), int(k), _p(idx), _p(val), _p(ws),
                                    ws_bytes, _stream()), "score_topk")
     return idx, val
+
+
+def score_topk_tc(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=None, mask_col_offset=0):
+    """K3 on tensor cores: same result as score_topk, bit for bit.  Returns (idx, val, n_rows_redone)."""
+    lib = _lib.load()
+    _need(users_emb, torch.float32, "users_emb", 2), _need(items_emb, torch.float32, "items_emb", 2)
+    Bt = users_emb.shape[0] if users is None else users.numel()
+    m_items, d = items_emb.shape
+    if not lib.lgcn_score_topk_tc_supported(d, k) or Bt == 0:
+        idx, val = score_topk(users_emb, items_emb, users, k, mask_indptr, mask_indices, mask_col_offset)
+        return idx, val, Bt
+    dev = items_emb.device
+    if users is not None:
+        _need(users, torch.int64, "users", 1)
+    idx = torch.empty((Bt, k), dtype=torch.int64, device=dev)
+    val = torch.empty((Bt, k), dtype=torch.float32, device=dev)
+    flags = torch.empty(Bt, dtype=torch.int32, device=dev)
+    n_flagged = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.lgcn_score_topk_tc_workspace_bytes(Bt, m_items, k)
+    ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+    _lib.check(lib.lgcn_score_topk_tc(_p(users_emb), _p(items_emb), _p(users), Bt, m_items, d, _p(mask_indptr), _p(mask_indices),
+                                      int(mask_col_offset), int(k), _p(idx), _p(val), _p(flags), _p(n_flagged),
+                                      c_void_p(ws_ptr), ws_bytes, _stream()), "score_topk_tc")
+    n = int(n_flagged.item())
+    if n:   # rows whose certificate failed: exact path, scattered back
+        rows = torch.nonzero(flags, as_tuple=False).flatten()
+        sub = rows if users is None else users[rows].contiguous()
+        idx2, val2 = score_topk(users_emb, items_emb, sub, k, mask_indptr, mask_indices, mask_col_offset)
+        idx[rows] = idx2
+        val[rows] = val2
+    return idx, val, n
 
 
 def score_dense(users_emb, items_emb, users):

@@ -47,6 +47,8 @@ config = {
     # extras understood by this implementation only (all optional)
     'deterministic': False,     # K2 owner-computes reduction instead of float atomics
     'cuda_graph': True,         # capture the fused training step in a CUDA graph
+    'prune_dead_rows': True,    # training step skips rows of the last layers that the batch never reads
+    'score_tensor_core': True,  # evaluation scores on tcgen05 (exact result; rows failing the certificate are redone)
     'spmm_seg_len': 128,        # degree-binning threshold of K1
 }
 

@@ -73,6 +73,9 @@ int lgcn_coo_to_csr(const int64_t* rows, const int64_t* cols, int64_t nnz, int32
  *   plain    : Y[i,:] = g[i,:]
  *   adam     : torch.optim.Adam update of P,M,V rows with gradient g (code/utils.py:51,62);
  *              Y may be NULL.
+ * row_mask / col_mask (optional bitmaps over rows / columns, bit i of word i>>5): rows whose bit is 0 are
+ * skipped (Y not written); columns whose bit is 0 are rows of X known to be all-zero and are never read.
+ * Used by the training step to drop work nobody consumes; NULL = full product.
  * X is indexed by GLOBAL column id; Y, Z_t, P, M, V by LOCAL row i (callers pre-offset the
  * pointers for a row partition).  d in {16,32,64,128,256}.
  *
@@ -119,7 +122,8 @@ typedef struct {           /* device-resident Adam scalars, written by lgcn_adam
 int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                   int32_t n_rows, int32_t d, const float* X, float* Y,
                   float alpha, float beta, const float* const* z_host, int32_t nz,
-                  const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream);
+                  const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
+                  lgcn_stream_t stream);
 
 /* profiling hook: selects a tuning variant (unroll / CTA size / occupancy cap / L1 policy) of the d=64
  * plain kernel; 0 = shipped configuration.  Returns the previous value.  Results are identical. */
@@ -129,7 +133,8 @@ int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const floa
                        int32_t n_rows, int32_t d, const float* X, float* Y /* may be NULL */,
                        float alpha, float beta, const float* const* z_host, int32_t nz,
                        float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
-                       const lgcn_spmm_plan_t* plan_host, lgcn_stream_t stream);
+                       const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
+                       lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Adam (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad)
@@ -175,6 +180,12 @@ int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t* pos, cons
                         int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t d,
                         lgcn_stream_t stream);
 int lgcn_batch_advance(int32_t* batch_ctl_dev, int32_t B_cap, lgcn_stream_t stream);
+/* bitmaps over the N nodes for the current batch window: m0 = the 3B rows the loss reads, m1 = m0 plus their
+ * neighbours in the CSR (both cleared first; m1 may be NULL).  uint32[(n_nodes+31)/32] each. */
+int lgcn_batch_masks(const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t B_cap,
+                     const int32_t* batch_ctl_dev, int32_t n_users, int32_t n_nodes,
+                     const int32_t* indptr, const int32_t* indices, uint32_t* m0, uint32_t* m1,
+                     lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  user x item scores fused with the train-item mask and per-row top-k
@@ -192,6 +203,18 @@ int lgcn_score_topk(const float* users_emb, const float* items_emb, const int64_
                     int32_t m_items, int32_t d, const int32_t* mask_indptr, const int32_t* mask_indices,
                     int32_t mask_col_offset, int32_t k, int64_t* idx_out, float* val_out,
                     void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+/* Tensor-core path of the same operation (tcgen05 TF32 MMA + TMA + TMEM, d = 64, k <= 24): an approximate
+ * filter keeps 32 candidates per row and item split, the candidates are rescored with the exact fp32 FMA chain
+ * and the top-k is certified against everything that was filtered out.  Rows whose
+ * certificate fails get flags_out[b] = 1 (count in n_flagged_out, device int32[1]) and MUST be recomputed with
+ * lgcn_score_topk; all other rows are bit-identical to it.  workspace must be 1024-byte aligned. */
+int lgcn_score_topk_tc_supported(int32_t d, int32_t k);
+size_t lgcn_score_topk_tc_workspace_bytes(int32_t Bt, int32_t m_items, int32_t k);
+int lgcn_score_topk_tc(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
+                       int32_t m_items, int32_t d, const int32_t* mask_indptr, const int32_t* mask_indices,
+                       int32_t mask_col_offset, int32_t k, int64_t* idx_out, float* val_out,
+                       int32_t* flags_out, int32_t* n_flagged_out,
+                       void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 /* dense scores float32[Bt,m_items] for the unfused API (getUsersRating returns the matrix) */
 int lgcn_score_dense(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
                      int32_t m_items, int32_t d, float* scores, lgcn_stream_t stream);

@@ -89,6 +89,9 @@ def probe_eval_and_build(name):
         med, best = time_fn(lambda: lg.ops.score_topk(out[:nu], out[nu:], users, 20, g.indptr, g.indices, nu), reps=5, warm=1)
         fl = 2.0 * Bt * ni * 64
         emit(kind="score_topk", graph=name, Bt=Bt, us=med, tflops=fl / med / 1e6)
+        med, best = time_fn(lambda: lg.ops.score_topk_tc(out[:nu], out[nu:], users, 20, g.indptr, g.indices, nu), reps=5, warm=1)
+        redone = lg.ops.score_topk_tc(out[:nu], out[nu:], users, 20, g.indptr, g.indices, nu)[2]
+        emit(kind="score_topk_tc", graph=name, Bt=Bt, us=med, tflops=fl / med / 1e6, rows_redone=redone)
     users = torch.arange(2048, device="cuda")
     med, best = time_fn(lambda: torch.topk(out[:nu][users] @ out[nu:].T, 20), reps=5, warm=1)
     emit(kind="torch_matmul_topk_nomask", graph=name, Bt=2048, us=med)
@@ -103,6 +106,15 @@ if __name__ == "__main__":
     if which in ("all", "eval"):
         probe_eval_and_build("yelp2018")
         probe_eval_and_build("amazon-book")
+    if which == "evaltc":
+        gr = lg.synth.make_graph("yelp2018")
+        nu, ni = gr['n_users'], gr['m_items']
+        g = lg.ops.csr_build(torch.from_numpy(gr['train_user']).cuda(), torch.from_numpy(gr['train_item']).cuda(), nu, ni)
+        out = (0.1 * torch.randn((nu + ni, 64), device="cuda")).contiguous()
+        for _ in range(2):
+            lg.ops.score_topk_tc(out[:nu], out[nu:], None, 20, g.indptr, g.indices, nu)
+        torch.cuda.synchronize()
+        print("evaltc done")
     if which == "ncu":
         # short run for `ncu -k regex:spmm_kernel`: 3 cold launches of the shipped kernel on yelp2018
         gr = lg.synth.make_graph("yelp2018")

@@ -40,7 +40,7 @@ def _worker(rank, world, port, mode, q):
         for s in range(3):
             sh = (s * 17) % B
             u, p, n = (torch.from_numpy(np.roll(g[k], sh)).long().cuda() for k in ('users', 'pos', 'neg'))
-            if mode == 'dp':
+            if mode in ('dp', 'dp_idx'):
                 lo, hi = lg.engine.shard_batch(B, rank, world)
                 eng.step(u[lo:hi], p[lo:hi], n[lo:hi], B_global=B)
             else:
@@ -63,7 +63,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["dp", "rowpart"])
+@pytest.mark.parametrize("mode", ["dp", "dp_idx", "rowpart"])
 @pytest.mark.timeout(600)
 def test_two_rank_training_matches_reference(mode):
     if torch.cuda.device_count() < 2:

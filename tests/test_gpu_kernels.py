@@ -170,6 +170,62 @@ def test_spmm_full_size_properties(lg):
         assert rel_err(Av.cpu().numpy(), Ax.cpu().numpy()) < 1e-6, v
 
 
+def _bits(mask_np, n):
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.flatnonzero(mask_np)
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    return torch.from_numpy(words.view(np.int32)).cuda()
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_row_and_column_masks(lg, orc, d):
+    rng = np.random.default_rng(11 + d)
+    nu, ni = 600, 500
+    tu, ti = random_edges(rng, nu, ni, 9000)
+    tu[:400] = 2; ti[:400] = rng.permutation(ni)[:400]
+    g = build(lg, tu, ti, nu, ni, seg_len=32)
+    N = nu + ni
+    indptr, indices, vals = (t.cpu().numpy() for t in (g.indptr, g.indices, g.vals))
+    # column mask: X is zero outside the marked rows -> identical to the unmasked product, bit for bit
+    nz_rows = rng.random(N) < 0.1
+    X = rng.normal(0, 0.1, (N, d)).astype(np.float32); X[~nz_rows] = 0
+    Z = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+    Yf = torch.empty((N, d), device='cuda'); Ym = torch.empty((N, d), device='cuda')
+    lg.ops.spmm(g, dev(X), Yf, 0.25, 0.5, [dev(Z)])
+    lg.ops.spmm(g, dev(X), Ym, 0.25, 0.5, [dev(Z)], col_mask=_bits(nz_rows, N))
+    assert torch.equal(Yf, Ym)
+    assert rel_err(Ym.cpu().numpy(), 0.25 * orc.spmm_scipy(indptr, indices, vals.astype(np.float64), X.astype(np.float64)) + 0.5 * Z) < TOL
+    # row mask: marked rows equal the full product, the others are left untouched
+    rows = rng.random(N) < 0.3; rows[2] = True
+    X2 = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+    lg.ops.spmm(g, dev(X2), Yf)
+    Ym.fill_(7.0)
+    lg.ops.spmm(g, dev(X2), Ym, row_mask=_bits(rows, N))
+    r = torch.from_numpy(rows).cuda()
+    assert torch.equal(Ym[r], Yf[r]) and bool((Ym[~r] == 7.0).all())
+    # a second full launch must not be disturbed by the skipped segments (arrival counters untouched)
+    lg.ops.spmm(g, dev(X2), Ym)
+    assert torch.equal(Ym, Yf)
+
+
+def test_batch_masks(lg):
+    rng = np.random.default_rng(5)
+    nu, ni, B = 400, 300, 100
+    tu, ti = random_edges(rng, nu, ni, 5000)
+    g = build(lg, tu, ti, nu, ni)
+    N = nu + ni
+    users = rng.integers(0, nu, B); pos = rng.integers(0, ni, B); neg = rng.integers(0, ni, B)
+    ctl = torch.tensor([3, B, B + 3, 0], dtype=torch.int32, device='cuda')
+    pad = lambda a: dev(np.concatenate([np.zeros(3, np.int64), a.astype(np.int64), np.zeros(50, np.int64)]))
+    m0 = torch.full(((N + 31) // 32,), -1, dtype=torch.int32, device='cuda'); m1 = m0.clone()
+    lg.ops.batch_masks(pad(users), pad(pos), pad(neg), 128, ctl, nu, g, m0, m1)
+    rows = np.unique(np.concatenate([users, nu + pos, nu + neg]))
+    indptr, indices = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+    nb = np.unique(np.concatenate([indices[indptr[r]:indptr[r + 1]] for r in rows] + [rows]))
+    unpack = lambda m: np.flatnonzero(np.unpackbits(m.cpu().numpy().view(np.uint8), bitorder='little')[:N])
+    assert np.array_equal(unpack(m0), rows) and np.array_equal(unpack(m1), nb)
+
+
 # ------------------------------------------------------------------------------------ Adam
 def test_adam_matches_torch_and_oracle(lg, orc):
     rng = np.random.default_rng(0)
@@ -332,6 +388,40 @@ def test_score_topk_k_exceeds_unmasked_items(lg, orc):
         lg.ops.score_topk(o[:nu], o[nu:], None, 61)
 
 
+@pytest.mark.parametrize("scale", [0.1, 1.0])
+def test_score_topk_tensor_core_is_bit_identical_to_exact(lg, scale):
+    """tcgen05 filter + exact rescoring + certificate == the exact kernel, indices AND scores."""
+    rng = np.random.default_rng(int(scale * 10))
+    nu, ni, d, k = 700, 3001, 64, 20
+    tu, ti = random_edges(rng, nu, ni, 30000)
+    tu[:2990] = 5; ti[:2990] = rng.permutation(ni)[:2990]       # user 5: only 11 unmasked items -> must be flagged
+    g = build(lg, tu, ti, nu, ni)
+    out = (scale * rng.normal(0, 1, (nu + ni, d))).astype(np.float32)
+    out[nu + 7] = out[nu + 3]                                   # exact ties
+    o = dev(out)
+    for users in (None, dev(rng.permutation(nu)[:130].astype(np.int64)), dev(np.array([5, 6, 5], np.int64))):
+        ei, ev = lg.ops.score_topk(o[:nu], o[nu:], users, k, g.indptr, g.indices, nu)
+        ti_, tv, redone = lg.ops.score_topk_tc(o[:nu], o[nu:], users, k, g.indptr, g.indices, nu)
+        assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+        n_rows = nu if users is None else users.numel()
+        assert redone < max(3, n_rows // 20), redone           # the certificate almost always holds
+    ei, ev = lg.ops.score_topk(o[:nu], o[nu:], None, k)
+    ti_, tv, _ = lg.ops.score_topk_tc(o[:nu], o[nu:], None, k)   # no mask
+    assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+
+
+def test_score_topk_tensor_core_small_item_table(lg):
+    g0 = load_golden('edge')                                    # 60 items (< one 256-item tile), d = 32 -> exact path
+    nu, ni = int(g0['n_users']), int(g0['m_items'])
+    rng = np.random.default_rng(1)
+    out = rng.normal(0, 0.3, (nu + ni, 64)).astype(np.float32); o = dev(out)
+    g = build(lg, g0['train_user'], g0['train_item'], nu, ni)
+    ei, ev = lg.ops.score_topk(o[:nu], o[nu:], None, 20, g.indptr, g.indices, nu)
+    ti_, tv, redone = lg.ops.score_topk_tc(o[:nu], o[nu:], None, 20, g.indptr, g.indices, nu)
+    assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+    assert redone >= 1                                          # user 0 has 15 unmasked items < k
+
+
 def test_score_dense_bit_exact(lg, orc):
     rng = np.random.default_rng(3)
     nu, ni, d = 130, 700, 64
@@ -350,6 +440,9 @@ def test_score_topk_full_size_against_fp64(lg):
     out = (0.1 * torch.randn((nu + ni, d), device='cuda', generator=gen)).contiguous()
     idx, val = lg.ops.score_topk(out[:nu], out[nu:], None, k, g.indptr, g.indices, nu)
     assert bool((val[:, :-1] >= val[:, 1:]).all())             # sorted descending
+    tidx, tval, redone = lg.ops.score_topk_tc(out[:nu], out[nu:], None, k, g.indptr, g.indices, nu)
+    assert torch.equal(tidx, idx) and torch.equal(tval, val)    # tensor-core path: bit-identical at full size
+    assert redone < nu // 100
     sub = torch.arange(0, nu, 37, device='cuda')
     S = out[:nu][sub].double() @ out[nu:].double().T
     indptr = g.indptr.cpu().numpy(); indices = g.indices.cpu().numpy()

@@ -123,6 +123,18 @@ def test_graph_replay_equals_eager_bitwise(lg, golden_tiny):
     assert np.array_equal(res[0], res[1])
 
 
+def test_dead_row_pruning_is_bitwise_neutral(lg, golden):
+    """Skipping the rows nobody reads (engine.prune) must not change a single bit of the parameters."""
+    res = []
+    for prune in (True, False):
+        cfg, _, m = make_model(lg, golden, deterministic=True, prune_dead_rows=prune)
+        assert m._engine.prune == prune
+        bpr = lg.utils.BPRLoss(m, cfg)
+        losses = [bpr.stageOne(*(t.cuda() for t in triples(golden, s * 3))) for s in range(4)]
+        res.append((params(m), losses))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+
+
 def test_getUsersRating_and_Test_match_reference(lg, golden):
     cfg, ds, m = make_model(lg, golden)
     nu = int(golden['n_users'])
