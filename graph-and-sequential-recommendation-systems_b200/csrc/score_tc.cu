@@ -35,20 +35,22 @@ constexpr int TC_N = 256;            // items per MMA tile
 constexpr int TC_D = 64;             // embedding width handled by this path
 constexpr int TC_KP = 32;            // candidates kept per (row, split)
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int TC_KEEP = 16;            // entries a buffer is compacted to
 constexpr int TC_ATOM_K = 32;        // fp32 elements per 128-byte swizzle atom row
 constexpr int TC_A_ATOM_BYTES = TC_M * 128;           // 16 KB
 constexpr int TC_B_ATOM_BYTES = TC_N * 128;           // 32 KB
 constexpr int TC_A_BYTES = 2 * TC_A_ATOM_BYTES;       // 32 KB
 constexpr int TC_B_STAGE_BYTES = 2 * TC_B_ATOM_BYTES; // 64 KB
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_A_BYTES + TC_STAGES * TC_B_STAGE_BYTES + 2 * (TC_KP + 1) * TC_M * 4 + 256;
+constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_A_BYTES + TC_STAGES * TC_B_STAGE_BYTES + 2 * (8 * 32 * TC_KP) * 4 + TC_M * 4 + 128;
 constexpr float TC_EPS_C = 0.0025f;  // > 2^-9 (both operands truncated to 10 mantissa bits) + accumulation slack
 
 struct TcArgs {
     const long long* users; int Bt; int m_items;
     const int* mask_indptr; const int* mask_indices; int mask_col_offset;
     int tiles_per_split; int n_splits;
-    float* cand_val; int* cand_idx;      // [Bt][n_splits][TC_KP]
+    float* cand_val; int* cand_idx;      // [Bt][2*n_splits][TC_KP]
+    float* cand_tau;                     // [Bt][2*n_splits]: everything the sub-stream dropped is <= this
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -114,15 +116,49 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
+// order-preserving float <-> int (for atomicMax on thresholds that may be negative)
+__device__ __forceinline__ int tc_enc(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float tc_dec(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct RowState { int cnt; float tau; };
+
+// Warp-cooperative compaction of the candidate buffers named in `need` (one bit per lane/row): every lane takes one
+// entry of the row, ranks it with 32 shuffles, the best TC_KEEP are written back and the row's threshold becomes
+// the TC_KEEP-th best.  Returns the calling lane's updated (cnt, tau).
+__device__ __noinline__ RowState tc_compact_rows(unsigned need, float* bv, int* bi, int* tau_row, int lane, int cnt, float tau) {
+    while (need) {
+        const int L = __ffs(need) - 1; need &= need - 1;
+        const int n = __shfl_sync(0xffffffffu, cnt, L);
+        const int slot = L * TC_KP + ((lane + L) & 31);
+        const float sv = (lane < n) ? bv[slot] : -FLT_MAX;
+        const int sid = (lane < n) ? bi[slot] : 0x7fffffff;
+        int rank = 0;
+#pragma unroll
+        for (int o = 0; o < 32; ++o) {
+            const float so = __shfl_sync(0xffffffffu, sv, o);
+            rank += (so > sv || (so == sv && o < lane)) ? 1 : 0;
+        }
+        __syncwarp();
+        if (rank < TC_KEEP) { const int d = L * TC_KP + ((rank + L) & 31); bv[d] = sv; bi[d] = sid; }
+        const int src = __ffs(__ballot_sync(0xffffffffu, rank == TC_KEEP - 1)) - 1;
+        const float t16 = __shfl_sync(0xffffffffu, sv, src);
+        if (lane == L) { cnt = TC_KEEP; tau = fmaxf(tau, t16); atomicMax(tau_row + L, tc_enc(t16)); }
+        __syncwarp();
+    }
+    RowState r; r.cnt = cnt; r.tau = tau;
+    return r;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024-B alignment
     uint8_t* sA = smem;
     uint8_t* sB = sA + TC_A_BYTES;
-    float* lv = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_STAGE_BYTES);      // [TC_M][TC_KP+1]
-    int* li = reinterpret_cast<int*>(lv + (TC_KP + 1) * TC_M);                     // [TC_M][TC_KP+1]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li + (TC_KP + 1) * TC_M);
+    float* lv = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_STAGE_BYTES);      // [8 warps][32 rows][TC_KP]
+    int* li = reinterpret_cast<int*>(lv + 8 * 32 * TC_KP);
+    int* tau_sh = li + 8 * 32 * TC_KP;                                             // [TC_M] row thresholds shared by the two halves
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tau_sh + TC_M);
     // bars: 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 tmem_full | 7,8 tmem_empty ; then the TMEM base address
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     const uint32_t bar0 = smem_u32(bars);
@@ -138,9 +174,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (threadIdx.x == 0) {
         mbar_init(BAR(0), 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(1 + s), 1); mbar_init(BAR(3 + s), 1); }
-        for (int c = 0; c < 2; ++c) { mbar_init(BAR(5 + c), 1); mbar_init(BAR(7 + c), 128); }
+        for (int c = 0; c < 2; ++c) { mbar_init(BAR(5 + c), 1); mbar_init(BAR(7 + c), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < TC_M) tau_sh[threadIdx.x] = tc_enc(-FLT_MAX);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -188,11 +225,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else {
-        // ================= epilogue: thread-per-row filter, warp-cooperative insertion =================
-        // Thread t owns row 32*q+t and only COMPARES; whenever some lanes of the warp see a candidate, the whole
-        // warp inserts them one at a time into that row's sorted 32-entry list (lane p holds entry p: one ballot,
-        // one shuffle, no loop) — the candidate path would otherwise serialise 32 divergent scalar insertions.
-        const int q = warp & 3;                                // TMEM lane quarter this warp may read
+        // ================= epilogue: 8 warps, thread-per-row threshold filter =================
+        // Warp e reads TMEM lane quarter q = warp%4 (hardware rule) and every other 32-column chunk (half h), so a
+        // row is watched by two threads with private candidate buffers.  A thread only compares: max of 4 scores
+        // against its row threshold tau; hits are APPENDED to a 32-slot buffer (no sorting, no cooperation, lanes
+        // proceed independently).  When a buffer holds >= 24 entries the warp compacts it cooperatively (one entry
+        // per lane, rank by 32 shuffles) to its 16 best and raises tau to the 16th.  Everything that was ever
+        // dropped or skipped is <= the final tau, which is what phase B needs for its certificate.
+        const int e = warp - 2, q = warp & 3, h = e >> 2;
         const int r = q * 32 + lane;                           // row of the tile owned by this thread
         const bool live = (ub + r) < a.Bt;
         const int* mrow = nullptr; int m_cur = 0, m_end = 0, m_next = 0x7fffffff;
@@ -201,51 +241,53 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int lo = __ldg(a.mask_indptr + my_user), hi = __ldg(a.mask_indptr + my_user + 1);
             mrow = a.mask_indices + lo; m_end = hi - lo;
             const int first_item = t_begin * TC_N + a.mask_col_offset;        // first column id this CTA scores
-            int l = 0, h = m_end;                                             // lower_bound: cursor into the sorted row
-            while (l < h) { const int mid = (l + h) >> 1; if (__ldg(mrow + mid) < first_item) l = mid + 1; else h = mid; }
+            int l = 0, hh = m_end;                                            // lower_bound: cursor into the sorted row
+            while (l < hh) { const int mid = (l + hh) >> 1; if (__ldg(mrow + mid) < first_item) l = mid + 1; else hh = mid; }
             m_cur = l;
             if (m_cur < m_end) m_next = __ldg(mrow + m_cur) - a.mask_col_offset;
         }
-        float* lrow_v = lv + (q * 32) * 33;                    // this warp's 32 lists: [row][33]
-        int* lrow_i = li + (q * 32) * 33;
-        int cnt = 0; float tau = -FLT_MAX;
+        float* bv = lv + e * (32 * TC_KP);                     // this warp's 32 buffers: slot(row, p) = row*32 + ((p+row)&31)
+        int* bi = li + e * (32 * TC_KP);
+        int cnt = 0; float tau = live ? -FLT_MAX : FLT_MAX; bool lost = false;
+        int* tau_row = tau_sh + q * 32;
         for (int it = 0; it < n_tiles; ++it) {
             const int acc = it & 1, ra = it >> 1;
             mbar_wait(BAR(5 + acc), ra & 1);
             tc_fence_after();
             const int ib = (t_begin + it) * TC_N;
 #pragma unroll 1
-            for (int ch = 0; ch < TC_N / 32; ++ch) {
+            for (int ch = h; ch < TC_N / 32; ch += 2) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_N + ch * 32), v);
                 const int i0 = ib + ch * 32;
-                // train items of this row inside [i0, i0+32): advance the cursor through the sorted CSR row
+                // (2) train items of this row inside [i0, i0+32): advance the cursor through the sorted CSR row
                 unsigned mbits = 0;
                 while (m_next < i0 + 32) {
                     if (m_next >= i0) mbits |= 1u << (m_next - i0);
                     ++m_cur;
                     m_next = (m_cur < m_end) ? __ldg(mrow + m_cur) - a.mask_col_offset : 0x7fffffff;
                 }
-                const unsigned okbits = live ? ~mbits & ((i0 + 32 <= a.m_items) ? 0xffffffffu : ((i0 < a.m_items) ? ((1u << (a.m_items - i0)) - 1u) : 0u)) : 0u;
+                unsigned bad = mbits;                                       // masked or out-of-range columns: rejected at append time
+                if (i0 + 32 > a.m_items) bad |= (i0 < a.m_items) ? ~((1u << (a.m_items - i0)) - 1u) : 0xffffffffu;
+                tau = fmaxf(tau, tc_dec(tau_row[lane]));                    // the other half may have raised the row's threshold
+                // (3) filter: 4 scores at a time
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const bool hit = ((okbits >> j) & 1u) && (v[j] > tau || cnt < TC_KP);
-                    unsigned hits = __ballot_sync(0xffffffffu, hit);
-                    while (hits) {
-                        const int L = __ffs(hits) - 1; hits &= hits - 1;
-                        const float sc = __shfl_sync(0xffffffffu, v[j], L);
-                        const int cntL = __shfl_sync(0xffffffffu, cnt, L);
-                        const float e = (lane < cntL) ? lrow_v[L * 33 + lane] : -FLT_MAX;
-                        const int id = (lane < cntL) ? lrow_i[L * 33 + lane] : 0x7fffffff;
-                        const int pos = __popc(__ballot_sync(0xffffffffu, e >= sc));      // entries that stay ahead (ties keep the older)
-                        const float e_up = __shfl_up_sync(0xffffffffu, e, 1);
-                        const int id_up = __shfl_up_sync(0xffffffffu, id, 1);
-                        const float ne = lane < pos ? e : (lane == pos ? sc : e_up);
-                        const int nid = lane < pos ? id : (lane == pos ? (i0 + j) : id_up);
-                        if (lane >= pos && lane <= cntL && lane < TC_KP) { lrow_v[L * 33 + lane] = ne; lrow_i[L * 33 + lane] = nid; }
-                        const float last = __shfl_sync(0xffffffffu, ne, TC_KP - 1);
-                        if (lane == L) { if (cnt < TC_KP) ++cnt; if (cnt == TC_KP) tau = last; }
-                        __syncwarp();
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    // make room first: a group appends at most 4 entries, so a buffer with <= 28 can never overflow
+                    const unsigned need = __ballot_sync(0xffffffffu, cnt > TC_KP - 4);
+                    if (need) { const RowState st = tc_compact_rows(need, bv, bi, tau_row, lane, cnt, tau); cnt = st.cnt; tau = st.tau; }
+                    const float m4 = fmaxf(fmaxf(v[4 * g4], v[4 * g4 + 1]), fmaxf(v[4 * g4 + 2], v[4 * g4 + 3]));
+                    if (m4 > tau) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const float sc = v[4 * g4 + x];
+                            if (sc > tau && !((bad >> (4 * g4 + x)) & 1u)) {
+                                if (cnt < TC_KP) {
+                                    const int d = lane * TC_KP + ((cnt + lane) & 31);
+                                    bv[d] = sc; bi[d] = i0 + 4 * g4 + x; ++cnt;
+                                } else lost = true;             // > 8 hits in one chunk on a nearly full buffer: give the row up
+                            }
+                        }
                     }
                 }
             }
@@ -254,11 +296,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         __syncwarp();
         if (live) {
-            const size_t o = ((size_t)(ub + r) * a.n_splits + blockIdx.y) * TC_KP;
+            const int n_sub = a.n_splits * 2, sub = blockIdx.y * 2 + h;
+            const size_t o = ((size_t)(ub + r) * n_sub + sub) * TC_KP;
             for (int p = 0; p < TC_KP; ++p) {
-                a.cand_val[o + p] = (p < cnt) ? lrow_v[lane * 33 + p] : -FLT_MAX;
-                a.cand_idx[o + p] = (p < cnt) ? lrow_i[lane * 33 + p] : 0x7fffffff;
+                const int d = lane * TC_KP + ((p + lane) & 31);
+                a.cand_val[o + p] = (p < cnt) ? bv[d] : -FLT_MAX;
+                a.cand_idx[o + p] = (p < cnt) ? bi[d] : 0x7fffffff;
             }
+            a.cand_tau[(size_t)(ub + r) * n_sub + sub] = lost ? FLT_MAX : fmaxf(tau, tc_dec(tau_row[lane]));
         }
     }
     tc_fence_before();
@@ -295,7 +340,7 @@ __global__ void item_norm_max_kernel(const float4* __restrict__ V, int m_items, 
 constexpr int RS_WARPS = 4;
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const long long* __restrict__ users, int Bt, int n_splits, int k,
-               const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ vmax_bits,
+               const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const float* __restrict__ cand_tau, const int* __restrict__ vmax_bits,
                long long* __restrict__ idx_out, float* __restrict__ val_out, int* __restrict__ flags, int* __restrict__ n_flagged) {
     __shared__ float s_sc[RS_WARPS][32 * TC_KP];
     __shared__ int s_id[RS_WARPS][32 * TC_KP];
@@ -311,11 +356,33 @@ rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const l
     __syncwarp();
     const int ncand = n_splits * TC_KP;
     const size_t base = (size_t)b * ncand;
+    const float eps = TC_EPS_C * sqrtf(un2) * __int_as_float(*vmax_bits);
+    // (1) approximate scores: find the k-th best; only candidates within 2*eps of it can be in the exact top-k
+    for (int c = lane; c < ncand; c += 32) { s_sc[w][c] = cand_val[base + c]; s_id[w][c] = cand_idx[base + c]; }
+    __syncwarp();
+    unsigned taken = 0; float kth_apx = -FLT_MAX;
+    for (int qq = 0; qq < k; ++qq) {
+        float bv = -FLT_MAX; int bc = -1;
+        for (int c = lane, t = 0; c < ncand; c += 32, ++t) {
+            const float s = s_sc[w][c];
+            if (!((taken >> t) & 1u) && s_id[w][c] != 0x7fffffff && s > bv) { bv = s; bc = c; }
+        }
+        float mv = bv; int mc = bc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, mv, o); const int oc = __shfl_xor_sync(0xffffffffu, mc, o);
+            if (ov > mv || (ov == mv && oc > mc)) { mv = ov; mc = oc; }
+        }
+        if (mc >= 0 && (mc & 31) == lane) taken |= 1u << (mc >> 5);
+        kth_apx = mv;
+    }
+    const float keep_above = kth_apx - 2.f * eps;
+    // (2) exact fp32 FMA chain for the survivors
     int valid = 0;
     for (int c = lane; c < ncand; c += 32) {
-        const int id = cand_idx[base + c];
+        const int id = s_id[w][c];
         float s = -FLT_MAX;
-        if (id != 0x7fffffff) {
+        if (id != 0x7fffffff && s_sc[w][c] >= keep_above) {
             const float4* vr = reinterpret_cast<const float4*>(V + (size_t)id * TC_D);
             s = 0.f;
 #pragma unroll
@@ -325,16 +392,15 @@ rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const l
                 s = fmaf(s_u[w][4 * c4 + 2], x.z, s); s = fmaf(s_u[w][4 * c4 + 3], x.w, s);
             }
             ++valid;
+        } else {
+            s_id[w][c] = 0x7fffffff;
         }
-        s_sc[w][c] = s; s_id[w][c] = id;
+        s_sc[w][c] = s;
     }
     for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-    // smallest kept approximate score over the FULL splits = bound for everything that was filtered out
+    // bound for everything that was filtered out: the largest final threshold of the row's sub-streams
     float tmin = -FLT_MAX;
-    for (int s = lane; s < n_splits; s += 32) {
-        const float last = cand_val[base + (size_t)s * TC_KP + TC_KP - 1];   // -FLT_MAX when the split kept everything
-        tmin = fmaxf(tmin, last);
-    }
+    for (int s = lane; s < n_splits; s += 32) tmin = fmaxf(tmin, cand_tau[(size_t)b * n_splits + s]);
     for (int o = 16; o > 0; o >>= 1) tmin = fmaxf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     __syncwarp();
     float kth = -FLT_MAX;
@@ -357,8 +423,7 @@ rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const l
         __syncwarp();
     }
     if (lane == 0) {
-        const float eps = TC_EPS_C * sqrtf(un2) * __int_as_float(*vmax_bits);
-        const bool ok = (valid >= k) && (tmin == -FLT_MAX || tmin + eps < kth);
+        const bool ok = (valid >= k) && (tmin == -FLT_MAX || (tmin < FLT_MAX && tmin + eps < kth));
         flags[b] = ok ? 0 : 1;
         if (!ok) atomicAdd(n_flagged, 1);
     }
@@ -396,7 +461,8 @@ static int make_map(CUtensorMap* m, const float* base, uint64_t rows, uint32_t b
 static int tc_pick_splits(int Bt, int m_items) {
     const int row_tiles = (Bt + TC_M - 1) / TC_M, item_tiles = (m_items + TC_N - 1) / TC_N;
     int want = (2 * sm_count() + row_tiles - 1) / row_tiles;
-    if (want > 32) want = 32;
+    if (want < 2) want = 2;                         // >= 4 sub-streams per row: no single one can hold most of the top-k
+    if (want > 16) want = 16;                       // 2 sub-streams per split, 32 per row at most
     if (want > item_tiles) want = item_tiles;
     if (want < 1) want = 1;
     return want;
@@ -410,7 +476,7 @@ using namespace lgcn;
 extern "C" size_t lgcn_score_topk_tc_workspace_bytes(int32_t Bt, int32_t m_items, int32_t k) {
     if (Bt <= 0 || m_items <= 0 || k <= 0) return 0;
     const size_t bt_pad = ((size_t)Bt + TC_M - 1) / TC_M * TC_M;
-    return align_up(bt_pad * TC_D * 4, 1024) + 2 * align_up((size_t)Bt * 32 * TC_KP * 4, 256) + 256;
+    return align_up(bt_pad * TC_D * 4, 1024) + 2 * align_up((size_t)Bt * 32 * TC_KP * 4, 256) + align_up((size_t)Bt * 32 * 4, 256) + 256;
 }
 
 extern "C" int lgcn_score_topk_tc_supported(int32_t d, int32_t k) { return (d == TC_D && k >= 1 && k <= TC_KP - 8) ? 1 : 0; }
@@ -434,7 +500,8 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
     const size_t cand_bytes = align_up((size_t)Bt * 32 * TC_KP * 4, 256);
     float* cand_val = reinterpret_cast<float*>(w + align_up((size_t)bt_pad * TC_D * 4, 1024));
     int* cand_idx = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_val) + cand_bytes);
-    int* vmax = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_idx) + cand_bytes);
+    float* cand_tau = reinterpret_cast<float*>(reinterpret_cast<char*>(cand_idx) + cand_bytes);
+    int* vmax = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_tau) + align_up((size_t)Bt * 32 * 4, 256));
 
     gather_rows_kernel<<<(bt_pad * 16 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(users_emb),
                                                                  reinterpret_cast<const long long*>(users), Bt, bt_pad, reinterpret_cast<float4*>(A));
@@ -454,14 +521,14 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
     a.n_splits = tc_pick_splits(Bt, m_items);
     a.tiles_per_split = (item_tiles + a.n_splits - 1) / a.n_splits;
     a.n_splits = (item_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
-    a.cand_val = cand_val; a.cand_idx = cand_idx;
+    a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_tau = cand_tau;
     cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return fail("score_topk_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     dim3 grid(bt_pad / TC_M, a.n_splits);
     score_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
     LGCN_CHECK_LAUNCH("score_tc_kernel");
     rescore_kernel<<<(Bt + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, st>>>(users_emb, items_emb, reinterpret_cast<const long long*>(users), Bt,
-        a.n_splits, k, cand_val, cand_idx, vmax, reinterpret_cast<long long*>(idx_out), val_out, flags_out, n_flagged_out);
+        2 * a.n_splits, k, cand_val, cand_idx, cand_tau, vmax, reinterpret_cast<long long*>(idx_out), val_out, flags_out, n_flagged_out);
     LGCN_CHECK_LAUNCH("rescore_kernel");
     return 0;
 }
