@@ -43,9 +43,28 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
     Recmodel = recommend_model
     Recmodel.train()
     bpr = loss_class
+    bs = world.config['bpr_batch_size']
+    if world.config.get('device_sampler', False) and getattr(bpr, 'fused', False):
+        # K5: sample + shuffle on the device, straight into the layout the step reads (no host phase, no H2D)
+        eng = Recmodel._engine
+        with timer(name="Sample"):
+            S_dev = ops.sample_bpr(Recmodel._csr, dataset.n_users, dataset.m_items, dataset.trainDataSize,
+                                   world.seed, epoch)
+        if eng.B_cap != bs:
+            eng._alloc_batch(bs)
+        eng.set_lr(bpr.opt.param_groups[0]['lr'])
+        eng.decay = float(bpr.weight_decay)
+        steps = eng.begin_epoch(S_dev)
+        for _ in range(steps):
+            eng.epoch_step()
+        total_batch = S_dev.shape[1] // bs + 1
+        aver_loss = float(eng.loss_to_host()[3]) / total_batch
+        _append_csv('train_epoch_metrics.csv', ['epoch', 'loss'], [epoch, aver_loss])
+        time_info = timer.dict()
+        timer.zero()
+        return f"loss{aver_loss:.3f}-{time_info}"
     with timer(name="Sample"):
         S = utils.UniformSample_original(dataset)
-    bs = world.config['bpr_batch_size']
     # int64 on the device directly (the reference's torch.Tensor(...).long() float32 round trip,
     # code/Procedure.py:52-54, is exact only below 2^24 — SURVEY.md A16)
     S_t = torch.from_numpy(np.ascontiguousarray(S[:, :3].T)).to(torch.int64)

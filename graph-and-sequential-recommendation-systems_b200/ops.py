@@ -323,3 +323,14 @@ def rank_metrics(topk_idx, test_indptr, test_indices, ks):
                                      _p(_need(test_indices, torch.int32, "test_indices", 1)), _p(ks_t), len(ks),
                                      _p(sums), _stream()), "rank_metrics")
     return sums.view(len(ks), 3)
+
+
+def sample_bpr(g, n_users, m_items, train_num, seed, epoch, out=None):
+    """Device-side sampler + shuffle: int64 tensor [3, n] (users, pos, neg), n = (train_num // n_users) * n_users."""
+    n = (int(train_num) // int(n_users)) * int(n_users)
+    if out is None or out.shape[1] < n:
+        out = torch.empty((3, max(n, 1)), dtype=torch.int64, device=g.device)
+    S = out[:, :n]
+    _lib.check(_lib.load().lgcn_sample_bpr(_p(g.indptr), _p(g.indices), n_users, m_items, int(train_num), int(seed) & (2**64 - 1),
+                                           int(epoch), _p(out[0]), _p(out[1]), _p(out[2]), _stream()), "sample_bpr")
+    return S

@@ -81,3 +81,45 @@ def write_txt(graph, path):
                 cuts = np.flatnonzero(np.diff(u)) + 1
                 for uu, its in zip(u[np.concatenate([[0], cuts])], np.split(i, cuts)):
                     f.write(f"{uu} {' '.join(map(str, its.tolist()))}\n")
+
+
+def make_powerlaw_device(n_users, m_items, n_edges, seed=2020, device=None, chunk=1 << 26):
+    """BASELINE config 5 (scaled power-law graph) generated ON THE DEVICE: int64 (train_user, train_item) tensors.
+    u = floor(n_users * r^2), i = floor(m_items * r^2.5): hub user ~ n_edges/sqrt(n_users), hub item ~ n_edges/m_items^0.4.
+    Duplicate pairs are left in (K4 sums them like scipy's csr_matrix)."""
+    import torch
+    device = device or torch.device('cuda')
+    gen = torch.Generator(device=device).manual_seed(seed)
+    tu = torch.empty(n_edges, dtype=torch.int64, device=device)
+    ti = torch.empty(n_edges, dtype=torch.int64, device=device)
+    for lo in range(0, n_edges, chunk):
+        hi = min(n_edges, lo + chunk)
+        r1 = torch.rand(hi - lo, device=device, generator=gen, dtype=torch.float64)
+        r2 = torch.rand(hi - lo, device=device, generator=gen, dtype=torch.float64)
+        tu[lo:hi] = (r1 * r1 * n_users).long().clamp_(0, n_users - 1)
+        ti[lo:hi] = (r2.pow(2.5) * m_items).long().clamp_(0, m_items - 1)
+    return tu, ti
+
+
+class DeviceGraphDataset:
+    """Minimal dataset over device-resident edge arrays (no host copies): what LightGCN needs to build its graph.
+    Training uses the device sampler (world.config['device_sampler'])."""
+
+    def __init__(self, n_users, m_items, train_user_dev, train_item_dev, seg_len=128):
+        self.n_users, self.m_items = int(n_users), int(m_items)
+        self.trainDataSize = int(train_user_dev.numel())
+        self._tu, self._ti, self._seg_len = train_user_dev, train_item_dev, seg_len
+        self._csr, self.Graph = None, None
+        self.testDict = {}
+
+    def getCSRGraph(self):
+        if self._csr is None:
+            from . import ops
+            self._csr = ops.csr_build(self._tu, self._ti, self.n_users, self.m_items, seg_len=self._seg_len)
+            self._tu = self._ti = None            # the edge list is no longer needed
+        return self._csr
+
+    def getSparseGraph(self):
+        if self.Graph is None:
+            self.Graph = self.getCSRGraph().to_torch_sparse_csr()
+        return self.Graph

@@ -49,6 +49,7 @@ config = {
     'cuda_graph': True,         # capture the fused training step in a CUDA graph
     'prune_dead_rows': True,    # training step skips rows of the last layers that the batch never reads
     'score_tensor_core': True,  # evaluation scores on tcgen05 (exact result; rows failing the certificate are redone)
+    'device_sampler': False,    # True: K5 device sampler+shuffle (distributional parity); False: the reference's rand() stream
     'spmm_seg_len': 128,        # degree-binning threshold of K1
 }
 

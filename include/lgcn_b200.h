@@ -241,6 +241,17 @@ int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_n
                              const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
                              int32_t neg_num, int32_t* out_host);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-side BPR sampler + shuffle
+ * replaces  utils.UniformSample_original + utils.shuffle  code/utils.py:68-81,142-151 ; code/Procedure.py:50-55
+ * indptr/indices: the adjacency CSR (user rows hold n_users + item).  Every user gets train_num/n_users triples
+ * (uniform positive of its row, rejection-sampled negative outside it); output is already permuted, int64,
+ * users_out/pos_out/neg_out[n] with n = (train_num/n_users)*n_users.  Counter-based RNG keyed by (seed, epoch).
+ * -------------------------------------------------------------------------------------------*/
+int lgcn_sample_bpr(const int32_t* indptr, const int32_t* indices, int32_t n_users, int32_t m_items,
+                    int64_t train_num, uint64_t seed, uint64_t epoch,
+                    int64_t* users_out, int64_t* pos_out, int64_t* neg_out, lgcn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -462,6 +462,35 @@ def test_score_topk_full_size_against_fp64(lg):
         assert np.intersect1d(got[b].cpu().numpy(), indices[indptr[u]:indptr[u + 1]] - nu).size == 0
 
 
+def test_device_sampler_properties(lg):
+    """K5 keeps the reference sampler's contract (per-user counts, positives in / negatives out of the row) and
+    emits a permutation; the stream is counter-based, so parity is distributional, not bit-level."""
+    gr = lg.synth.make_graph('tiny', seed=2)
+    nu, ni = gr['n_users'], gr['m_items']
+    g = build(lg, gr['train_user'], gr['train_item'], nu, ni)
+    E = gr['train_user'].size
+    S = lg.ops.sample_bpr(g, nu, ni, E, seed=2020, epoch=0).cpu().numpy()
+    per = E // nu
+    assert S.shape == (3, per * nu)
+    assert np.array_equal(np.bincount(S[0], minlength=nu), np.full(nu, per))           # exactly per_user triples per user
+    indptr, indices = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+    rows = [set((indices[indptr[u]:indptr[u + 1]] - nu).tolist()) for u in range(nu)]
+    assert all(p in rows[u] and n not in rows[u] and 0 <= n < ni for u, p, n in S.T[::7])
+    assert not np.array_equal(S[0], np.sort(S[0]))                                      # shuffled, not in user order
+    S2 = lg.ops.sample_bpr(g, nu, ni, E, seed=2020, epoch=0).cpu().numpy()
+    S3 = lg.ops.sample_bpr(g, nu, ni, E, seed=2020, epoch=1).cpu().numpy()
+    assert np.array_equal(S, S2) and not np.array_equal(S, S3)                          # reproducible, epoch-dependent
+    # positives are uniform over the row: chi-square-ish check on the busiest user
+    u = int(np.argmax(np.diff(indptr[:nu + 1])))
+    big = np.concatenate([lg.ops.sample_bpr(g, nu, ni, E, seed=1, epoch=e).cpu().numpy()[:, :] for e in range(40)], axis=1)
+    pu = big[1][big[0] == u]
+    counts = np.array([np.sum(pu == it) for it in sorted(rows[u])])
+    assert counts.min() > 0 and counts.max() < 4 * counts.mean() + 10
+    # negatives are uniform over the complement
+    nn_ = big[2]
+    assert abs(nn_.mean() - (ni - 1) / 2) < 0.05 * ni
+
+
 def test_rank_metrics_vs_oracle(lg, orc):
     rng = np.random.default_rng(5)
     n, m, kmax = 257, 400, 20

@@ -197,6 +197,23 @@ def test_epoch_training_and_eval_on_synthetic(lg, tmp_path):
         lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048)
 
 
+def test_training_with_device_sampler(lg, tmp_path):
+    lg.world.configure(checkpoint_dir=str(tmp_path), bpr_batch_size=256, device_sampler=True)
+    try:
+        cfg = dict(lg.world.config)
+        ds = lg.synth.make_dataset('tiny', config=cfg)
+        lg.utils.set_seed(2020)
+        m = lg.LightGCN(cfg, ds)
+        bpr = lg.utils.BPRLoss(m, cfg)
+        r0 = lg.Procedure.Test(ds, m, 0)
+        infos = [lg.Procedure.BPR_train_original(ds, m, bpr, e) for e in range(30)]
+        r1 = lg.Procedure.Test(ds, m, 30)
+        assert float(infos[-1].split('-')[0][4:]) < float(infos[0].split('-')[0][4:])
+        assert r1['recall'][0] > r0['recall'][0]
+    finally:
+        lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048, device_sampler=False)
+
+
 def test_epoch_mode_equals_step_mode(lg, golden_tiny):
     """Device-resident epoch (window advance + graph replay) == explicit stageOne calls on the same batches."""
     g = golden_tiny
