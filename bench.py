@@ -210,10 +210,15 @@ def run_ours(args):
 
     # ---- leg 1: inputs resident in HBM ----------------------------------------------------------
     if mode is None:
-        eng.begin_epoch(S_host.cuda())
-        for _ in range(W):
-            eng.epoch_step()
-        step1 = lambda i: eng.epoch_step()
+        n_epoch_steps = eng.begin_epoch(S_host.cuda())
+        pos = [0]
+
+        def step1(i):
+            if pos[0] >= n_epoch_steps - 1:      # keep to full batches; wrap around to the start of the resident epoch
+                eng.rewind_epoch(); pos[0] = 0
+            eng.epoch_step(); pos[0] += 1
+        for i in range(W):
+            step1(i)
     else:
         S_dev = S_host.cuda()
         B_glob = B * world if mode == 'dp' else 0

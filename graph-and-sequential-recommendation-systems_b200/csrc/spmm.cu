@@ -12,7 +12,8 @@
 //     that share a warp/CTA do the same amount of work, the long items start first, and the item
 //     descriptor is ONE coalesced 16-byte load instead of the row_order -> indptr -> indptr chain.
 //   * one GROUP of LANES lanes owns one item; every lane holds d/4/LANES float4 accumulators
-//     (d=64, LANES=16: one 256-B embedding row is one 16-byte load per lane, two items per warp);
+//     (d=64, LANES=8: a 256-B embedding row is two 16-byte loads per lane, four items per warp — half the
+//     shuffles per gathered byte of the 16-lane layout, which is what the L1 data pipe was spending its time on);
 //   * the item's (col,val) pairs are read LANES at a time with one coalesced streaming load each and
 //     handed round the group with shuffles; lanes past the end re-read the last valid column with
 //     weight 0, so the gather loop has no predicates; the next chunk is prefetched;

@@ -356,7 +356,15 @@ class Engine:
         S[:, :n].copy_(S_dev)
         ctl.copy_(torch.tensor([0, 0, n, 0], dtype=torch.int32), non_blocking=False)
         self.loss_out.zero_()
-        return (n + self.B_cap - 1) // self.B_cap
+        self._epoch_pos = 0
+        self._epoch_steps = (n + self.B_cap - 1) // self.B_cap
+        return self._epoch_steps
+
+    def rewind_epoch(self):
+        """Start the resident epoch over (same triples) without touching the data: only the window is reset."""
+        S, ctl = self._epoch
+        ctl[:2].zero_()
+        self._epoch_pos = 0
 
     def epoch_step(self):
         S, ctl = self._epoch

@@ -121,22 +121,22 @@ def UniformSample_original(dataset, neg_ratio=1):
 
 
 def UniformSample_original_python(dataset):
-    """The reference's numpy fallback (code/utils.py:84-110), kept for comparisons."""
-    user_num = dataset.trainDataSize
-    users = np.random.randint(0, dataset.n_users, user_num)
-    allPos = dataset.allPos
-    S = []
-    for user in users:
-        posForUser = allPos[user]
-        if len(posForUser) == 0:
+    """numpy fallback with the reference's semantics (code/utils.py:84-110): trainDataSize iid users from the global
+    numpy RNG, one uniform positive each, negatives redrawn until they miss the user's positives; users without
+    positives are skipped.  Kept for comparisons — the C sampler above is what the procedures use."""
+    picked = np.random.randint(0, dataset.n_users, dataset.trainDataSize)
+    positives = dataset.allPos
+    triples = []
+    for u in picked:
+        mine = positives[u]
+        if len(mine) == 0:
             continue
-        positem = np.random.choice(posForUser)
-        while True:
-            negitem = np.random.randint(0, dataset.m_items)
-            if negitem not in posForUser:
-                break
-        S.append([user, positem, negitem])
-    return np.array(S)
+        p = np.random.choice(mine)
+        n = np.random.randint(0, dataset.m_items)
+        while n in mine:
+            n = np.random.randint(0, dataset.m_items)
+        triples.append((u, p, n))
+    return np.asarray(triples)
 
 
 # ---------------------------------------------------------------------------- helpers
@@ -221,27 +221,32 @@ class timer:
 
 
 # ---------------------------------------------------------------------------- metrics (host, numpy)
+# Same definitions as the reference (code/utils.py:173-200,212-217); the procedures use the device kernel
+# (ops.rank_metrics), these stay for API parity and as its cross-check.
+def _discounts(k):
+    return 1.0 / np.log2(np.arange(k) + 2.0)
+
+
 def RecallPrecision_ATk(test_data, r, k):
-    right_pred = r[:, :k].sum(1)
-    recall_n = np.array([len(test_data[i]) for i in range(len(test_data))])
-    return {'recall': np.sum(right_pred / recall_n), 'precision': np.sum(right_pred) / k}
+    """r: {0,1} hit matrix [n_users, >=k] in rank order -> sums over users of recall@k and precision@k."""
+    hits = np.asarray(r)[:, :k].sum(axis=1)
+    n_relevant = np.fromiter((len(t) for t in test_data), dtype=np.float64, count=len(test_data))
+    return {'recall': float(np.sum(hits / n_relevant)), 'precision': float(np.sum(hits) / k)}
 
 
 def NDCGatK_r(test_data, r, k):
-    assert len(r) == len(test_data)
-    pred_data = r[:, :k]
-    test_matrix = np.zeros((len(pred_data), k))
-    for i, items in enumerate(test_data):
-        test_matrix[i, :min(k, len(items))] = 1
-    disc = 1. / np.log2(np.arange(2, k + 2))
-    idcg = np.sum(test_matrix * disc, axis=1)
-    dcg = np.sum(pred_data * disc, axis=1)
-    idcg[idcg == 0.] = 1.
-    return np.sum(dcg / idcg)
+    """Sum over users of DCG@k / IDCG@k with IDCG over min(k, |ground truth|) ones (0 -> 1)."""
+    r = np.asarray(r)
+    if len(r) != len(test_data):
+        raise AssertionError("one hit row per user expected")
+    disc = _discounts(k)
+    dcg = (r[:, :k] * disc).sum(axis=1)
+    ideal = np.array([disc[:min(k, len(t))].sum() for t in test_data])
+    ideal[ideal == 0.0] = 1.0
+    return float(np.sum(dcg / ideal))
 
 
 def getLabel(groundTruth, predictTopK):
-    if not isinstance(groundTruth, (list, set, tuple, np.ndarray)):
-        groundTruth = [groundTruth]
-    gt = set(int(x) for x in groundTruth)
-    return np.array([1.0 if int(x) in gt else 0.0 for x in predictTopK], dtype=np.float32)
+    """Hit vector (float32) of a ranked list against a ground-truth collection (or a single item)."""
+    truth = groundTruth if isinstance(groundTruth, (list, set, tuple, np.ndarray)) else [groundTruth]
+    return np.isin(np.asarray(predictTopK).astype(np.int64), np.fromiter((int(x) for x in truth), dtype=np.int64)).astype(np.float32)

@@ -214,6 +214,22 @@ def test_training_with_device_sampler(lg, tmp_path):
         lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048, device_sampler=False)
 
 
+def test_train_driver_checkpoint_resume(lg, tmp_path):
+    """The driver's checkpoint uses the reference's schema/keys and resumes to the same state."""
+    from lgcn_b200 import train
+    args = ['--synthetic', 'tiny', '--epochs', '3', '--bpr_batch', '256', '--checkpoint_dir', str(tmp_path), '--save_every', '1']
+    try:
+        m = train.main(args)
+        ck = torch.load(str(tmp_path / 'last.pth.tar'), map_location='cpu', weights_only=False)
+        assert set(ck['model_state'].keys()) == {'embedding_user.weight', 'embedding_item.weight'}
+        assert ck['epoch'] == 3 and float(ck['optimizer_state']['state'][0]['step']) > 0
+        assert torch.equal(ck['model_state']['embedding_user.weight'], m.embedding_user.weight.detach().cpu())
+        m2 = train.main(args[:3] + ['4'] + args[4:] + ['--resume', str(tmp_path / 'last.pth.tar')])
+        assert m2._engine._host_step > m._engine._host_step * 0 + int(float(ck['optimizer_state']['state'][0]['step']))
+    finally:
+        lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048, epochs=1000, device_sampler=False)
+
+
 def test_epoch_mode_equals_step_mode(lg, golden_tiny):
     """Device-resident epoch (window advance + graph replay) == explicit stageOne calls on the same batches."""
     g = golden_tiny
