@@ -22,6 +22,10 @@ class SpmmPlan(Structure):
     ]
 
 
+class SpmmPeers(Structure):
+    _fields_ = [("n_peers", c_int32), ("pad", c_int32), ("y", c_void_p * 7), ("p", c_void_p * 7)]
+
+
 class AdamScalars(Structure):
     _fields_ = [
         ("step_size", c_float), ("bc2_sqrt", c_float), ("beta1", c_float), ("beta2", c_float),
@@ -35,16 +39,18 @@ _SIGNATURES = {
     "lgcn_abi_version": (ctypes.c_int, []),
     "lgcn_last_error": (c_char_p, []),
     "lgcn_device_info": (ctypes.c_int, [POINTER(c_int32)]),
+    "lgcn_enable_peer_access": (ctypes.c_int, [c_int32]),
+    "lgcn_debug_poke": (ctypes.c_int, [_P, c_float, c_int32, POINTER(c_int32), _P]),
     "lgcn_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "lgcn_csr_build": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "lgcn_coo_to_csr": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
     "lgcn_spmm_plan_count": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P]),
     "lgcn_spmm_plan_workspace_bytes": (c_size_t, [c_int32]),
-    "lgcn_spmm_plan_fill": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P, c_size_t, _P]),
+    "lgcn_spmm_plan_fill": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_size_t, _P]),
     "lgcn_spmm_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                      POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P]),
     "lgcn_spmm_adam_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
-                                          POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, _P]),
+                                          POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
     "lgcn_debug_spmm_variant": (ctypes.c_int, [ctypes.c_int]),
     "lgcn_adam_init": (ctypes.c_int, [_P, c_double, c_double, c_double, c_double, c_int32, _P]),
     "lgcn_adam_tick": (ctypes.c_int, [_P, _P]),

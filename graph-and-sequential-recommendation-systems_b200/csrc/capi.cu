@@ -49,6 +49,38 @@ extern "C" int lgcn_device_info(int32_t* out_host) {
     return 0;
 }
 
+// Peer access from the current device to `peer_device` (needed before a kernel may dereference memory of another GPU
+// that was mapped into this process, e.g. through CUDA IPC).  Idempotent.
+extern "C" int lgcn_enable_peer_access(int32_t peer_device) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail("enable_peer_access: %s", cudaGetErrorString(e));
+    if (dev == peer_device) return 0;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dev, peer_device);
+    if (!can) return fail("enable_peer_access: device %d cannot access device %d", dev, peer_device);
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return fail("enable_peer_access: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+__global__ void poke_kernel(float* p, float v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+// Diagnostic: store `value` into n floats at `ptr` from a kernel on the current device; returns the CUDA error code after
+// synchronising the stream (0 = ok).  out_host[0..3] = pointer attributes {type, device, current device, canAccessPeer}.
+extern "C" int lgcn_debug_poke(float* ptr, float value, int32_t n, int32_t* out_host, lgcn_stream_t stream) {
+    cudaPointerAttributes at; memset(&at, 0, sizeof(at));
+    cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+    int dev = -1; cudaGetDevice(&dev);
+    int can = -1; if (e == cudaSuccess && at.device != dev) cudaDeviceCanAccessPeer(&can, dev, at.device);
+    if (out_host) { out_host[0] = (int)at.type; out_host[1] = at.device; out_host[2] = dev; out_host[3] = can; }
+    poke_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(ptr, value, n);
+    e = cudaStreamSynchronize(as_stream(stream));
+    if (e != cudaSuccess) return fail("debug_poke: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ---- host sampler: glibc rand() stream, same draw order as sampling.cpp ---------------------
 extern "C" void lgcn_sampler_seed(uint32_t seed) { srand(seed); }
 

@@ -41,6 +41,9 @@ struct SpmmArgs {
     float4* P; float4* M; float4* V; const lgcn_adam_scalars_t* sc;   // adam epilogue
     const unsigned* row_mask;   // optional bitmap: items whose row bit is 0 are skipped (output not written)
     const unsigned* col_mask;   // optional bitmap: columns whose bit is 0 are known-zero rows of X (never read)
+    // fused exchange (row partition over GPUs): every finished row is also stored into the peers' copies of Y
+    // (and of P in the Adam epilogue) over NVLink, so no separate all-gather pass re-reads and re-sends it
+    int n_peers; float4* peerY[LGCN_MAX_PEERS]; float4* peerP[LGCN_MAX_PEERS];
 };
 
 __device__ __forceinline__ bool mask_bit(const unsigned* m, int i) { return (__ldg(m + (i >> 5)) >> (i & 31)) & 1u; }
@@ -154,9 +157,14 @@ __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, c
             adam_update1(pw.z, m.z, vv.z, g.z, b2, w1, w2, step_size, bc2s, eps);
             adam_update1(pw.w, m.w, vv.w, g.w, b2, w1, w2, step_size, bc2s, eps);
             a.P[off] = pw; a.M[off] = m; a.V[off] = vv;
-            if (a.Y != nullptr) st_stream_f4(a.Y + off, g);
+            for (int q = 0; q < a.n_peers; ++q) if (a.peerP[q]) st_stream_f4(a.peerP[q] + off, pw);
+            if (a.Y != nullptr) {
+                st_stream_f4(a.Y + off, g);
+                for (int q = 0; q < a.n_peers; ++q) if (a.peerY[q]) st_stream_f4(a.peerY[q] + off, g);
+            }
         } else {
             st_stream_f4(a.Y + off, g);
+            for (int q = 0; q < a.n_peers; ++q) st_stream_f4(a.peerY[q] + off, g);
         }
     }
 }
@@ -215,22 +223,33 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
 
 // ---- plan kernels -------------------------------------------------------------------------
 // ws ints: [0]=long cursor, [1]=segment cursor, then bins[seg_len+1], offsets[seg_len+1], cursors[seg_len+1]
+// A hub row is cut into at most kMaxParts segments: the last-arriving segment adds the partials serially, so the
+// number of parts bounds that tail (a 1.5 M-nnz item row: 256 parts of 5.9 k instead of 12 k parts of 128).
+constexpr int kMaxParts = 256;
+
+__device__ __forceinline__ void split_row(int deg, int seg_len, int& n_parts, int& len) {
+    n_parts = (deg + seg_len - 1) / seg_len;
+    if (n_parts > kMaxParts) n_parts = kMaxParts;
+    len = (deg + n_parts - 1) / n_parts;                     // equal-length parts, never empty
+    n_parts = (deg + len - 1) / len;
+}
+
+// counts: {n_long, n_segs, longest item}
 __global__ void plan_count_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* counts) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int deg = indptr[r + 1] - indptr[r];
     if (deg > seg_len) {
+        int n_parts, len; split_row(deg, seg_len, n_parts, len);
         atomicAdd(counts + 0, 1);
-        atomicAdd(counts + 1, (deg + seg_len - 1) / seg_len);
+        atomicAdd(counts + 1, n_parts);
+        atomicMax(counts + 2, len);
+    } else {
+        atomicMax(counts + 2, deg);
     }
 }
 
-__device__ __forceinline__ void split_row(int deg, int seg_len, int& n_parts, int& len) {
-    n_parts = (deg + seg_len - 1) / seg_len;
-    len = (deg + n_parts - 1) / n_parts;                     // equal-length parts, never empty
-}
-
-__global__ void plan_hist_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* bins) {
+__global__ void plan_hist_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* bins) {   // bins[0..max_len]
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int deg = indptr[r + 1] - indptr[r];
@@ -243,10 +262,10 @@ __global__ void plan_hist_kernel(const int* __restrict__ indptr, int n_rows, int
 }
 
 // offsets[l] = number of items longer than l  (descending-length layout)
-__global__ void plan_offsets_kernel(const int* __restrict__ bins, int seg_len, int* offsets) {
+__global__ void plan_offsets_kernel(const int* __restrict__ bins, int max_len, int* offsets) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int run = 0;
-    for (int l = seg_len; l >= 0; --l) { offsets[l] = run; run += bins[l]; }
+    for (int l = max_len; l >= 0; --l) { offsets[l] = run; run += bins[l]; }
 }
 
 __global__ void plan_scatter_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, const int* __restrict__ offsets,
@@ -321,7 +340,7 @@ static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
 static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices, const float* vals,
                      int32_t n_rows, int32_t d, const float* X, float* Y, float alpha, float beta,
                      const float* const* z_host, int32_t nz, const lgcn_spmm_plan_t* plan,
-                     const uint32_t* row_mask, const uint32_t* col_mask) {
+                     const uint32_t* row_mask, const uint32_t* col_mask, const lgcn_spmm_peers_t* peers) {
     LGCN_CHECK_ARG(X, "spmm: null X");
     LGCN_CHECK_ARG(n_rows >= 0, "spmm: n_rows < 0");
     LGCN_CHECK_ARG(nz >= 0 && nz <= LGCN_MAX_Z, "spmm: nz=%d out of range (max %d)", nz, LGCN_MAX_Z);
@@ -348,6 +367,16 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
     }
     a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr;
     a.row_mask = row_mask; a.col_mask = col_mask;
+    a.n_peers = 0;
+    for (int q = 0; q < LGCN_MAX_PEERS; ++q) { a.peerY[q] = nullptr; a.peerP[q] = nullptr; }
+    if (peers) {
+        LGCN_CHECK_ARG(peers->n_peers >= 0 && peers->n_peers <= LGCN_MAX_PEERS, "spmm: n_peers=%d out of range", peers->n_peers);
+        a.n_peers = peers->n_peers;
+        for (int q = 0; q < a.n_peers; ++q) {
+            LGCN_CHECK_ARG(((uintptr_t)peers->y[q] % 16) == 0 && ((uintptr_t)peers->p[q] % 16) == 0, "spmm: peer pointers must be 16-byte aligned");
+            a.peerY[q] = reinterpret_cast<float4*>(peers->y[q]); a.peerP[q] = reinterpret_cast<float4*>(peers->p[q]);
+        }
+    }
     return 0;
 }
 
@@ -361,33 +390,32 @@ extern "C" int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32
                                     int32_t* counts_out, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(indptr && counts_out && seg_len > 0 && n_rows >= 0, "spmm_plan_count: bad arguments");
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(counts_out, 0, 2 * sizeof(int32_t), st);
+    cudaMemsetAsync(counts_out, 0, 4 * sizeof(int32_t), st);
     if (n_rows > 0) plan_count_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(indptr, n_rows, seg_len, counts_out);
     LGCN_CHECK_LAUNCH("plan_count_kernel");
     return 0;
 }
 
-extern "C" size_t lgcn_spmm_plan_workspace_bytes(int32_t seg_len) {
-    if (seg_len <= 0) return 0;
-    return sizeof(int32_t) * (4 + 3 * ((size_t)seg_len + 1));
+extern "C" size_t lgcn_spmm_plan_workspace_bytes(int32_t max_len) {
+    if (max_len < 0) return 0;
+    return sizeof(int32_t) * (4 + 3 * ((size_t)max_len + 1));
 }
 
-extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
+extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len, int32_t max_len,
                                    int32_t* items_out, int32_t* seginfo_out,
                                    void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
-    LGCN_CHECK_ARG(indptr && items_out && seg_len > 0 && n_rows >= 0, "spmm_plan_fill: bad arguments");
-    LGCN_CHECK_ARG(seg_len <= (1 << 20), "spmm_plan_fill: seg_len too large");
-    LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_spmm_plan_workspace_bytes(seg_len), "spmm_plan_fill: workspace too small");
+    LGCN_CHECK_ARG(indptr && items_out && seg_len > 0 && n_rows >= 0 && max_len >= 0, "spmm_plan_fill: bad arguments");
+    LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_spmm_plan_workspace_bytes(max_len), "spmm_plan_fill: workspace too small");
     LGCN_CHECK_ARG(((uintptr_t)items_out % 16) == 0 && ((uintptr_t)seginfo_out % 16) == 0, "spmm_plan_fill: outputs must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     int* ws = static_cast<int*>(workspace);
-    int* long_cursor = ws; int* bins = ws + 4; int* offsets = bins + seg_len + 1; int* cursors = offsets + seg_len + 1;
-    cudaMemsetAsync(workspace, 0, lgcn_spmm_plan_workspace_bytes(seg_len), st);
+    int* long_cursor = ws; int* bins = ws + 4; int* offsets = bins + max_len + 1; int* cursors = offsets + max_len + 1;
+    cudaMemsetAsync(workspace, 0, lgcn_spmm_plan_workspace_bytes(max_len), st);
     if (n_rows == 0) return 0;
     const unsigned nb = (n_rows + 255) / 256;
     plan_hist_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, bins);
     LGCN_CHECK_LAUNCH("plan_hist_kernel");
-    plan_offsets_kernel<<<1, 32, 0, st>>>(bins, seg_len, offsets);
+    plan_offsets_kernel<<<1, 32, 0, st>>>(bins, max_len, offsets);
     LGCN_CHECK_LAUNCH("plan_offsets_kernel");
     plan_scatter_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, offsets, cursors, long_cursor,
                                             reinterpret_cast<int4*>(items_out), reinterpret_cast<int4*>(seginfo_out));
@@ -399,10 +427,11 @@ extern "C" int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, cons
                              int32_t n_rows, int32_t d, const float* X, float* Y,
                              float alpha, float beta, const float* const* z_host, int32_t nz,
                              const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
-                             lgcn_stream_t stream) {
+                             const lgcn_spmm_peers_t* peers_host, lgcn_stream_t stream) {
     SpmmArgs a;
-    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask)) return rc;
+    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask, peers_host)) return rc;
     LGCN_CHECK_ARG(Y, "spmm: Y is null");
+    for (int q = 0; q < a.n_peers; ++q) LGCN_CHECK_ARG(a.peerY[q], "spmm: peer Y pointer %d is null", q);
     return dispatch_spmm<false>(d, a, as_stream(stream));
 }
 
@@ -411,9 +440,9 @@ extern "C" int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices,
                                   float alpha, float beta, const float* const* z_host, int32_t nz,
                                   float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
                                   const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
-                                  lgcn_stream_t stream) {
+                                  const lgcn_spmm_peers_t* peers_host, lgcn_stream_t stream) {
     SpmmArgs a;
-    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask)) return rc;
+    if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask, peers_host)) return rc;
     LGCN_CHECK_ARG(P && M && V && scalars_dev, "spmm_adam: null P/M/V/scalars");
     LGCN_CHECK_ARG(((uintptr_t)P % 16) == 0 && ((uintptr_t)M % 16) == 0 && ((uintptr_t)V % 16) == 0, "spmm_adam: P/M/V must be 16-byte aligned");
     a.P = reinterpret_cast<float4*>(P); a.M = reinterpret_cast<float4*>(M); a.V = reinterpret_cast<float4*>(V);

@@ -20,9 +20,12 @@ Multi-GPU (one process per GPU, torch.distributed):
                   all-reducing the 18 MB gradient: G is a function of (out, indices) and out is replicated,
                   so every rank scatters the global batch itself (K2 is ~10 us).  Same result, and the
                   compute part stays inside the single-GPU CUDA graph.
-  mode 'rowpart'  rows of A partitioned in contiguous nnz-balanced blocks; every layer's output block
-                  is all-gathered; K2 runs redundantly on the full batch so no gradient collective is
-                  needed; Adam only touches owned rows.
+  mode 'rowpart'  rows of A partitioned in contiguous nnz-balanced blocks; K2 runs redundantly on the full
+                  batch so no gradient collective is needed; Adam only touches owned rows.  Exchange of every
+                  layer's output block: FUSED into K1 (p2p=True, default on one NVSwitch box) — the ranks map
+                  each other's buffers (CUDA IPC) and K1's epilogue stores each finished row into all peers
+                  over NVLink while the gathers of the following rows are in flight; a 4-byte all-reduce is the
+                  only collective left per layer.  p2p=False falls back to NCCL broadcasts after the kernel.
 """
 import torch
 
@@ -56,6 +59,26 @@ def allgather_rows(buf, bounds, group=None):
     return buf
 
 
+def map_peer_buffers(t, group=None):
+    """Every rank exports `t` (CUDA IPC handle of its allocation) and opens the others' in ITS OWN device context, so
+    that kernels on this GPU may load/store the peers' memory directly over NVLink.  Returns a list indexed by rank
+    (own entry = t itself).  torch is used for the handle exchange only."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    meta = t.untyped_storage()._share_cuda_()
+    objs = [None] * world
+    dist.all_gather_object(objs, (meta, t.storage_offset(), tuple(t.shape), tuple(t.stride())), group=group)
+    out = []
+    for p, (m, off, shape, stride) in enumerate(objs):
+        if p == rank:
+            out.append(t)
+            continue
+        st = torch.UntypedStorage._new_shared_cuda(dev, *m[1:])       # opened in my context: lazy peer access
+        out.append(torch.empty(0, dtype=t.dtype, device=t.device).set_(st, off, shape, stride))
+    return out
+
+
 def shard_batch(n, rank, world):
     """Contiguous shard [lo,hi) of a batch of n triples for data-parallel rank `rank`."""
     per = (n + world - 1) // world
@@ -65,7 +88,7 @@ def shard_batch(n, rank, world):
 
 class Engine:
     def __init__(self, csr, n_users, m_items, d, n_layers, device, *, lr=1e-3, decay=1e-4, B_cap=2048,
-                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True):
+                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True):
         if n_layers > 8:
             raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
         self.csr = csr
@@ -109,6 +132,19 @@ class Engine:
             self.bounds = balanced_row_bounds(csr.indptr.cpu(), self.world)
             self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
             self.local = csr.rows(self.r0, self.r1)
+        # fused exchange: map the peers' copies of every exchanged buffer
+        self.p2p = bool(p2p) and dist_mode == 'rowpart' and self.world > 1 and self.world - 1 <= 7
+        self._peer = {}
+        self._e0_synced = False
+        if self.p2p:
+            import torch.distributed as dist
+            from . import _lib
+            for p_dev in range(torch.cuda.device_count()):
+                _lib.load().lgcn_enable_peer_access(p_dev)
+            for buf in [self.E0, self.out] + self.X:
+                self._peer[buf.data_ptr()] = map_peer_buffers(buf, group)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+            dist.barrier(group)
         # batch staging: [ctl(4 x int32) | users | pos | neg] in one block so that a host batch is one H2D
         self._alloc_batch(self.B_cap)
         self._epoch = None          # (S tensor [3,cap], ctl) for epoch-resident mode
@@ -169,11 +205,23 @@ class Engine:
         """Every rank broadcasts its row block of `buf` (uneven all-gather, in place)."""
         allgather_rows(buf, self.bounds, self.group)
 
+    def _rank_barrier(self):
+        """Stream-ordered rendezvous of the ranks (4-byte all-reduce): every rank's stores into my buffers are complete
+        and visible once the kernels enqueued after it start.  Does not block the host."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
     def _layer(self, X, Y, alpha, beta, zs, row_mask=None, col_mask=None):
         r0, r1 = self.r0, self.r1
         if self.dist_mode == 'rowpart':
-            ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None)
-            self._allgather_rows(Y)
+            peers = self._peer.get(Y.data_ptr()) if self.p2p else None
+            if peers is not None:
+                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None,
+                         peer_y=[peers[p][r0:r1] for p in range(self.world) if p != self.rank])
+                self._rank_barrier()
+            else:
+                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None)
+                self._allgather_rows(Y)
         else:
             ops.spmm(self.csr, X, Y, alpha, beta, zs, row_mask=row_mask, col_mask=col_mask)
 
@@ -183,7 +231,7 @@ class Engine:
         masks=(m0, m1): only the rows a training step reads are produced — `out` on the batch rows m0, X_{L-1}
         on m0 + neighbours m1; earlier layers are complete.  The skipped rows are simply not written."""
         L, s = self.L, 1.0 / (self.L + 1)
-        if self.dist_mode == 'rowpart':
+        if self.dist_mode == 'rowpart' and not (self.p2p and self._e0_synced):
             self._allgather_rows(self.E0)       # owners publish their updated parameter rows
         if L == 0:
             self.out.copy_(self.E0)
@@ -278,9 +326,15 @@ class Engine:
         else:
             g = self.local if self.dist_mode == 'rowpart' else self.csr
 
+            peers_e0 = self._peer.get(self.E0.data_ptr()) if self.p2p else None
+
             def last(X, alpha, beta, zs, col_mask):
                 ops.spmm_adam(g, X, self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.scalars, alpha, beta,
-                              [z[r0:r1] for z in zs], col_mask=col_mask)
+                              [z[r0:r1] for z in zs], col_mask=col_mask,
+                              peer_p=None if peers_e0 is None else [peers_e0[p][r0:r1] for p in range(self.world) if p != self.rank])
+                if peers_e0 is not None:        # the updated parameter rows are already in every replica
+                    self._rank_barrier()
+                    self._e0_synced = True
             self._backward_chain(self.G, last)
         if self.dist_mode == 'dp':
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched

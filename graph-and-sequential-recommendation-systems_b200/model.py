@@ -129,7 +129,8 @@ class LightGCN(nn.Module):
                               B_cap=config.get('bpr_batch_size', 2048),
                               deterministic=config.get('deterministic', False),
                               use_graph=config.get('cuda_graph', True),
-                              dist_mode=config.get('dist_mode', None), prune=config.get('prune_dead_rows', True))
+                              dist_mode=config.get('dist_mode', None), prune=config.get('prune_dead_rows', True),
+                              p2p=config.get('rowpart_p2p', True))
         self._cache_key = None
         self._pack_params()
 
@@ -144,6 +145,7 @@ class LightGCN(nn.Module):
         self.embedding_user.weight.data = eng.E0[:nu]
         self.embedding_item.weight.data = eng.E0[nu:]
         self._cache_key = None
+        self._engine._e0_synced = False
 
     def _params_packed(self, user_w=None, item_w=None):
         eng = self._engine

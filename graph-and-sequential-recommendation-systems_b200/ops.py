@@ -57,17 +57,18 @@ class CSRGraph:
         """Degree-binned work items (descending length) + segments of the long rows."""
         lib = _lib.load()
         self.seg_len = int(seg_len)
-        counts = torch.zeros(2, dtype=torch.int32, device=self.device)
+        counts = torch.zeros(4, dtype=torch.int32, device=self.device)
         _lib.check(lib.lgcn_spmm_plan_count(_p(self.indptr), self.n_rows, self.seg_len, _p(counts), _stream()), "spmm_plan_count")
-        n_long, n_segs = (int(v) for v in counts.cpu().tolist())      # one-time setup sync
+        n_long, n_segs, max_len, _ = (int(v) for v in counts.cpu().tolist())      # one-time setup sync
+        self.max_item_len = max_len
         self.n_long, self.n_segs = n_long, n_segs
         self.n_items = self.n_rows - n_long + n_segs
         self._items = torch.zeros(max(self.n_items, 1) * 4, dtype=torch.int32, device=self.device)
         self._seginfo = torch.zeros(max(n_segs, 1) * 4, dtype=torch.int32, device=self.device)
         self._counters = torch.zeros(max(n_long, 1), dtype=torch.int32, device=self.device)
-        ws_bytes = lib.lgcn_spmm_plan_workspace_bytes(self.seg_len)
+        ws_bytes = lib.lgcn_spmm_plan_workspace_bytes(max_len)
         ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.int32, device=self.device)
-        _lib.check(lib.lgcn_spmm_plan_fill(_p(self.indptr), self.n_rows, self.seg_len, _p(self._items), _p(self._seginfo),
+        _lib.check(lib.lgcn_spmm_plan_fill(_p(self.indptr), self.n_rows, self.seg_len, max_len, _p(self._items), _p(self._seginfo),
                                            _p(ws), ws.numel() * 4, _stream()), "spmm_plan_fill")
         self._partials = None
         self._plan = None
@@ -159,7 +160,20 @@ def _z_array(zs):
     return arr, len(zs)
 
 
-def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None):
+def _peers_struct(peer_y=None, peer_p=None):
+    ys, ps = list(peer_y or []), list(peer_p or [])
+    n = max(len(ys), len(ps))
+    if n == 0:
+        return None
+    st = _lib.SpmmPeers()
+    st.n_peers = n
+    for i in range(n):
+        st.y[i] = ys[i].data_ptr() if i < len(ys) and ys[i] is not None else None
+        st.p[i] = ps[i].data_ptr() if i < len(ps) and ps[i] is not None else None
+    return byref(st)
+
+
+def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None, peer_y=None):
     """Y = alpha * (A @ X) + beta * sum(zs)  — K1.  X is indexed by column id, Y/zs by local row."""
     lib = _lib.load()
     d = X.shape[1]
@@ -172,11 +186,11 @@ def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None):
     for z in (zs or []):
         _need(z, torch.float32, "z", 2)
     _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
-                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _p(row_mask), _p(col_mask), _stream()), "spmm")
+                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(peer_y), _stream()), "spmm")
     return Y
 
 
-def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None):
+def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None, peer_p=None):
     """K1 with the Adam epilogue: grad = alpha*(A@X) + beta*sum(zs); P,M,V updated in place."""
     lib = _lib.load()
     d = X.shape[1]
@@ -185,7 +199,7 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_
     arr, nz = _z_array(zs)
     _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                       float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
-                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _stream()), "spmm_adam")
+                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p), _stream()), "spmm_adam")
 
 
 def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):

@@ -50,6 +50,7 @@ config = {
     'prune_dead_rows': True,    # training step skips rows of the last layers that the batch never reads
     'score_tensor_core': True,  # evaluation scores on tcgen05 (exact result; rows failing the certificate are redone)
     'device_sampler': False,    # True: K5 device sampler+shuffle (distributional parity); False: the reference's rand() stream
+    'rowpart_p2p': True,        # dist_mode='rowpart': K1 stores its rows into the peers' buffers (fused exchange)
     'spmm_seg_len': 128,        # degree-binning threshold of K1
 }
 

@@ -30,6 +30,7 @@ extern "C" {
 #define LGCN_ABI_VERSION 1
 #define LGCN_MAX_Z 8          /* max number of own-row addends in the SpMM epilogue (layers L <= 8) */
 #define LGCN_MAX_TOPK 128     /* max k of the fused score/top-k kernel */
+#define LGCN_MAX_PEERS 7      /* other GPUs of one NVSwitch box a K1 launch can store its rows into */
 
 typedef void* lgcn_stream_t;  /* cudaStream_t */
 
@@ -38,6 +39,12 @@ const char* lgcn_last_error(void);
 /* Device properties the host side sizes grids with: out[0]=SM count, out[1]=max dyn smem per block,
  * out[2]=compute capability major*10+minor.  Host-side query, no stream. */
 int lgcn_device_info(int32_t* out_host);
+/* Enable access from the current device to memory of `peer_device` (multi-GPU row partition: K1 stores its
+ * finished rows straight into the peers' buffers over NVLink).  Idempotent; host-side, no stream. */
+int lgcn_enable_peer_access(int32_t peer_device);
+/* diagnostic for the peer-memory path: kernel store of `value` to n floats at ptr, synchronous; out_host int32[4] =
+ * {pointer type, owning device, current device, canAccessPeer} */
+int lgcn_debug_poke(float* ptr, float value, int32_t n, int32_t* out_host, lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  device CSR builder + degree normaliser
@@ -98,12 +105,21 @@ typedef struct {
     float* partials;          /* float32[n_segs*d_max]                                             */
 } lgcn_spmm_plan_t;
 
-/* counts_out int32[2] = {n_long, n_segs} (device) */
+/* Fused SpMM + all-gather for the row partition: pointers to the PEER GPUs' copies of Y (and of P for
+ * the Adam epilogue), mapped into this process (CUDA IPC) and pre-offset to this rank's row block like Y itself.  The
+ * epilogue stores every finished row locally and into each peer over NVLink; the ranks then only need a barrier. */
+typedef struct {
+    int32_t n_peers; int32_t pad;
+    void* y[LGCN_MAX_PEERS];      /* NULL entries are skipped by the Adam variant when Y is not written */
+    void* p[LGCN_MAX_PEERS];      /* Adam variant only */
+} lgcn_spmm_peers_t;
+
+/* counts_out int32[4] = {n_long, n_segs, longest item, -} (device).  A row is cut into at most 256 segments. */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
                          int32_t* counts_out, lgcn_stream_t stream);
-size_t lgcn_spmm_plan_workspace_bytes(int32_t seg_len);
-/* fills items_out int32[4*n_items] and seginfo_out int32[4*n_segs] */
-int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
+size_t lgcn_spmm_plan_workspace_bytes(int32_t max_len);
+/* fills items_out int32[4*n_items] and seginfo_out int32[4*n_segs]; max_len = counts_out[2] */
+int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len, int32_t max_len,
                         int32_t* items_out, int32_t* seginfo_out,
                         void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 
@@ -123,7 +139,7 @@ int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* va
                   int32_t n_rows, int32_t d, const float* X, float* Y,
                   float alpha, float beta, const float* const* z_host, int32_t nz,
                   const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
-                  lgcn_stream_t stream);
+                  const lgcn_spmm_peers_t* peers_host, lgcn_stream_t stream);
 
 /* profiling hook: selects a tuning variant (unroll / CTA size / occupancy cap / L1 policy) of the d=64
  * plain kernel; 0 = shipped configuration.  Returns the previous value.  Results are identical. */
@@ -134,7 +150,7 @@ int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const floa
                        float alpha, float beta, const float* const* z_host, int32_t nz,
                        float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
                        const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
-                       lgcn_stream_t stream);
+                       const lgcn_spmm_peers_t* peers_host, lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Adam (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad)

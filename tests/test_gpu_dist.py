@@ -17,6 +17,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, mode, q):
+    p2p = mode != 'rowpart_nccl'
+    mode = 'rowpart' if mode.startswith('rowpart') else mode
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -27,7 +29,7 @@ def _worker(rank, world, port, mode, q):
         g = load_golden('tiny')
         cfg = dict(lg.world.config)
         cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), bpr_batch_size=len(g['users']),
-                   decay=float(g['decay']), lr=float(g['lr']), dist_mode=mode, deterministic=True)
+                   decay=float(g['decay']), lr=float(g['lr']), dist_mode=mode, deterministic=True, rowpart_p2p=p2p)
         ds = lg.InteractionDataset(int(g['n_users']), int(g['m_items']), g['train_user'], g['train_item'],
                                    g['test_user'], g['test_item'], config=cfg)
         m = lg.LightGCN(cfg, ds)
@@ -35,6 +37,7 @@ def _worker(rank, world, port, mode, q):
         with torch.no_grad():
             m.embedding_user.weight.copy_(torch.from_numpy(g['E0'][:nu])); m.embedding_item.weight.copy_(torch.from_numpy(g['E0'][nu:]))
         eng = m._engine
+        assert eng.p2p == (mode == 'rowpart' and p2p)
         B = len(g['users'])
         losses = []
         for s in range(3):
@@ -46,7 +49,7 @@ def _worker(rank, world, port, mode, q):
             else:
                 eng.step(u, p, n)
             losses.append(float(eng.loss_to_host()[2]))
-        if mode == 'rowpart':
+        if mode == 'rowpart' and not eng.p2p:
             eng._allgather_rows(eng.E0)
         params = eng.E0.cpu().numpy()
         with torch.no_grad():
@@ -63,7 +66,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["dp", "dp_idx", "rowpart"])
+@pytest.mark.parametrize("mode", ["dp", "dp_idx", "rowpart", "rowpart_nccl"])
 @pytest.mark.timeout(600)
 def test_two_rank_training_matches_reference(mode):
     if torch.cuda.device_count() < 2:

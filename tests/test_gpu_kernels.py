@@ -100,15 +100,17 @@ def test_coo_to_csr(lg, orc):
 
 # ------------------------------------------------------------------------------------ K1
 @pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
-@pytest.mark.parametrize("seg_len", [128, 8])
+@pytest.mark.parametrize("seg_len", [128, 8, 2])
 def test_spmm_vs_oracle(lg, orc, d, seg_len):
     rng = np.random.default_rng(d + seg_len)
-    nu, ni = 700, 450
+    nu, ni = 700, 900
     tu, ti = random_edges(rng, nu, ni, 9000, 100)
-    tu[:600] = 3; ti[:600] = rng.permutation(ni)[:600] if ni >= 600 else rng.integers(0, ni, 600)   # a hub row
+    tu[:800] = 3; ti[:800] = rng.permutation(ni)[:800]          # a hub row with 800 non-zeros
     g = build(lg, tu, ti, nu, ni, seg_len=seg_len)
-    if seg_len == 8:
+    if seg_len <= 8:
         assert g.n_segs > 0 and g.n_long > 0
+    if seg_len == 2:
+        assert g.max_item_len >= 3                       # the hub row hit the 256-segment cap: longer segments
     N = nu + ni
     X = rng.normal(0, 0.1, (N, d)).astype(np.float32)
     Z1 = rng.normal(0, 0.1, (N, d)).astype(np.float32); Z2 = rng.normal(0, 0.1, (N, d)).astype(np.float32)

@@ -28,7 +28,7 @@ def test_host_side_queries_without_gpu():
     assert lib.lgcn_bpr_workspace_bytes(2048, 64) >= 16 + 2048 * 4
     assert lib.lgcn_score_topk_workspace_bytes(100, 1000, 20) >= 100 * 32 * 20 * 8
     # argument validation happens before any launch
-    assert lib.lgcn_spmm_f32(None, None, None, 1, 64, None, None, 1.0, 0.0, None, 0, None, None, None, None) != 0
+    assert lib.lgcn_spmm_f32(None, None, None, 1, 64, None, None, 1.0, 0.0, None, 0, None, None, None, None, None) != 0
     assert b'null' in lib.lgcn_last_error()
 
 
