@@ -32,14 +32,17 @@ import torch
 from . import ops
 
 
-def balanced_row_bounds(indptr_cpu, parts):
-    """Contiguous row blocks with ~equal nnz: returns parts+1 boundaries (host int list)."""
+def balanced_row_bounds(indptr_cpu, parts, row_cost=0):
+    """Contiguous row blocks with ~equal cost = nnz + row_cost * rows: returns parts+1 boundaries (host int list).
+    row_cost expresses what publishing one output row to the peers costs in units of one gathered non-zero (with the
+    fused NVLink exchange a 256-byte row sent to 7 peers is worth ~64 gathers); 0 balances non-zeros only."""
     n_rows = indptr_cpu.numel() - 1
-    nnz = int(indptr_cpu[-1])
+    cost = indptr_cpu.to(torch.int64) + int(row_cost) * torch.arange(n_rows + 1, dtype=torch.int64)
+    total = int(cost[-1])
     bounds = [0]
     for p in range(1, parts):
-        target = nnz * p // parts
-        r = int(torch.searchsorted(indptr_cpu, torch.tensor(target, dtype=indptr_cpu.dtype), right=False))
+        target = total * p // parts
+        r = int(torch.searchsorted(cost, torch.tensor(target, dtype=torch.int64), right=False))
         r = max(bounds[-1], min(r, n_rows))
         bounds.append(r)
     bounds.append(n_rows)
@@ -88,7 +91,7 @@ def shard_batch(n, rank, world):
 
 class Engine:
     def __init__(self, csr, n_users, m_items, d, n_layers, device, *, lr=1e-3, decay=1e-4, B_cap=2048,
-                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True):
+                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True, row_cost=None):
         if n_layers > 8:
             raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
         self.csr = csr
@@ -129,7 +132,9 @@ class Engine:
         self.bounds = [0, N]
         self.local = csr
         if dist_mode == 'rowpart':
-            self.bounds = balanced_row_bounds(csr.indptr.cpu(), self.world)
+            if row_cost is None:
+                row_cost = d if (p2p and self.world > 1) else 0
+            self.bounds = balanced_row_bounds(csr.indptr.cpu(), self.world, row_cost)
             self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
             self.local = csr.rows(self.r0, self.r1)
         # fused exchange: map the peers' copies of every exchanged buffer

@@ -12,10 +12,14 @@ Differences that are not visible through the API:
   * `fused_train_step` runs forward+backward+Adam without materialising gradients (used by this
     package's utils.BPRLoss);  the generic path (`bpr_loss(...)` -> `.backward()` -> any torch
     optimiser) stays available for the reference's own utils.BPRLoss.
-Pop-gate (code/model.py:66-96,139-157) and item-item smoothing (:99-109,228-229) are outside the
-accelerated path and raise NotImplementedError when switched on.
+The two optional variants of the reference are supported through the generic
+autograd path: item-item smoothing (code/model.py:99-109,228-229) is one more K1 product with an explicit-value CSR
+(and its transpose in the backward), the popularity gate (code/model.py:66-96,139-157,176-181) keeps its two tiny MLPs
+as torch modules with the reference's parameter names.  Neither uses the fused training step.
 """
+import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import ops, world
@@ -94,6 +98,33 @@ class _BprLoss(torch.autograd.Function):
         return G, None, None, None, None
 
 
+class _I2ISmooth(torch.autograd.Function):
+    """items -> items + alpha * (I2I @ items)   (code/model.py:228-229); backward uses the transposed CSR."""
+
+    @staticmethod
+    def forward(ctx, items, model):
+        x = items.contiguous()
+        y = torch.empty_like(x)
+        ops.spmm(model._i2i, x, y, model.i2i_alpha, 1.0, [x])
+        ctx.model = model
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.model
+        gc = g.contiguous()
+        gx = torch.empty_like(gc)
+        ops.spmm(model._i2i_t, gc, gx, model.i2i_alpha, 1.0, [gc])
+        return gx, None
+
+
+def _csr_from_scipy(m, device, seg_len):
+    m = m.tocsr().astype(np.float32)
+    m.sort_indices()
+    return ops.CSRGraph(torch.from_numpy(m.indptr.astype(np.int32)).to(device), torch.from_numpy(m.indices.astype(np.int32)).to(device),
+                        torch.from_numpy(m.data.astype(np.float32)).to(device), m.shape[1], seg_len=seg_len)
+
+
 class LightGCN(nn.Module):
     def __init__(self, config, dataset):
         super().__init__()
@@ -109,9 +140,7 @@ class LightGCN(nn.Module):
         self.keep_prob = config.get('keep_prob', 0.6)
         self.use_pop_gate = bool(config.get('use_pop_gate', False))
         self.use_item_item = bool(config.get('use_item_item', False))
-        if self.use_pop_gate or (self.use_item_item and config.get('i2i_path')):
-            raise NotImplementedError("pop-gate / item-item variants are outside the accelerated hot path "
-                                      "(SURVEY.md §2 rows 1a/1b, §8f #4)")
+        self.i2i_alpha = float(config.get('i2i_alpha', 0.0))
         # Same RNG consumption as the reference (code/model.py:57-60): two default nn.Embedding inits on
         # the CPU generator, then normal_(std=0.1) on user then item table.
         self.embedding_user = nn.Embedding(self.n_users, self.latent_dim)
@@ -130,9 +159,53 @@ class LightGCN(nn.Module):
                               deterministic=config.get('deterministic', False),
                               use_graph=config.get('cuda_graph', True),
                               dist_mode=config.get('dist_mode', None), prune=config.get('prune_dead_rows', True),
-                              p2p=config.get('rowpart_p2p', True))
+                              p2p=config.get('rowpart_p2p', True), row_cost=config.get('rowpart_row_cost', None))
         self._cache_key = None
         self._pack_params()
+        seg_len = int(config.get('spmm_seg_len', ops.DEFAULT_SEG_LEN))
+
+        # popularity gate (code/model.py:66-96): same construction order, so the CPU RNG stream matches the reference
+        self.pop_hidden = int(config.get('pop_hidden', 32))
+        self.gate_hidden = int(config.get('gate_hidden', 64))
+        self.gate_entropy_coeff = float(config.get('gate_entropy_coeff', 1e-4))
+        self.pop_gate_temp = float(config.get('pop_gate_temp', 1.0))
+        self.item_pop_scalar, self.pop_mlp, self.gate_mlp = None, None, None
+        if self.use_pop_gate:
+            pop = torch.log1p(torch.from_numpy(np.asarray(dataset.items_D)).float().clamp(min=0.0))
+            self.item_pop_scalar = ((pop - pop.mean()) / (pop.std() + 1e-8)).to(self.device)
+            self.pop_mlp = nn.Sequential(nn.Linear(1, self.pop_hidden), nn.ReLU(), nn.Linear(self.pop_hidden, self.latent_dim)).to(self.device)
+            self.gate_mlp = nn.Sequential(nn.Linear(2 * self.latent_dim, self.gate_hidden), nn.ReLU(), nn.Linear(self.gate_hidden, 1)).to(self.device)
+
+        # item-item smoothing (code/model.py:99-109): explicit-value CSR and its transpose, both served by K1
+        self._i2i = self._i2i_t = None
+        if self.use_item_item and config.get('i2i_path'):
+            import scipy.sparse as sp
+            try:
+                m = sp.load_npz(config['i2i_path'])
+                self._i2i = _csr_from_scipy(m, self.device, seg_len)
+                self._i2i_t = _csr_from_scipy(m.T, self.device, seg_len)
+                world.cprint(f"[I2I] loaded {config['i2i_path']}, nnz={m.nnz}")
+            except Exception as e:      # the reference only warns and carries on without the item graph
+                world.cprint(f"[I2I] WARNING: cannot load {config['i2i_path']}: {e}")
+                self._i2i = self._i2i_t = None
+
+    @property
+    def plain(self):
+        """True when neither optional variant is active, i.e. the fused training step applies."""
+        return not self.use_pop_gate and not (self._i2i is not None and self.i2i_alpha > 0.0)
+
+    def _fuse_item_embeddings(self, items_emb):
+        """gate = sigmoid(gate_mlp([items, pop_vec]) / T); fused = gate*items + (1-gate)*pop_vec  (code/model.py:139-157)."""
+        pop_vec = self.pop_mlp(self.item_pop_scalar.unsqueeze(1))
+        logit = self.gate_mlp(torch.cat([items_emb, pop_vec], dim=1))
+        if self.pop_gate_temp != 1.0:
+            logit = logit / self.pop_gate_temp
+        gate = torch.sigmoid(logit)
+        self._last_item_gate = gate
+        return gate * items_emb + (1.0 - gate) * pop_vec
+
+    def _items_for_scoring(self, all_items):
+        return self._fuse_item_embeddings(all_items).contiguous() if self.use_pop_gate else all_items
 
     # ------------------------------------------------------------------ parameter storage
     def _pack_params(self):
@@ -185,27 +258,37 @@ class LightGCN(nn.Module):
         if torch.is_grad_enabled() and (uw.requires_grad or iw.requires_grad):
             out = _Propagate.apply(uw, iw, self)
             self._cache_key = None
-            return out[:nu], out[nu:]
+            items = out[nu:]
+            if self._i2i is not None and self.i2i_alpha > 0.0:
+                items = _I2ISmooth.apply(items, self)
+            return out[:nu], items
         key = self._param_key()
         if self._cache_key != key:
             self._sync_params_into_engine(uw, iw)
             self._engine.forward()
             self._cache_key = key
+            self._items_smoothed = None
+            if self._i2i is not None and self.i2i_alpha > 0.0:
+                x = self._engine.out[nu:]
+                self._items_smoothed = torch.empty_like(x)
+                ops.spmm(self._i2i, x, self._items_smoothed, self.i2i_alpha, 1.0, [x])
         out = self._engine.out
-        return out[:nu], out[nu:]
+        items = out[nu:] if getattr(self, '_items_smoothed', None) is None else self._items_smoothed
+        return out[:nu], items
 
     def getUsersRating(self, users):
         """Scores of every item for a batch of users (code/model.py:114-123) -> (B, m_items)."""
         with torch.no_grad():            # the reference only calls this under no_grad (code/Procedure.py:161,174)
             all_users, all_items = self.computer()
             users = users.to(self.device, dtype=torch.int64).contiguous()
-            return ops.score_dense(all_users, all_items, users)
+            return ops.score_dense(all_users, self._items_for_scoring(all_items), users)
 
     def rank_topk(self, users, k, mask=True):
         """Fused getUsersRating + train-item mask (-1024) + top-k (code/Procedure.py:174-183):
         returns (item ids int64 [B,k], scores float32 [B,k]); the B x M matrix is never written."""
         with torch.no_grad():
             all_users, all_items = self.computer()
+            all_items = self._items_for_scoring(all_items)
             users = users.to(self.device, dtype=torch.int64).contiguous()
             g = self._csr
             mi, mx = (g.indptr, g.indices) if mask else (None, None)
@@ -216,15 +299,27 @@ class LightGCN(nn.Module):
 
     def getEmbedding(self, users, pos_items, neg_items):
         all_users, all_items = self.computer()
+        i_emb = self._fuse_item_embeddings(all_items) if self.use_pop_gate else all_items
         u = all_users[users.long()]
-        pos = all_items[pos_items.long()]
-        neg = all_items[neg_items.long()]
+        pos = i_emb[pos_items.long()]
+        neg = i_emb[neg_items.long()]
         return u, pos, neg, all_users, all_items
 
     def bpr_loss(self, users, pos, neg):
         """(bpr, reg) as in code/model.py:162-183; both support .backward() through loss + decay*reg."""
         uw, iw = self.embedding_user.weight, self.embedding_item.weight
         users, pos, neg = (t.to(torch.int64).contiguous() for t in (users, pos, neg))
+        if not self.plain:
+            # variants: the reference's arithmetic on top of the kernel-backed propagation (code/model.py:162-183)
+            u, pos_e, neg_e, _, _ = self.getEmbedding(users.to(self.device), pos.to(self.device), neg.to(self.device))
+            bpr = -torch.mean(F.logsigmoid((u * pos_e).sum(dim=1) - (u * neg_e).sum(dim=1)))
+            reg = 0.5 * (u.norm(2).pow(2) + pos_e.norm(2).pow(2) + neg_e.norm(2).pow(2)) / float(u.shape[0])
+            if self.use_pop_gate:
+                gates = torch.cat([self._last_item_gate[pos.to(self.device)], self._last_item_gate[neg.to(self.device)]], dim=0)
+                gates = torch.clamp(gates, 1e-6, 1.0 - 1e-6)
+                entropy = -(gates * torch.log(gates) + (1 - gates) * torch.log(1 - gates)).mean()
+                bpr = bpr - self.gate_entropy_coeff * entropy
+            return bpr, reg
         if torch.is_grad_enabled() and (uw.requires_grad or iw.requires_grad):
             out = _Propagate.apply(uw, iw, self)
             self._cache_key = None
@@ -235,12 +330,15 @@ class LightGCN(nn.Module):
 
     def forward(self, users, items):
         all_users, all_items = self.computer()
-        return (all_users[users.long()] * all_items[items.long()]).sum(dim=1)
+        i_emb = self._fuse_item_embeddings(all_items) if self.use_pop_gate else all_items
+        return (all_users[users.long()] * i_emb[items.long()]).sum(dim=1)
 
     # ------------------------------------------------------------------ fused training step
     def fused_train_step(self, users, pos, neg, lr=None, B_global=0):
         """stageOne without autograd: forward, BPR, backward and Adam in one captured sequence.
         Returns the engine (loss in engine.loss_out on the device)."""
+        if not self.plain:
+            raise RuntimeError("the fused step covers the plain LightGCN path; pop-gate / item-item variants train through bpr_loss().backward()")
         if not self._params_packed():
             self._pack_params()
         eng = self._engine

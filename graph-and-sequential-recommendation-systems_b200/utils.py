@@ -63,7 +63,7 @@ class BPRLoss:
         self.model = recmodel
         self.weight_decay = config['decay']
         self.lr = config['lr']
-        self.fused = hasattr(recmodel, 'fused_train_step')
+        self.fused = hasattr(recmodel, 'fused_train_step') and getattr(recmodel, 'plain', True)
         if self.fused:
             recmodel._engine.decay = float(self.weight_decay)
             recmodel._engine.set_lr(self.lr)

@@ -41,6 +41,10 @@ config = {
     'sched_gamma': 0.5,
     'sched_milestones': [120, 240, 360, 480],
     'use_pop_gate': False,
+    'pop_hidden': 32,
+    'gate_hidden': 64,
+    'gate_entropy_coeff': 1e-4,
+    'pop_gate_temp': 1.0,
     'use_item_item': False,
     'i2i_path': None,
     'i2i_alpha': 0.0,

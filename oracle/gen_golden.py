@@ -26,14 +26,17 @@ CASES = {
     #        users items d  L  topks      batch
     'tiny': (300, 500, 64, 3, '[20]', 256),
     'edge': (40, 60, 32, 2, '[5,20]', 64),
+    # model variants of SURVEY.md §8f #4 (same data as 'tiny'): popularity gate / item-item smoothing
+    'popgate': (300, 500, 64, 3, '[20]', 256),
+    'i2i': (300, 500, 64, 3, '[20]', 256),
 }
 
 
 def make_case(name):
-    rng = np.random.default_rng(7 if name == 'tiny' else 11)
+    rng = np.random.default_rng(11 if name == 'edge' else 7)
     nu, ni = CASES[name][:2]
     train, test = {}, {}
-    if name == 'tiny':
+    if name != 'edge':
         for u in range(nu):
             deg = int(np.clip(np.rint(np.exp(rng.normal(2.6, 0.8))), 3, 120))
             items = rng.choice(ni - 20, size=min(deg, ni - 20), replace=False)     # last 20 items: never in train
@@ -70,6 +73,19 @@ def run_case(name):
     write_case(data_dir, train, test)
     sys.argv = ['x', '--dataset', name, '--tensorboard', '0', '--checkpoint_dir', os.path.join(tmp, 'ckpt'),
                 '--recdim', str(d), '--layer', str(L), '--topks', topks, '--bpr_batch', str(B)]
+    extra = {}
+    if name == 'popgate':
+        sys.argv += ['--use_pop_gate']
+    if name == 'i2i':
+        import scipy.sparse as sp
+        r2 = np.random.default_rng(5)
+        dense = (r2.random((ni, ni)) < 0.02) * r2.random((ni, ni))
+        np.fill_diagonal(dense, 0.0)
+        i2i = sp.csr_matrix(dense.astype(np.float32))
+        i2i_path = os.path.join(tmp, 'i2i.npz')
+        sp.save_npz(i2i_path, i2i)
+        sys.argv += ['--use_item_item', '--i2i_path', i2i_path, '--i2i_alpha', '0.3']
+        extra = dict(i2i_indptr=i2i.indptr.astype(np.int32), i2i_indices=i2i.indices.astype(np.int32), i2i_data=i2i.data.astype(np.float32), i2i_alpha=0.3)
     sys.path.insert(0, REF)
     sys.dont_write_bytecode = True
     import world                                         # noqa: E402  (the reference's)
@@ -91,6 +107,9 @@ def run_case(name):
     ds = dataloader.Loader(world.config, path=data_dir)
     utils.set_seed(2020)
     m = model.LightGCN(world.config, ds)
+    variant = name in ('popgate', 'i2i')
+    if name == 'popgate':
+        extra = {'sd_' + k.replace('.', '__'): v.detach().numpy().copy() for k, v in m.state_dict().items() if not k.startswith('embedding')}
     E0 = torch.cat([m.embedding_user.weight, m.embedding_item.weight]).detach().numpy().copy()
     g = m.Graph.coalesce()
     out_u, out_i = m.computer()
@@ -108,6 +127,8 @@ def run_case(name):
     m.zero_grad()
     total.backward()
     grad = torch.cat([m.embedding_user.weight.grad, m.embedding_item.weight.grad]).numpy().copy()
+    if name == 'popgate':
+        extra.update({'grad_' + k.replace('.', '__'): p.grad.numpy().copy() for k, p in m.named_parameters() if not k.startswith('embedding')})
     m.zero_grad()
 
     bpr = utils.BPRLoss(m, world.config)
@@ -126,6 +147,17 @@ def run_case(name):
     res = Procedure.Test(ds, m, 0)
     out_after = torch.cat(m.computer()).detach().numpy().copy()
 
+    if variant:
+        os.makedirs(GOLDEN, exist_ok=True)
+        np.savez_compressed(
+            os.path.join(GOLDEN, f'{name}.npz'),
+            n_users=ds.n_users, m_items=ds.m_items, d=d, L=L, topks=np.array(world.topks), decay=world.config['decay'],
+            lr=world.config['lr'], train_user=ds.trainUser, train_item=ds.trainItem, test_user=ds.testUser, test_item=ds.testItem,
+            E0=E0, out=out, users=users, pos=pos, neg=neg, loss=loss.item(), reg=reg.item(), grad=grad,
+            step_losses=np.array(step_losses), params_after=params_after[-1], test_users=np.array(test_users), rating=rating,
+            precision=res['precision'], recall=res['recall'], ndcg=res['ndcg'], **extra)
+        print(f"[golden] {name}: loss={loss.item():.6f} reg={reg.item():.6f} recall={res['recall']} ndcg={res['ndcg']}")
+        return
     # ---- the port must reproduce the reference bit for bit -----------------------------------
     sys.path.insert(0, ROOT)
     from oracle import ref_port

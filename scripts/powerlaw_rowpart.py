@@ -19,6 +19,8 @@ ap.add_argument("--items", type=int, default=2_000_000)
 ap.add_argument("--edges", type=int, default=500_000_000)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--row_cost", type=int, default=-1)
+ap.add_argument("--no_p2p", action="store_true")
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr_ = int(os.environ.get("LOCAL_RANK", "0"))
@@ -27,7 +29,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
 lg.world.configure(device=f"cuda:{lr_}")
 cfg = dict(lg.world.config)
-cfg.update(dist_mode='rowpart' if world > 1 else None, cuda_graph=False, bpr_batch_size=2048)
+cfg.update(dist_mode='rowpart' if world > 1 else None, cuda_graph=False, bpr_batch_size=2048,
+           rowpart_row_cost=None if a.row_cost < 0 else a.row_cost, rowpart_p2p=not a.no_p2p)
 t0 = time.perf_counter()
 tu, ti = lg.synth.make_powerlaw_device(a.users, a.items, a.edges, seed=2020)
 torch.cuda.synchronize(); t_gen = time.perf_counter() - t0
@@ -81,7 +84,7 @@ if rank == 0:
                       "nnz": g.nnz, "n_long": g.n_long, "n_segs": g.n_segs, "gen_s": t_gen, "csr_build_s": t_build,
                       "ms_per_step": float(ms.item()), "samples_per_s": B / (float(ms.item()) * 1e-3), "loss": loss,
                       "local_spmm_ms": spmm_ms, "local_spmm_alg_gbs": alg / (spmm_ms * 1e-3) / 1e9,
-                      "rows_local": eng.local.n_rows, "nnz_local": nnz_local,
+                      "rows_local": eng.local.n_rows, "nnz_local": nnz_local, "bounds": eng.bounds, "p2p": eng.p2p,
                       "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -267,3 +267,61 @@ def test_gowalla_step0_known_answer_end_to_end(lg, gowalla, tmp_path):
     assert abs(res['precision'][0] - float(gowalla['kat_precision'])) < 2e-9
     assert abs(res['recall'][0] - float(gowalla['kat_recall'])) < 2e-9
     assert abs(res['ndcg'][0] - float(gowalla['kat_ndcg'])) < 2e-7
+
+
+# ------------------------------------------------------------------------------------ variants
+def _variant_model(lg, g, tmp_path, kind):
+    over = {}
+    if kind == 'popgate':
+        over = dict(use_pop_gate=True)
+    else:
+        import scipy.sparse as sp
+        ni = int(g['m_items'])
+        m = sp.csr_matrix((g['i2i_data'], g['i2i_indices'], g['i2i_indptr']), shape=(ni, ni))
+        path = str(tmp_path / 'i2i.npz'); sp.save_npz(path, m)
+        over = dict(use_item_item=True, i2i_path=path, i2i_alpha=float(g['i2i_alpha']))
+    cfg, ds, m = make_model(lg, g, **over)
+    if kind == 'popgate':
+        sd = {k[3:].replace('__', '.'): torch.from_numpy(v) for k, v in g.items() if k.startswith('sd_')}
+        missing = m.load_state_dict(sd, strict=False)
+        assert set(missing.missing_keys) == {'embedding_user.weight', 'embedding_item.weight'} and not missing.unexpected_keys
+    return cfg, ds, m
+
+
+@pytest.mark.parametrize("kind", ["popgate", "i2i"])
+def test_model_variants_match_reference(lg, tmp_path, kind):
+    """use_pop_gate / use_item_item: loss, gradients, three optimiser steps and scores against the real reference."""
+    g = load_golden(kind)
+    cfg, ds, m = _variant_model(lg, g, tmp_path, kind)
+    assert not m.plain
+    nu = int(g['n_users'])
+    with torch.no_grad():
+        out = torch.cat(m.computer()).cpu().numpy()
+    assert rel_err(out, g['out']) < TOL
+    u, p, n = (t.cuda() for t in triples(g))
+    loss, reg = m.bpr_loss(u, p, n)
+    assert abs(loss.item() - float(g['loss'])) < 2e-5 * abs(float(g['loss']))
+    assert abs(reg.item() - float(g['reg'])) < 2e-5 * abs(float(g['reg']))
+    (loss + reg * float(g['decay'])).backward()
+    grad = torch.cat([m.embedding_user.weight.grad, m.embedding_item.weight.grad]).cpu().numpy()
+    assert rel_err(grad, g['grad']) < 5e-5
+    if kind == 'popgate':
+        for name, prm in m.named_parameters():
+            if not name.startswith('embedding'):
+                assert rel_err(prm.grad.cpu().numpy(), g['grad_' + name.replace('.', '__')]) < 1e-4, name
+    m.zero_grad()
+    bpr = lg.utils.BPRLoss(m, cfg)
+    assert not bpr.fused
+    B = len(g['users'])
+    for s in range(3):
+        l = bpr.stageOne(*(t.cuda() for t in triples(g, (s * 17) % B)))
+        assert abs(l - g['step_losses'][s]) < 5e-5 * abs(g['step_losses'][s])
+    assert rel_err(params(m), g['params_after']) < 2e-4
+    users = torch.from_numpy(g['test_users']).long()
+    with torch.no_grad():
+        rating = m.getUsersRating(users.cuda()).cpu().numpy()
+    assert rel_err(rating, g['rating']) < 1e-4
+    lg.world.configure(checkpoint_dir=str(tmp_path))
+    res = lg.Procedure.Test(ds, m, 0)
+    for name in ('precision', 'recall', 'ndcg'):
+        assert np.allclose(res[name], g[name], rtol=0, atol=1e-4)
