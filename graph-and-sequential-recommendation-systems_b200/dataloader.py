@@ -166,14 +166,17 @@ class InteractionDataset(BasicDataset):
         """Test interactions as a device CSR over testDict's users (key order), items sorted: the
         ground truth the on-device metric kernel searches.  Returns (users int64, indptr, indices)."""
         if self._test_csr is None:
-            td = self.testDict
-            users = np.fromiter(td.keys(), dtype=np.int64, count=len(td))
-            lens = np.fromiter((len(v) for v in td.values()), dtype=np.int64, count=len(td))
-            indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-            items = np.concatenate([np.sort(np.asarray(v, dtype=np.int32)) for v in td.values()]) if len(td) else np.zeros(0, np.int32)
+            # users in testDict key order = order of first appearance in the test file; items sorted per user
+            uniq, first = np.unique(self.testUser, return_index=True)
+            users = uniq[np.argsort(first, kind='stable')]
+            rank_of = np.empty(self.n_user, dtype=np.int64); rank_of[users] = np.arange(users.size)
+            r = rank_of[self.testUser]
+            order = np.lexsort((self.testItem, r))
+            items = self.testItem[order].astype(np.int32)
+            indptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=users.size))]).astype(np.int32)
             dev = world.device
-            self._test_csr = (torch.from_numpy(users).to(dev), torch.from_numpy(indptr).to(dev),
-                              torch.from_numpy(items.astype(np.int32)).to(dev))
+            self._test_csr = (torch.from_numpy(users.astype(np.int64)).to(dev), torch.from_numpy(indptr).to(dev),
+                              torch.from_numpy(items).to(dev))
         return self._test_csr
 
     def __getitem__(self, idx):

@@ -75,6 +75,21 @@ def test_loader_parses_reference_format(tmp_path):
     assert ds.getUserItemFeedback([0, 1], [1, 1]).tolist() == [1, 0]
 
 
+def test_test_csr_matches_testDict(monkeypatch):
+    """The vectorised test CSR (what the device metric kernel reads) is testDict in key order with sorted items."""
+    import torch
+    import lgcn_b200 as lg
+    monkeypatch.setattr(lg.world, 'device', torch.device('cpu'))
+    g = lg.synth.make_graph('tiny', seed=9)
+    perm = np.random.default_rng(0).permutation(g['test_user'].size)          # users interleaved, not grouped
+    ds = lg.InteractionDataset(g['n_users'], g['m_items'], g['train_user'], g['train_item'], g['test_user'][perm], g['test_item'][perm])
+    users, indptr, items = (t.numpy() for t in ds.test_csr())
+    td = ds.testDict
+    assert users.tolist() == list(td.keys())
+    for j, u in enumerate(users):
+        assert items[indptr[j]:indptr[j + 1]].tolist() == sorted(td[int(u)])
+
+
 def test_loader_round_trip_of_synthetic_graph(tmp_path):
     import lgcn_b200 as lg
     g = lg.synth.make_graph('tiny', seed=5)
