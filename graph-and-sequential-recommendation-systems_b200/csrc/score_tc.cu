@@ -1,56 +1,75 @@
 // score_tc.cu — K3 (tensor-core path): user x item scores on tcgen05 (TF32, TMEM accumulators, TMA-fed
 // shared memory), fused with the train-item mask and a per-row candidate filter, followed by an EXACT
 // fp32 rescoring of the candidates with a certificate — so the result is bit-identical to the exact
-// path (score_topk.cu) and to the CPU oracle, while > 99 % of the 2*U*M*d flops run on tensor cores.
+// path (score_topk.cu) and to the CPU oracle, while the 2*U*M*d flops run on tensor cores.
 //
 // Replaces torch.matmul (reference code/model.py:122), the -(1<<10) mask (code/Procedure.py:177-181)
 // and torch.topk (code/Procedure.py:183).
 //
-//   phase A  score_tc_kernel: CTA = 128 users x (a split of) all items, 6 warps:
-//              warp 0   TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 2-stage ring of 256-item B tiles
-//              warp 1   MMA issuer     8 x tcgen05.mma.kind::tf32 (M=128,N=256,K=8) per tile into one of two
-//                                      256-column TMEM accumulators; tcgen05.commit frees the smem stage and
-//                                      publishes the accumulator
-//              warps 2-5 epilogue      tcgen05.ld 32x32b.x32: thread t owns row 32*(warp%4)+t, compares 256
-//                                      approximate scores per tile with its running K'-th best and, on a hit,
-//                                      binary-searches the user's CSR row (train-item mask) before inserting
-//            -> per (row, split) the K' = 32 best approximate candidates.
-//   phase B  rescore_kernel: warp per row recomputes the candidates' scores as the fp32 FMA chain of the
-//            exact contract, selects the top-k (score desc, item id asc) and CERTIFIES it: every item that
-//            was filtered out has approx <= t (the smallest kept approx of its split), hence
-//            exact <= t + eps with eps = c * |u| * max|v|  (TF32 truncation bound, Cauchy-Schwarz);
-//            if t + eps < (k-th exact score) nothing outside the candidate set can enter the top-k.
-//            Rows that fail the certificate (or have < k unmasked items) are flagged and re-done by the
-//            exact kernel — the caller sees one bit-exact result either way.
+// The B x M score matrix is produced twice on the tensor pipe and never written.  Both passes run at the rate at
+// which the accumulators can be read out of TMEM (tcgen05.ld, 4 B per score), which for K = 64 is about half the
+// tensor-pipe rate — the epilogues are arranged to stay under that:
 //
-// Only d = 64 and k <= 24 take this path (A stays resident in shared memory: 32 KB; B ring 128 KB; lists 32 KB).
+//   pass 1   score_tc_kernel<1>: CTA = 256 users (two 128-row MMA tiles sharing every B tile) x a split of the
+//            item tiles.  warp 0 = TMA producer (4-stage ring of 128-item tiles), warp 1 = MMA issuer
+//            (16 x tcgen05.mma.kind::tf32 M128 N128 K8 per tile, double-buffered TMEM accumulators), warps 2-9 =
+//            epilogue (two groups of 8 warps taking alternate tiles): a thread owns one row and reads the FIRST 64
+//            items of the tile (tcgen05.ld 32x32b.x32) — a 50 % sample, which halves the TMEM traffic — and reduces them
+//            to ONE number, the largest approximate score among the sampled items that are NOT train items of the
+//            row (a cursor walks the sorted CSR row) -> sample-maxima matrix Mx[row][tile].
+//   select   tc_select_kernel: warp per row, radix select: the KSEL-th largest sample maximum is the row threshold
+//            tau.  KSEL unmasked sampled items score >= tau, hence about 2*KSEL +- sqrt(2*KSEL) items overall (any
+//            tau is SAFE — the certificate below does not depend on how it was chosen; a poor tau only costs time).
+//   pass 2   score_tc_kernel<2>: the same GEMM; the epilogue compares against the now FIXED tau (4 scores per
+//            compare), and the rare hits are mask-checked (cursor through the sorted train row) and appended to
+//            the row's candidate list in global memory.  No sorting, no cooperation between lanes.
+//   rescore  rescore_kernel: warp per row recomputes the candidates' scores as the fp32 FMA chain of the exact
+//            contract, selects the top-k (score desc, item id asc) and CERTIFIES it: every item that is not a
+//            candidate is masked or has approx < tau, hence exact < tau + eps with
+//            eps = c * |u| * max|v| (TF32 truncation bound, Cauchy-Schwarz); if tau + eps < (k-th exact score)
+//            nothing outside the candidate set can enter the top-k.  Rows that fail the certificate, overflow
+//            their candidate list or have < k unmasked items are flagged and re-done by the exact kernel — the
+//            caller sees one bit-exact result either way.
+//
+// Only d = 64 and k <= 24 take this path.
 #include "common.cuh"
 #include <cuda.h>
 #include <float.h>
+#include <stdlib.h>
 
 namespace lgcn {
 
-constexpr int TC_M = 128;            // users per CTA
-constexpr int TC_N = 256;            // items per MMA tile
+constexpr int TC_M = 128;            // rows per MMA
+constexpr int TC_RT = 2;             // row tiles per CTA (both consume the same B tile from shared memory)
+constexpr int TC_ROWS = TC_M * TC_RT;
+constexpr int TC_N = 128;            // items per tile
 constexpr int TC_D = 64;             // embedding width handled by this path
-constexpr int TC_KP = 32;            // candidates kept per (row, split)
-constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int TC_KEEP = 16;            // entries a buffer is compacted to
+constexpr int TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 16;     // lane quarter = warp % 4 (hardware rule) x 2 row tiles x 2 column halves of the item tile
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int TC_HALF = TC_N / 2;    // items per epilogue warp and tile
 constexpr int TC_ATOM_K = 32;        // fp32 elements per 128-byte swizzle atom row
-constexpr int TC_A_ATOM_BYTES = TC_M * 128;           // 16 KB
-constexpr int TC_B_ATOM_BYTES = TC_N * 128;           // 32 KB
-constexpr int TC_A_BYTES = 2 * TC_A_ATOM_BYTES;       // 32 KB
-constexpr int TC_B_STAGE_BYTES = 2 * TC_B_ATOM_BYTES; // 64 KB
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_A_BYTES + TC_STAGES * TC_B_STAGE_BYTES + 2 * (8 * 32 * TC_KP) * 4 + TC_M * 4 + 128;
+constexpr int TC_A_ATOM_BYTES = TC_M * 128;                 // 16 KB: one row tile, one K atom
+constexpr int TC_A_BYTES = TC_RT * 2 * TC_A_ATOM_BYTES;     // 64 KB
+constexpr int TC_B_ATOM_BYTES = TC_N * 128;                 // 16 KB
+constexpr int TC_B_STAGE_BYTES = 2 * TC_B_ATOM_BYTES;       // 32 KB
+constexpr int TC_STG = 16;                                  // pass 1: maxima staged per row before a flush (64-byte row segments)
+constexpr int TC_STG_FLOATS = TC_EPI_WARPS * 32 * TC_STG;   // per epilogue warp 32 rows x TC_STG
+constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_A_BYTES + TC_STAGES * TC_B_STAGE_BYTES + TC_STG_FLOATS * 4 + 256;
+constexpr int TC_CAP = 32;           // hit events (4 neighbouring scores each) per (row, split, column half)
+constexpr int TC_KSEL = 28;          // tau = KSEL-th largest maximum of the 50 % sample: 56 +- 7.5 items reach it (k <= 24)
+constexpr int TC_MAX_SPLITS = 16;
 constexpr float TC_EPS_C = 0.0025f;  // > 2^-9 (both operands truncated to 10 mantissa bits) + accumulation slack
 
 struct TcArgs {
-    const long long* users; int Bt; int m_items;
+    int Bt; int m_items;
+    const long long* users;
     const int* mask_indptr; const int* mask_indices; int mask_col_offset;
     int tiles_per_split; int n_splits;
-    float* cand_val; int* cand_idx;      // [Bt][2*n_splits][TC_KP]
-    float* cand_tau;                     // [Bt][2*n_splits]: everything the sub-stream dropped is <= this
+    float* tile_max; int tile_stride;    // pass 1 out: [bt_pad][tile_stride]: maxima over the first 64 items of each tile
+    const float* tau;                    // pass 2 in : [bt_pad]
+    float4* cand_val; int* cand_idx;     // pass 2 out: [Bt][2*n_splits][TC_CAP] events: 4 scores | first item id + (masked bits << 28)
+    int* cand_cnt;                       //             [Bt][2*n_splits]  (-1: the list overflowed)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -67,10 +86,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (long long spin = 0; !done; ++spin) {
+    for (unsigned spin = 0; !done; ++spin) {
         asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1LL << 28)) __trap();          // a protocol bug must fail, not hang the GPU
+        if (spin > (1u << 28)) __trap();           // a protocol bug must fail, not hang the GPU
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -87,8 +106,8 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t a_desc, ui
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 lanes x 32 consecutive columns; the load is only ISSUED here — tmem_ld_wait() makes the registers valid
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -97,9 +116,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
 }
 
 // K-major operand, 128-byte swizzle, rows packed at 128 B (8-row groups 1024 B apart):
@@ -113,59 +138,99 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-// order-preserving float <-> int (for atomicMax on thresholds that may be negative)
-__device__ __forceinline__ int tc_enc(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
-__device__ __forceinline__ float tc_dec(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
-
-struct RowState { int cnt; float tau; };
-
-// Warp-cooperative compaction of the candidate buffers named in `need` (one bit per lane/row): every lane takes one
-// entry of the row, ranks it with 32 shuffles, the best TC_KEEP are written back and the row's threshold becomes
-// the TC_KEEP-th best.  Returns the calling lane's updated (cnt, tau).
-__device__ __noinline__ RowState tc_compact_rows(unsigned need, float* bv, int* bi, int* tau_row, int lane, int cnt, float tau) {
-    while (need) {
-        const int L = __ffs(need) - 1; need &= need - 1;
-        const int n = __shfl_sync(0xffffffffu, cnt, L);
-        const int slot = L * TC_KP + ((lane + L) & 31);
-        const float sv = (lane < n) ? bv[slot] : -FLT_MAX;
-        const int sid = (lane < n) ? bi[slot] : 0x7fffffff;
-        int rank = 0;
+__device__ __forceinline__ float tc_max32(const uint32_t (&r)[32]) {
+    float m[8];
 #pragma unroll
-        for (int o = 0; o < 32; ++o) {
-            const float so = __shfl_sync(0xffffffffu, sv, o);
-            rank += (so > sv || (so == sv && o < lane)) ? 1 : 0;
-        }
-        __syncwarp();
-        if (rank < TC_KEEP) { const int d = L * TC_KP + ((rank + L) & 31); bv[d] = sv; bi[d] = sid; }
-        const int src = __ffs(__ballot_sync(0xffffffffu, rank == TC_KEEP - 1)) - 1;
-        const float t16 = __shfl_sync(0xffffffffu, sv, src);
-        if (lane == L) { cnt = TC_KEEP; tau = fmaxf(tau, t16); atomicMax(tau_row + L, tc_enc(t16)); }
-        __syncwarp();
-    }
-    RowState r; r.cnt = cnt; r.tau = tau;
-    return r;
+    for (int i = 0; i < 8; ++i)
+        m[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+    return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+// columns named in `bad` (bit i = column i of the chunk) take no part
+__device__ __forceinline__ void tc_kill_columns(uint32_t (&r)[32], unsigned bad) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if ((bad >> i) & 1u) r[i] = __float_as_uint(-FLT_MAX);
+}
+// ties the registers of an in-flight tcgen05.ld to the preceding tcgen05.wait::ld for the compiler (no instruction)
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ unsigned tc_oob_bits(int i0, int m_items) {
+    if (i0 + 32 <= m_items) return 0u;
+    return (i0 < m_items) ? ~((1u << (m_items - i0)) - 1u) : 0xffffffffu;
 }
 
+// the row's train items ("mask"), walked in step with the item tiles: bits of the current 128-item tile
+struct TcMaskCursor {
+    const int* row; int cur, end, next, next2, off;
+    __device__ __forceinline__ void init(const TcArgs& a, bool live, int grow, int first_col) {
+        row = nullptr; cur = 0; end = 0; next = 0x7fffffff; next2 = 0x7fffffff; off = a.mask_col_offset;
+        if (!(live && a.mask_indptr)) return;
+        const long long my_user = a.users ? a.users[grow] : (long long)grow;
+        const int lo = __ldg(a.mask_indptr + my_user), hi = __ldg(a.mask_indptr + my_user + 1);
+        row = a.mask_indices + lo; end = hi - lo;
+        const int first_item = first_col + off;                            // first column id this CTA scores
+        int l = 0, hh = end;                                               // lower_bound into the sorted row
+        while (l < hh) { const int mid = (l + hh) >> 1; if (__ldg(row + mid) < first_item) l = mid + 1; else hh = mid; }
+        cur = l;
+        if (cur < end) next = __ldg(row + cur) - off;
+        if (cur + 1 < end) next2 = __ldg(row + cur + 1) - off;
+    }
+    // bits [0,64) and [64,128) of the tile starting at item ib; the entry after next is always already in flight
+    __device__ __forceinline__ void tile_bits(int ib, unsigned long long& b0, unsigned long long& b1) {
+        b0 = 0ull; b1 = 0ull;
+        while (next < ib + TC_N) {
+            const int o = next - ib;
+            if (o >= 64) b1 |= 1ull << (o - 64); else if (o >= 0) b0 |= 1ull << o;
+            ++cur; next = next2;
+            next2 = (cur + 1 < end) ? __ldg(row + cur + 1) - off : 0x7fffffff;
+        }
+    }
+};
+
+// pass 2: compare one 32-column chunk against the row's fixed threshold, 4 scores per compare.  A hit (rare per lane,
+// but some lane of the warp hits in every few groups) costs two stores: the 4 scores and where they came from —
+// which of them count is sorted out by the rescore kernel, so that the divergent path stays a handful of instructions.
+struct TcHits { float4* val; int* idx; int cnt; float tau; };
+__device__ __forceinline__ void tc_collect(const uint32_t (&r)[32], int i0, unsigned bad, TcHits& hs) {
+#pragma unroll
+    for (int g4 = 0; g4 < 8; ++g4) {
+        const float v0 = __uint_as_float(r[4 * g4]), v1 = __uint_as_float(r[4 * g4 + 1]);
+        const float v2 = __uint_as_float(r[4 * g4 + 2]), v3 = __uint_as_float(r[4 * g4 + 3]);
+        if (fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) >= hs.tau) {
+            if (hs.cnt < TC_CAP) {
+                hs.val[hs.cnt] = make_float4(v0, v1, v2, v3);
+                hs.idx[hs.cnt] = (i0 + 4 * g4) | (int)(((bad >> (4 * g4)) & 0xfu) << 28);
+            }
+            ++hs.cnt;                                                 // > TC_CAP at the end: the row is given up (flagged by rescore)
+        }
+    }
+}
+
+template <int PASS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024-B alignment
-    uint8_t* sA = smem;
-    uint8_t* sB = sA + TC_A_BYTES;
-    float* lv = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_STAGE_BYTES);      // [8 warps][32 rows][TC_KP]
-    int* li = reinterpret_cast<int*>(lv + 8 * 32 * TC_KP);
-    int* tau_sh = li + 8 * 32 * TC_KP;                                             // [TC_M] row thresholds shared by the two halves
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tau_sh + TC_M);
-    // bars: 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 tmem_full | 7,8 tmem_empty ; then the TMEM base address
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint8_t* sA = smem;                                    // [row tile][K atom][128 rows][128 B]
+    uint8_t* sB = sA + TC_A_BYTES;                         // [stage][K atom][128 items][128 B]
+    float* stg = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + TC_STG_FLOATS);
+    // bars: 0 a_full | 1..4 b_full | 5..8 b_empty | 9,10 tmem_full | 11,12 tmem_empty ; then the TMEM base address
+    constexpr int B_FULL = 1, B_EMPTY = 1 + TC_STAGES, T_FULL = 1 + 2 * TC_STAGES, T_EMPTY = 3 + 2 * TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T_EMPTY + 2);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ub = blockIdx.x * TC_M;
+    const int ub = blockIdx.x * TC_ROWS;
     const int n_item_tiles = (a.m_items + TC_N - 1) / TC_N;
     const int t_begin = blockIdx.y * a.tiles_per_split;
     const int t_end = min(n_item_tiles, t_begin + a.tiles_per_split);
@@ -173,11 +238,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (threadIdx.x == 0) {
         mbar_init(BAR(0), 1);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(1 + s), 1); mbar_init(BAR(3 + s), 1); }
-        for (int c = 0; c < 2; ++c) { mbar_init(BAR(5 + c), 1); mbar_init(BAR(7 + c), 256); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
+        for (int c = 0; c < 2; ++c) { mbar_init(BAR(T_FULL + c), 1); mbar_init(BAR(T_EMPTY + c), PASS == 1 ? 16 * TC_EPI_WARPS : 32 * TC_EPI_WARPS); }   // pass 1: one group per buffer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < TC_M) tau_sh[threadIdx.x] = tc_enc(-FLT_MAX);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -185,22 +249,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;                 // accumulator (buffer b, row tile rt) = columns (2b + rt) * 128 ...
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             mbar_expect_tx(BAR(0), TC_A_BYTES);
-            tma_load_2d(smem_u32(sA), &map_a, BAR(0), 0, ub);
-            tma_load_2d(smem_u32(sA + TC_A_ATOM_BYTES), &map_a, BAR(0), TC_ATOM_K, ub);
+            for (int rt = 0; rt < TC_RT; ++rt)
+                for (int ka = 0; ka < 2; ++ka)
+                    tma_load_2d(smem_u32(sA + (rt * 2 + ka) * TC_A_ATOM_BYTES), &map_a, BAR(0), ka * TC_ATOM_K, ub + rt * TC_M);
             for (int it = 0; it < n_tiles; ++it) {
                 const int s = it % TC_STAGES, r = it / TC_STAGES;
-                mbar_wait(BAR(3 + s), (r & 1) ^ 1);
-                mbar_expect_tx(BAR(1 + s), TC_B_STAGE_BYTES);
+                mbar_wait(BAR(B_EMPTY + s), (r & 1) ^ 1);
+                mbar_expect_tx(BAR(B_FULL + s), TC_B_STAGE_BYTES);
                 const int ib = (t_begin + it) * TC_N;
                 uint8_t* dst = sB + s * TC_B_STAGE_BYTES;
-                tma_load_2d(smem_u32(dst), &map_b, BAR(1 + s), 0, ib);
-                tma_load_2d(smem_u32(dst + TC_B_ATOM_BYTES), &map_b, BAR(1 + s), TC_ATOM_K, ib);
+                tma_load_2d(smem_u32(dst), &map_b, BAR(B_FULL + s), 0, ib);
+                tma_load_2d(smem_u32(dst + TC_B_ATOM_BYTES), &map_b, BAR(B_FULL + s), TC_ATOM_K, ib);
             }
         }
     } else if (warp == 1) {
@@ -209,101 +274,104 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(BAR(0), 0);
             for (int it = 0; it < n_tiles; ++it) {
                 const int s = it % TC_STAGES, r = it / TC_STAGES, acc = it & 1, ra = it >> 1;
-                mbar_wait(BAR(1 + s), r & 1);                 // B tile landed
-                mbar_wait(BAR(7 + acc), (ra & 1) ^ 1);        // accumulator drained by the epilogue
+                mbar_wait(BAR(B_FULL + s), r & 1);                 // B tile landed
+                mbar_wait(BAR(T_EMPTY + acc), (ra & 1) ^ 1);       // accumulator pair drained by the epilogue
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * TC_B_STAGE_BYTES);
 #pragma unroll
-                for (int j = 0; j < TC_D / 8; ++j) {
-                    const uint32_t koff = (j >> 2) * 0 + (j & 3) * 32;         // 32 bytes per K=8 step inside the atom
-                    const uint64_t da = umma_desc_k_sw128(a0 + (j >> 2) * TC_A_ATOM_BYTES + koff);
-                    const uint64_t db = umma_desc_k_sw128(b0 + (j >> 2) * TC_B_ATOM_BYTES + koff);
-                    tc_mma_tf32(tmem_base + acc * TC_N, da, db, TC_IDESC, j > 0 ? 1u : 0u);
+                for (int rt = 0; rt < TC_RT; ++rt) {
+#pragma unroll
+                    for (int j = 0; j < TC_D / 8; ++j) {
+                        const uint32_t koff = (j & 3) * 32;               // 32 bytes per K=8 step inside the atom
+                        const uint64_t da = umma_desc_k_sw128(a0 + (rt * 2 + (j >> 2)) * TC_A_ATOM_BYTES + koff);
+                        const uint64_t db = umma_desc_k_sw128(b0 + (j >> 2) * TC_B_ATOM_BYTES + koff);
+                        tc_mma_tf32(tmem_base + (acc * TC_RT + rt) * TC_N, da, db, TC_IDESC, j > 0 ? 1u : 0u);
+                    }
                 }
-                tc_commit(BAR(3 + s));                         // smem stage free when these MMAs retire
-                tc_commit(BAR(5 + acc));                       // accumulator ready
+                tc_commit(BAR(B_EMPTY + s));                       // smem stage free when these MMAs retire
+                tc_commit(BAR(T_FULL + acc));                      // accumulator pair ready
             }
         }
     } else {
-        // ================= epilogue: 8 warps, thread-per-row threshold filter =================
-        // Warp e reads TMEM lane quarter q = warp%4 (hardware rule) and every other 32-column chunk (half h), so a
-        // row is watched by two threads with private candidate buffers.  A thread only compares: max of 4 scores
-        // against its row threshold tau; hits are APPENDED to a 32-slot buffer (no sorting, no cooperation, lanes
-        // proceed independently).  When a buffer holds >= 24 entries the warp compacts it cooperatively (one entry
-        // per lane, rank by 32 shuffles) to its 16 best and raises tau to the 16th.  Everything that was ever
-        // dropped or skipped is <= the final tau, which is what phase B needs for its certificate.
-        const int e = warp - 2, q = warp & 3, h = e >> 2;
-        const int r = q * 32 + lane;                           // row of the tile owned by this thread
-        const bool live = (ub + r) < a.Bt;
-        const int* mrow = nullptr; int m_cur = 0, m_end = 0, m_next = 0x7fffffff;
-        if (live && a.mask_indptr) {
-            const long long my_user = a.users ? a.users[ub + r] : (long long)(ub + r);
-            const int lo = __ldg(a.mask_indptr + my_user), hi = __ldg(a.mask_indptr + my_user + 1);
-            mrow = a.mask_indices + lo; m_end = hi - lo;
-            const int first_item = t_begin * TC_N + a.mask_col_offset;        // first column id this CTA scores
-            int l = 0, hh = m_end;                                            // lower_bound: cursor into the sorted row
-            while (l < hh) { const int mid = (l + hh) >> 1; if (__ldg(mrow + mid) < first_item) l = mid + 1; else hh = mid; }
-            m_cur = l;
-            if (m_cur < m_end) m_next = __ldg(mrow + m_cur) - a.mask_col_offset;
-        }
-        float* bv = lv + e * (32 * TC_KP);                     // this warp's 32 buffers: slot(row, p) = row*32 + ((p+row)&31)
-        int* bi = li + e * (32 * TC_KP);
-        int cnt = 0; float tau = live ? -FLT_MAX : FLT_MAX; bool lost = false;
-        int* tau_row = tau_sh + q * 32;
-        for (int it = 0; it < n_tiles; ++it) {
-            const int acc = it & 1, ra = it >> 1;
-            mbar_wait(BAR(5 + acc), ra & 1);
-            tc_fence_after();
-            const int ib = (t_begin + it) * TC_N;
-#pragma unroll 1
-            for (int ch = h; ch < TC_N / 32; ch += 2) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_N + ch * 32), v);
-                const int i0 = ib + ch * 32;
-                // (2) train items of this row inside [i0, i0+32): advance the cursor through the sorted CSR row
-                unsigned mbits = 0;
-                while (m_next < i0 + 32) {
-                    if (m_next >= i0) mbits |= 1u << (m_next - i0);
-                    ++m_cur;
-                    m_next = (m_cur < m_end) ? __ldg(mrow + m_cur) - a.mask_col_offset : 0x7fffffff;
-                }
-                unsigned bad = mbits;                                       // masked or out-of-range columns: rejected at append time
-                if (i0 + 32 > a.m_items) bad |= (i0 < a.m_items) ? ~((1u << (a.m_items - i0)) - 1u) : 0xffffffffu;
-                tau = fmaxf(tau, tc_dec(tau_row[lane]));                    // the other half may have raised the row's threshold
-                // (3) filter: 4 scores at a time
-#pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    // make room first: a group appends at most 4 entries, so a buffer with <= 28 can never overflow
-                    const unsigned need = __ballot_sync(0xffffffffu, cnt > TC_KP - 4);
-                    if (need) { const RowState st = tc_compact_rows(need, bv, bi, tau_row, lane, cnt, tau); cnt = st.cnt; tau = st.tau; }
-                    const float m4 = fmaxf(fmaxf(v[4 * g4], v[4 * g4 + 1]), fmaxf(v[4 * g4 + 2], v[4 * g4 + 3]));
-                    if (m4 > tau) {
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const float sc = v[4 * g4 + x];
-                            if (sc > tau && !((bad >> (4 * g4 + x)) & 1u)) {
-                                if (cnt < TC_KP) {
-                                    const int d = lane * TC_KP + ((cnt + lane) & 31);
-                                    bv[d] = sc; bi[d] = i0 + 4 * g4 + x; ++cnt;
-                                } else lost = true;             // > 8 hits in one chunk on a nearly full buffer: give the row up
-                            }
-                        }
-                    }
-                }
+        // ================= epilogue: a thread owns one row; pass 2: one 64-item half of every tile, pass 1: the first half of every
+        // other tile (group g = e / 8 takes the tiles with it % 2 == g, i.e. always the same accumulator buffer) =================
+        const int e = warp - 2, q = warp & 3, rt = (e >> 2) & 1, grp = e >> 3;    // TMEM lane quarter q = warp % 4 is a hardware rule
+        const int half = (PASS == 1) ? 0 : grp;
+        const int row = ub + rt * TC_M + q * 32 + lane;
+        const bool live = row < a.Bt;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rt * TC_N + half * TC_HALF);
+        uint32_t ra_[32], rb_[32];
+
+        if (PASS == 3) {                                           // debug: MMA-only pacing (accumulators released unread)
+            for (int it = 0; it < n_tiles; ++it) {
+                const int acc = it & 1, rph = it >> 1;
+                mbar_wait(BAR(T_FULL + acc), rph & 1);
+                tc_fence_after();
+                tc_fence_before();
+                mbar_arrive(BAR(T_EMPTY + acc));
             }
-            tc_fence_before();
-            mbar_arrive(BAR(7 + acc));
-        }
-        __syncwarp();
-        if (live) {
-            const int n_sub = a.n_splits * 2, sub = blockIdx.y * 2 + h;
-            const size_t o = ((size_t)(ub + r) * n_sub + sub) * TC_KP;
-            for (int p = 0; p < TC_KP; ++p) {
-                const int d = lane * TC_KP + ((p + lane) & 31);
-                a.cand_val[o + p] = (p < cnt) ? bv[d] : -FLT_MAX;
-                a.cand_idx[o + p] = (p < cnt) ? bi[d] : 0x7fffffff;
+        } else         if (PASS == 1) {
+            // ---- maxima over 64 items, staged TC_STG tiles at a time so that the global stores are row segments ----
+            float* my = stg + e * (32 * TC_STG);                   // slot(row l, p) = l*TC_STG + ((p + l) % TC_STG)
+            int nbuf = 0;
+            float* out_rows = a.tile_max + (size_t)(ub + rt * TC_M + q * 32) * a.tile_stride;
+            auto flush = [&](int t0) {
+                __syncwarp();
+                for (int rr = (lane >> 4); rr < 32; rr += 2) {                       // two rows per step, 16 lanes each
+                    const int p = lane & (TC_STG - 1);                              // staged tiles are 2 apart (the other group has the rest)
+                    if (p < nbuf) out_rows[(size_t)rr * a.tile_stride + t0 + 2 * p] = my[rr * TC_STG + ((p + rr) & (TC_STG - 1))];
+                }
+                __syncwarp();
+            };
+            TcMaskCursor mc; mc.init(a, live, row, t_begin * TC_N);
+            int first_staged = t_begin + grp;
+            for (int it = grp; it < n_tiles; it += 2) {
+                const int acc = grp, rph = it >> 1;
+                const int ib = (t_begin + it) * TC_N;
+                unsigned long long mb0, mb1;
+                mc.tile_bits(ib, mb0, mb1);                        // before the wait: overlaps the MMA of this tile
+                const unsigned long long mb = half ? mb1 : mb0;
+                const int i0 = ib + half * TC_HALF;
+                mbar_wait(BAR(T_FULL + acc), rph & 1);
+                tc_fence_after();
+                const uint32_t tb = t_row + (uint32_t)(acc * TC_RT * TC_N);
+                tmem_ld32_issue(tb, ra_); tmem_ld32_issue(tb + 32, rb_);
+                tmem_ld_wait(ra_); tmem_ld_fence(rb_);
+                tc_fence_before();
+                mbar_arrive(BAR(T_EMPTY + acc));                   // accumulator free: this warp's part is in registers
+                // train items of the row, and the items TMA zero-filled in the ragged last tile, take no part
+                const unsigned bad0 = (unsigned)mb | tc_oob_bits(i0, a.m_items), bad1 = (unsigned)(mb >> 32) | tc_oob_bits(i0 + 32, a.m_items);
+                if (bad0) tc_kill_columns(ra_, bad0);
+                if (bad1) tc_kill_columns(rb_, bad1);
+                my[lane * TC_STG + ((nbuf + lane) & (TC_STG - 1))] = fmaxf(tc_max32(ra_), tc_max32(rb_));
+                if (++nbuf == TC_STG) { flush(first_staged); nbuf = 0; first_staged = t_begin + it + 2; }
             }
-            a.cand_tau[(size_t)(ub + r) * n_sub + sub] = lost ? FLT_MAX : fmaxf(tau, tc_dec(tau_row[lane]));
+            if (nbuf) flush(first_staged);
+        } else {
+            // ---- fixed threshold: collect everything >= tau that is not a train item ----
+            TcMaskCursor mc; mc.init(a, live, row, t_begin * TC_N);
+            TcHits hs;
+            hs.cnt = 0; hs.tau = live ? a.tau[row] : FLT_MAX;
+            const size_t list = live ? ((size_t)row * a.n_splits + blockIdx.y) * 2 + half : 0;
+            hs.val = a.cand_val + list * TC_CAP; hs.idx = a.cand_idx + list * TC_CAP;
+            for (int it = 0; it < n_tiles; ++it) {
+                const int acc = it & 1, rph = it >> 1;
+                const int ib = (t_begin + it) * TC_N;
+                unsigned long long mb0, mb1;
+                mc.tile_bits(ib, mb0, mb1);
+                const unsigned long long mb = half ? mb1 : mb0;
+                mbar_wait(BAR(T_FULL + acc), rph & 1);
+                tc_fence_after();
+                const uint32_t tb = t_row + (uint32_t)(acc * TC_RT * TC_N);
+                const int i0 = ib + half * TC_HALF;
+                tmem_ld32_issue(tb, ra_); tmem_ld32_issue(tb + 32, rb_);
+                tmem_ld_wait(ra_); tmem_ld_fence(rb_);
+                tc_fence_before();
+                mbar_arrive(BAR(T_EMPTY + acc));
+                tc_collect(ra_, i0, (unsigned)mb | tc_oob_bits(i0, a.m_items), hs);
+                tc_collect(rb_, i0 + 32, (unsigned)(mb >> 32) | tc_oob_bits(i0 + 32, a.m_items), hs);
+            }
+            if (live) a.cand_cnt[list] = (hs.cnt > TC_CAP) ? -1 : hs.cnt;
         }
     }
     tc_fence_before();
@@ -314,7 +382,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-// A operand: the batch's user rows, gathered and zero-padded to a multiple of 128 rows
+// A operand: the batch's user rows, gathered and zero-padded to a multiple of 256 rows
 __global__ void gather_rows_kernel(const float4* __restrict__ U, const long long* __restrict__ users, int Bt, int Bt_pad, float4* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;            // one float4 per thread, 16 per row (d = 64)
     if (i >= Bt_pad * 16) return;
@@ -336,15 +404,74 @@ __global__ void item_norm_max_kernel(const float4* __restrict__ V, int m_items, 
     if ((threadIdx.x & 31) == 0) atomicMax(vmax_bits, __float_as_int(nrm));        // non-negative floats order like ints
 }
 
-// phase B: warp per row — exact rescoring, top-k, certificate
+// order-preserving float -> uint (larger float <=> larger key)
+__device__ __forceinline__ unsigned tc_key(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float tc_unkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// select: warp per row — tau = KSEL-th largest sample maximum, to 16 significant key bits (sign, exponent, 7 mantissa
+// bits: tau is the lower edge of the bucket the KSEL-th largest falls into, so at least KSEL sample maxima reach it);
+// radix select, 2 x 8 bits from the top
+constexpr int SEL_WARPS = 4;
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+tc_select_kernel(int Bt, int n_item_tiles, const float* __restrict__ tile_max, int tile_stride, int ksel, float* __restrict__ tau_out) {
+    __shared__ int s_hist[SEL_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * SEL_WARPS + w;
+    if (b >= Bt) return;
+    const float* M0 = tile_max + (size_t)b * tile_stride;
+    const unsigned dead = tc_key(-FLT_MAX);                               // nothing but train items in the sample
+    unsigned prefix = 0; int remaining = ksel; bool enough = true;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = lane; i < 256; i += 32) s_hist[w][i] = 0;
+        __syncwarp();
+        const unsigned hi_mask = pass ? (0xffffffffu << (shift + 8)) : 0u;
+        for (int c = lane; c < n_item_tiles; c += 32) {
+            const unsigned key = tc_key(__ldg(M0 + c));
+            if (key != dead && ((key ^ prefix) & hi_mask) == 0u) atomicAdd(&s_hist[w][(key >> shift) & 255u], 1);
+        }
+        __syncwarp();
+        // lane l owns bins 255-8l .. 248-8l (descending); inclusive scan over lanes from the top
+        int mine = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mine += s_hist[w][255 - 8 * lane - i];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const unsigned hit = __ballot_sync(0xffffffffu, incl >= remaining);
+        if (hit == 0u) { enough = false; break; }                        // fewer than ksel usable tiles
+        const int L = __ffs(hit) - 1;
+        int digit = 0, rem2 = 0;
+        if (lane == L) {
+            int before = incl - mine;
+            for (int i = 0; i < 8; ++i) {
+                const int bin = 255 - 8 * lane - i, cnt = s_hist[w][bin];
+                if (before + cnt >= remaining) { digit = bin; rem2 = remaining - before; break; }
+                before += cnt;
+            }
+        }
+        digit = __shfl_sync(0xffffffffu, digit, L); remaining = __shfl_sync(0xffffffffu, rem2, L);
+        prefix |= (unsigned)digit << shift;
+        __syncwarp();
+    }
+    // smallest float whose key starts with the 16 selected bits (for negative values the low key bits run the other way)
+    if (lane == 0) tau_out[b] = enough ? tc_unkey(prefix) : -FLT_MAX;
+}
+
+// rescore: warp per row — exact rescoring of every candidate, top-k by rank counting, certificate
 constexpr int RS_WARPS = 4;
+constexpr int RS_CAP = 192;
+constexpr int RS_BATCH = 16;         // item rows staged per step
 __global__ void __launch_bounds__(RS_WARPS * 32)
-rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const long long* __restrict__ users, int Bt, int n_splits, int k,
-               const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const float* __restrict__ cand_tau, const int* __restrict__ vmax_bits,
+rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const long long* __restrict__ users, int Bt, int n_lists, int k,
+               const float4* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt,
+               const float* __restrict__ tau_row, const int* __restrict__ vmax_bits,
                long long* __restrict__ idx_out, float* __restrict__ val_out, int* __restrict__ flags, int* __restrict__ n_flagged) {
-    __shared__ float s_sc[RS_WARPS][32 * TC_KP];
-    __shared__ int s_id[RS_WARPS][32 * TC_KP];
-    __shared__ float s_u[RS_WARPS][TC_D];
+    __shared__ unsigned long long s_key[RS_WARPS][RS_CAP];           // (ordered exact score << 32) | (0x7fffffff - item id): larger is better
+    __shared__ int s_id[RS_WARPS][RS_CAP];
+    __shared__ int s_pre[RS_WARPS][32];
+    __shared__ __align__(16) float s_u[RS_WARPS][TC_D];
+    __shared__ __align__(16) float s_rows[RS_WARPS][RS_BATCH * 68];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * RS_WARPS + w;
     if (b >= Bt) return;
@@ -353,77 +480,91 @@ rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const l
     float un2 = 0.f;
     for (int c = lane; c < TC_D; c += 32) { const float x = __ldg(ur + c); s_u[w][c] = x; un2 += x * x; }
     for (int o = 16; o > 0; o >>= 1) un2 += __shfl_xor_sync(0xffffffffu, un2, o);
-    __syncwarp();
-    const int ncand = n_splits * TC_KP;
-    const size_t base = (size_t)b * ncand;
     const float eps = TC_EPS_C * sqrtf(un2) * __int_as_float(*vmax_bits);
-    // (1) approximate scores: find the k-th best; only candidates within 2*eps of it can be in the exact top-k
-    for (int c = lane; c < ncand; c += 32) { s_sc[w][c] = cand_val[base + c]; s_id[w][c] = cand_idx[base + c]; }
+    const float tau = tau_row[b];
+    // the row's hit events live in n_lists (<= 32) lists; flatten them with a prefix over the list lengths
+    const int my_cnt = (lane < n_lists) ? cand_cnt[(size_t)b * n_lists + lane] : 0;
+    bool lost = __any_sync(0xffffffffu, my_cnt < 0);
+    int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int T = __shfl_sync(0xffffffffu, incl, 31);
+    s_pre[w][lane] = incl - my_cnt;
     __syncwarp();
-    unsigned taken = 0; float kth_apx = -FLT_MAX;
-    for (int qq = 0; qq < k; ++qq) {
-        float bv = -FLT_MAX; int bc = -1;
-        for (int c = lane, t = 0; c < ncand; c += 32, ++t) {
-            const float s = s_sc[w][c];
-            if (!((taken >> t) & 1u) && s_id[w][c] != 0x7fffffff && s > bv) { bv = s; bc = c; }
-        }
-        float mv = bv; int mc = bc;
+    int n = 0;
+    if (!lost) {
+        for (int f0 = 0; f0 < T; f0 += 32) {
+            const int f = f0 + lane;
+            const bool have = f < T;
+            int li = 0;                                                // last list whose first event is <= f
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, mv, o); const int oc = __shfl_xor_sync(0xffffffffu, mc, o);
-            if (ov > mv || (ov == mv && oc > mc)) { mv = ov; mc = oc; }
-        }
-        if (mc >= 0 && (mc & 31) == lane) taken |= 1u << (mc >> 5);
-        kth_apx = mv;
-    }
-    const float keep_above = kth_apx - 2.f * eps;
-    // (2) exact fp32 FMA chain for the survivors
-    int valid = 0;
-    for (int c = lane; c < ncand; c += 32) {
-        const int id = s_id[w][c];
-        float s = -FLT_MAX;
-        if (id != 0x7fffffff && s_sc[w][c] >= keep_above) {
-            const float4* vr = reinterpret_cast<const float4*>(V + (size_t)id * TC_D);
-            s = 0.f;
+            for (int st = 16; st > 0; st >>= 1) if (s_pre[w][li + st] <= f) li += st;
+            float4 v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX); int meta = 0;
+            if (have) { const size_t at = ((size_t)b * n_lists + li) * TC_CAP + (f - s_pre[w][li]); v = cand_val[at]; meta = cand_idx[at]; }
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            const int first = meta & 0x0fffffff;
 #pragma unroll
-            for (int c4 = 0; c4 < TC_D / 4; ++c4) {                 // the exact contract: one fp32 FMA chain in k order
-                const float4 x = __ldg(vr + c4);
-                s = fmaf(s_u[w][4 * c4 + 0], x.x, s); s = fmaf(s_u[w][4 * c4 + 1], x.y, s);
-                s = fmaf(s_u[w][4 * c4 + 2], x.z, s); s = fmaf(s_u[w][4 * c4 + 3], x.w, s);
+            for (int x = 0; x < 4; ++x) {                              // keep the scores that reach tau and are not train items
+                const bool take = have && vv[x] >= tau && !((meta >> (28 + x)) & 1);
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                const int pos = n + __popc(m & ((1u << lane) - 1u));
+                if (take && pos < RS_CAP) s_id[w][pos] = first + x;
+                n += __popc(m);
             }
-            ++valid;
-        } else {
-            s_id[w][c] = 0x7fffffff;
         }
-        s_sc[w][c] = s;
+        if (n > RS_CAP) lost = true;
     }
-    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
-    // bound for everything that was filtered out: the largest final threshold of the row's sub-streams
-    float tmin = -FLT_MAX;
-    for (int s = lane; s < n_splits; s += 32) tmin = fmaxf(tmin, cand_tau[(size_t)b * n_splits + s]);
-    for (int o = 16; o > 0; o >>= 1) tmin = fmaxf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    if (lost || n < k) {                                             // the exact kernel redoes this row
+        if (lane == 0) { flags[b] = 1; atomicAdd(n_flagged, 1); }
+        return;
+    }
     __syncwarp();
-    float kth = -FLT_MAX;
-    for (int q = 0; q < k; ++q) {
-        float bv = -FLT_MAX; int bi = 0x7fffffff, bc = -1;
-        for (int c = lane; c < ncand; c += 32) {
-            const float s = s_sc[w][c]; const int id = s_id[w][c];
-            if (id != 0x7fffffff && (s > bv || (s == bv && id < bi))) { bv = s; bi = id; bc = c; }
-        }
+    // exact scores, RS_BATCH candidates at a time: the item rows are staged through shared memory with coalesced loads
+    // (two rows per warp instruction); a lane then runs the FMA chain of the exact contract over its own candidate's
+    // row.  Rows are 68 floats apart: 16-byte accesses of 8 consecutive lanes hit 32 different banks.
+    const float4* V4 = reinterpret_cast<const float4*>(V);
+    for (int c0 = 0; c0 < n; c0 += RS_BATCH) {
+        const int nb = min(RS_BATCH, n - c0);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bc = oc; }
+        for (int t = 0; t < RS_BATCH / 2; ++t) {
+            const int r = 2 * t + (lane >> 4);
+            if (r < nb) *reinterpret_cast<float4*>(&s_rows[w][r * 68 + 4 * (lane & 15)]) = __ldg(V4 + (size_t)s_id[w][c0 + r] * 16 + (lane & 15));
         }
-        if (bc >= 0 && (bc & 31) == lane) s_id[w][bc] = 0x7fffffff;       // taken
-        if (lane == 0) { idx_out[(size_t)b * k + q] = bi; val_out[(size_t)b * k + q] = bv; }
-        kth = bv;
+        __syncwarp();
+        if (lane < nb) {
+            const float* vr = &s_rows[w][lane * 68];
+            float sc = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < TC_D / 4; ++c4) {                   // one fp32 FMA chain in k order
+                const float4 x = *reinterpret_cast<const float4*>(vr + 4 * c4);
+                const float4 y = *reinterpret_cast<const float4*>(&s_u[w][4 * c4]);
+                sc = fmaf(y.x, x.x, sc); sc = fmaf(y.y, x.y, sc); sc = fmaf(y.z, x.z, sc); sc = fmaf(y.w, x.w, sc);
+            }
+            s_key[w][c0 + lane] = ((unsigned long long)tc_key(sc) << 32) | (unsigned)(0x7fffffff - s_id[w][c0 + lane]);
+        }
         __syncwarp();
     }
+    // rank of a candidate = how many others beat it (score desc, item id asc); ranks < k are the answer, in place
+    unsigned long long kth_key = 0ull;
+    for (int c0 = 0; c0 < n; c0 += 64) {
+        const int ca = c0 + lane, cb = c0 + 32 + lane;
+        const unsigned long long ka = ca < n ? s_key[w][ca] : 0ull, kb = cb < n ? s_key[w][cb] : 0ull;
+        int rka = 0, rkb = 0;
+        for (int j = 0; j < n; ++j) {
+            const unsigned long long o = s_key[w][j];                 // broadcast read
+            rka += (o > ka) ? 1 : 0; rkb += (o > kb) ? 1 : 0;
+        }
+        if (ca < n && rka < k) { idx_out[(size_t)b * k + rka] = 0x7fffffff - (int)(unsigned)ka; val_out[(size_t)b * k + rka] = tc_unkey((unsigned)(ka >> 32)); }
+        if (cb < n && rkb < k) { idx_out[(size_t)b * k + rkb] = 0x7fffffff - (int)(unsigned)kb; val_out[(size_t)b * k + rkb] = tc_unkey((unsigned)(kb >> 32)); }
+        if (ca < n && rka == k - 1) kth_key = ka;
+        if (cb < n && rkb == k - 1) kth_key = kb;
+    }
+    unsigned kth_hi = (unsigned)(kth_key >> 32);
+    for (int o = 16; o > 0; o >>= 1) kth_hi = max(kth_hi, __shfl_xor_sync(0xffffffffu, kth_hi, o));
     if (lane == 0) {
-        const bool ok = (valid >= k) && (tmin == -FLT_MAX || (tmin < FLT_MAX && tmin + eps < kth));
+        // everything that is not a candidate is a train item or has approx < tau  =>  exact < tau + eps
+        const float kth = tc_unkey(kth_hi);
+        const bool ok = (tau == -FLT_MAX || tau + eps < kth);
         flags[b] = ok ? 0 : 1;
         if (!ok) atomicAdd(n_flagged, 1);
     }
@@ -458,28 +599,54 @@ static int make_map(CUtensorMap* m, const float* base, uint64_t rows, uint32_t b
     return 0;
 }
 
+// Item-tile splits per 256-row block: the grid (row blocks x splits, one CTA per SM) should fill whole waves;
+// a split keeps >= 8 tiles so that the A load and the pipeline fill stay amortised.
 static int tc_pick_splits(int Bt, int m_items) {
-    const int row_tiles = (Bt + TC_M - 1) / TC_M, item_tiles = (m_items + TC_N - 1) / TC_N;
-    int want = (2 * sm_count() + row_tiles - 1) / row_tiles;
-    if (want < 2) want = 2;                         // >= 4 sub-streams per row: no single one can hold most of the top-k
-    if (want > 16) want = 16;                       // 2 sub-streams per split, 32 per row at most
-    if (want > item_tiles) want = item_tiles;
-    if (want < 1) want = 1;
-    return want;
+    const int row_blocks = (Bt + TC_ROWS - 1) / TC_ROWS, item_tiles = (m_items + TC_N - 1) / TC_N;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int best = 1; double best_eff = 0.0;
+    for (int s = 1; s <= TC_MAX_SPLITS; ++s) {
+        const int per = (item_tiles + s - 1) / s;
+        if (s > 1 && per < 8) break;
+        const int real = (item_tiles + per - 1) / per;
+        const long long ctas = (long long)row_blocks * real;
+        const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = real; }
+    }
+    return best;
+}
+
+struct TcLayout { int bt_pad, item_tiles, tile_stride, n_splits, tiles_per_split; size_t off_mx, off_tau, off_cv, off_ci, off_cc, off_vmax, total; };
+static TcLayout tc_layout(int Bt, int m_items) {
+    TcLayout L;
+    L.bt_pad = (Bt + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+    L.item_tiles = (m_items + TC_N - 1) / TC_N;
+    L.tile_stride = L.item_tiles;
+    L.n_splits = tc_pick_splits(Bt, m_items);
+    L.tiles_per_split = (L.item_tiles + L.n_splits - 1) / L.n_splits;
+    L.n_splits = (L.item_tiles + L.tiles_per_split - 1) / L.tiles_per_split;
+    size_t o = align_up((size_t)L.bt_pad * TC_D * 4, 1024);
+    L.off_mx = o;   o += align_up((size_t)L.bt_pad * L.tile_stride * 4, 256);
+    L.off_tau = o;  o += align_up((size_t)L.bt_pad * 4, 256);
+    L.off_cv = o;   o += align_up((size_t)Bt * 2 * L.n_splits * TC_CAP * 16, 256);
+    L.off_ci = o;   o += align_up((size_t)Bt * 2 * L.n_splits * TC_CAP * 4, 256);
+    L.off_cc = o;   o += align_up((size_t)Bt * 2 * L.n_splits * 4, 256);
+    L.off_vmax = o; o += 256;
+    L.total = o;
+    return L;
 }
 
 }  // namespace lgcn
 
 using namespace lgcn;
 
-// workspace: [A_gathered: Bt_pad*64 floats][cand_val: Bt*32*KP floats][cand_idx: Bt*32*KP ints][vmax: 16 B]
+// workspace: [A gathered][tile maxima][tau][cand_val][cand_idx][cand_cnt][vmax]
 extern "C" size_t lgcn_score_topk_tc_workspace_bytes(int32_t Bt, int32_t m_items, int32_t k) {
     if (Bt <= 0 || m_items <= 0 || k <= 0) return 0;
-    const size_t bt_pad = ((size_t)Bt + TC_M - 1) / TC_M * TC_M;
-    return align_up(bt_pad * TC_D * 4, 1024) + 2 * align_up((size_t)Bt * 32 * TC_KP * 4, 256) + align_up((size_t)Bt * 32 * 4, 256) + 256;
+    return tc_layout(Bt, m_items).total;
 }
 
-extern "C" int lgcn_score_topk_tc_supported(int32_t d, int32_t k) { return (d == TC_D && k >= 1 && k <= TC_KP - 8) ? 1 : 0; }
+extern "C" int lgcn_score_topk_tc_supported(int32_t d, int32_t k) { return (d == TC_D && k >= 1 && k <= 24) ? 1 : 0; }
 
 extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
                                   int32_t m_items, int32_t d, const int32_t* mask_indptr, const int32_t* mask_indices,
@@ -487,24 +654,26 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
                                   int32_t* flags_out, int32_t* n_flagged_out,
                                   void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(users_emb && items_emb && idx_out && val_out && flags_out && n_flagged_out, "score_topk_tc: null argument");
-    LGCN_CHECK_ARG(lgcn_score_topk_tc_supported(d, k), "score_topk_tc: only d=%d and k<=%d take the tensor-core path", TC_D, TC_KP - 8);
-    LGCN_CHECK_ARG(Bt > 0 && m_items >= k, "score_topk_tc: Bt=%d m_items=%d k=%d", Bt, m_items, k);
+    LGCN_CHECK_ARG(lgcn_score_topk_tc_supported(d, k), "score_topk_tc: only d=%d and k<=24 take the tensor-core path", TC_D);
+    LGCN_CHECK_ARG(Bt > 0 && m_items >= k && m_items < (1 << 28), "score_topk_tc: Bt=%d m_items=%d k=%d", Bt, m_items, k);
     LGCN_CHECK_ARG((mask_indptr == nullptr) == (mask_indices == nullptr), "score_topk_tc: mask arrays must both be set or both null");
-    LGCN_CHECK_ARG(workspace && ((uintptr_t)workspace % 1024) == 0 && workspace_bytes >= lgcn_score_topk_tc_workspace_bytes(Bt, m_items, k),
+    const TcLayout L = tc_layout(Bt, m_items);
+    LGCN_CHECK_ARG(workspace && ((uintptr_t)workspace % 1024) == 0 && workspace_bytes >= L.total,
                    "score_topk_tc: workspace too small or not 1024-byte aligned");
     LGCN_CHECK_ARG(((uintptr_t)items_emb % 16) == 0 && ((uintptr_t)users_emb % 16) == 0, "score_topk_tc: tables must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    const int bt_pad = (Bt + TC_M - 1) / TC_M * TC_M;
     char* w = static_cast<char*>(workspace);
     float* A = reinterpret_cast<float*>(w);
-    const size_t cand_bytes = align_up((size_t)Bt * 32 * TC_KP * 4, 256);
-    float* cand_val = reinterpret_cast<float*>(w + align_up((size_t)bt_pad * TC_D * 4, 1024));
-    int* cand_idx = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_val) + cand_bytes);
-    float* cand_tau = reinterpret_cast<float*>(reinterpret_cast<char*>(cand_idx) + cand_bytes);
-    int* vmax = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_tau) + align_up((size_t)Bt * 32 * 4, 256));
+    float* tile_max = reinterpret_cast<float*>(w + L.off_mx);
+    float* tau = reinterpret_cast<float*>(w + L.off_tau);
+    float4* cand_val = reinterpret_cast<float4*>(w + L.off_cv);
+    int* cand_idx = reinterpret_cast<int*>(w + L.off_ci);
+    int* cand_cnt = reinterpret_cast<int*>(w + L.off_cc);
+    int* vmax = reinterpret_cast<int*>(w + L.off_vmax);
+    const long long* users_ll = reinterpret_cast<const long long*>(users);
 
-    gather_rows_kernel<<<(bt_pad * 16 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(users_emb),
-                                                                 reinterpret_cast<const long long*>(users), Bt, bt_pad, reinterpret_cast<float4*>(A));
+    gather_rows_kernel<<<(L.bt_pad * 16 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(users_emb), users_ll, Bt, L.bt_pad,
+                                                                   reinterpret_cast<float4*>(A));
     LGCN_CHECK_LAUNCH("gather_rows_kernel");
     cudaMemsetAsync(vmax, 0, 16, st);
     cudaMemsetAsync(n_flagged_out, 0, sizeof(int32_t), st);
@@ -512,23 +681,31 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
     LGCN_CHECK_LAUNCH("item_norm_max_kernel");
 
     CUtensorMap map_a, map_b;
-    if (int rc = make_map(&map_a, A, (uint64_t)bt_pad, TC_M)) return rc;
+    if (int rc = make_map(&map_a, A, (uint64_t)L.bt_pad, TC_M)) return rc;
     if (int rc = make_map(&map_b, items_emb, (uint64_t)m_items, TC_N)) return rc;
     TcArgs a;
-    a.users = reinterpret_cast<const long long*>(users); a.Bt = Bt; a.m_items = m_items;
+    a.Bt = Bt; a.m_items = m_items; a.users = users_ll;
     a.mask_indptr = mask_indptr; a.mask_indices = mask_indices; a.mask_col_offset = mask_col_offset;
-    const int item_tiles = (m_items + TC_N - 1) / TC_N;
-    a.n_splits = tc_pick_splits(Bt, m_items);
-    a.tiles_per_split = (item_tiles + a.n_splits - 1) / a.n_splits;
-    a.n_splits = (item_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
-    a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_tau = cand_tau;
-    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    a.n_splits = L.n_splits; a.tiles_per_split = L.tiles_per_split;
+    a.tile_max = tile_max; a.tile_stride = L.tile_stride; a.tau = tau;
+    a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt;
+    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(score_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) return fail("score_topk_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    dim3 grid(bt_pad / TC_M, a.n_splits);
-    score_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
-    LGCN_CHECK_LAUNCH("score_tc_kernel");
-    rescore_kernel<<<(Bt + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, st>>>(users_emb, items_emb, reinterpret_cast<const long long*>(users), Bt,
-        2 * a.n_splits, k, cand_val, cand_idx, cand_tau, vmax, reinterpret_cast<long long*>(idx_out), val_out, flags_out, n_flagged_out);
+    dim3 grid(L.bt_pad / TC_ROWS, L.n_splits);
+    score_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
+    LGCN_CHECK_LAUNCH("score_tc_kernel<1>");
+    tc_select_kernel<<<(Bt + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(Bt, L.item_tiles, tile_max, L.tile_stride, TC_KSEL, tau);
+    LGCN_CHECK_LAUNCH("tc_select_kernel");
+    score_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
+    LGCN_CHECK_LAUNCH("score_tc_kernel<2>");
+    rescore_kernel<<<(Bt + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, st>>>(users_emb, items_emb, users_ll, Bt, 2 * L.n_splits, k,
+        cand_val, cand_idx, cand_cnt, tau, vmax, reinterpret_cast<long long*>(idx_out), val_out, flags_out, n_flagged_out);
     LGCN_CHECK_LAUNCH("rescore_kernel");
+    if (getenv("LGCN_TC_DEBUG_MMA_ONLY")) {
+        cudaFuncSetAttribute(score_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        score_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
+        LGCN_CHECK_LAUNCH("score_tc_kernel<3>");
+    }
     return 0;
 }

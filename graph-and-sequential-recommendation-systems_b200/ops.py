@@ -281,13 +281,17 @@ def score_topk(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=No
     return idx, val
 
 
-def score_topk_tc(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=None, mask_col_offset=0):
-    """K3 on tensor cores: same result as score_topk, bit for bit.  Returns (idx, val, n_rows_redone)."""
+TC_MIN_ITEMS = 16384      # below this the row threshold cannot be taken from tile maxima (128 items per tile, 48 tiles needed)
+
+
+def score_topk_tc(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=None, mask_col_offset=0, min_items=TC_MIN_ITEMS):
+    """K3 on tensor cores: same result as score_topk, bit for bit.  Returns (idx, val, n_rows_redone);
+    item tables smaller than `min_items` go to the exact kernel directly (every row counts as redone)."""
     lib = _lib.load()
     _need(users_emb, torch.float32, "users_emb", 2), _need(items_emb, torch.float32, "items_emb", 2)
     Bt = users_emb.shape[0] if users is None else users.numel()
     m_items, d = items_emb.shape
-    if not lib.lgcn_score_topk_tc_supported(d, k) or Bt == 0:
+    if not lib.lgcn_score_topk_tc_supported(d, k) or Bt == 0 or m_items < min_items:
         idx, val = score_topk(users_emb, items_emb, users, k, mask_indptr, mask_indices, mask_col_offset)
         return idx, val, Bt
     dev = items_emb.device

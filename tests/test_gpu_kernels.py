@@ -394,9 +394,9 @@ def test_score_topk_k_exceeds_unmasked_items(lg, orc):
 def test_score_topk_tensor_core_is_bit_identical_to_exact(lg, scale):
     """tcgen05 filter + exact rescoring + certificate == the exact kernel, indices AND scores."""
     rng = np.random.default_rng(int(scale * 10))
-    nu, ni, d, k = 700, 3001, 64, 20
-    tu, ti = random_edges(rng, nu, ni, 30000)
-    tu[:2990] = 5; ti[:2990] = rng.permutation(ni)[:2990]       # user 5: only 11 unmasked items -> must be flagged
+    nu, ni, d, k = 700, 20011, 64, 20
+    tu, ti = random_edges(rng, nu, ni, 60000)
+    tu[:ni - 11] = 5; ti[:ni - 11] = rng.permutation(ni)[:ni - 11]    # user 5: only 11 unmasked items -> must be flagged
     g = build(lg, tu, ti, nu, ni)
     out = (scale * rng.normal(0, 1, (nu + ni, d))).astype(np.float32)
     out[nu + 7] = out[nu + 3]                                   # exact ties
@@ -410,6 +410,20 @@ def test_score_topk_tensor_core_is_bit_identical_to_exact(lg, scale):
     ei, ev = lg.ops.score_topk(o[:nu], o[nu:], None, k)
     ti_, tv, _ = lg.ops.score_topk_tc(o[:nu], o[nu:], None, k)   # no mask
     assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+
+
+def test_score_topk_tensor_core_too_few_tiles_still_exact(lg):
+    """Fewer item tiles than the threshold rank: no row threshold exists, every candidate list overflows,
+    all rows are flagged and redone — the result is still the exact kernel's."""
+    rng = np.random.default_rng(11)
+    nu, ni, k = 300, 3001, 20
+    tu, ti = random_edges(rng, nu, ni, 9000)
+    g = build(lg, tu, ti, nu, ni)
+    o = dev(rng.normal(0, 0.3, (nu + ni, 64)).astype(np.float32))
+    ei, ev = lg.ops.score_topk(o[:nu], o[nu:], None, k, g.indptr, g.indices, nu)
+    ti_, tv, redone = lg.ops.score_topk_tc(o[:nu], o[nu:], None, k, g.indptr, g.indices, nu, min_items=0)
+    assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+    assert redone == nu
 
 
 def test_score_topk_tensor_core_small_item_table(lg):
