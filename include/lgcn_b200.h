@@ -220,8 +220,10 @@ int lgcn_score_topk(const float* users_emb, const float* items_emb, const int64_
                     int32_t mask_col_offset, int32_t k, int64_t* idx_out, float* val_out,
                     void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 /* Tensor-core path of the same operation (tcgen05 TF32 MMA + TMA + TMEM, d = 64, k <= 24): an approximate
- * filter keeps 32 candidates per row and item split, the candidates are rescored with the exact fp32 FMA chain
- * and the top-k is certified against everything that was filtered out.  Rows whose
+ * two-pass filter (sampled tile maxima -> row threshold -> the ~50 items that reach it) picks candidates, the
+ * candidates are rescored with the exact fp32 FMA chain and the top-k is certified against everything that was
+ * filtered out.  Meant for item tables of >= 16 k items (fewer tiles than the threshold rank:
+ * every row is flagged).  m_items < 2^28.  Rows whose
  * certificate fails get flags_out[b] = 1 (count in n_flagged_out, device int32[1]) and MUST be recomputed with
  * lgcn_score_topk; all other rows are bit-identical to it.  workspace must be 1024-byte aligned. */
 int lgcn_score_topk_tc_supported(int32_t d, int32_t k);
