@@ -74,6 +74,7 @@ _SIGNATURES = {
     "lgcn_sample_bpr": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int64, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P]),
     "lgcn_sampler_seed": (None, [c_uint32]),
     "lgcn_sample_negative": (c_int64, [c_int32, c_int32, c_int64, _P, _P, c_int32, _P]),
+    "lgcn_parse_interactions": (c_int64, [ctypes.c_char_p, _P, _P, c_int64, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
+#include <cstdio>
 
 namespace lgcn {
 
@@ -109,4 +111,49 @@ extern "C" int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int6
         }
     }
     return (int64_t)user_num * per_user;
+}
+
+// ---- ingest: the reference's interaction files --------------------------------------------------
+// "uid item item ..." per line, whitespace separated; blank lines and lines without items are skipped
+// (code/dataloader.py:82-115).  One pass over the file; pairs beyond `capacity` are counted, not stored.
+extern "C" int64_t lgcn_parse_interactions(const char* path, int64_t* users_out_host, int64_t* items_out_host, int64_t capacity,
+                                           int64_t* max_user_out_host, int64_t* max_item_out_host) {
+    if (!path) { set_error("parse_interactions: null path"); return -1; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("parse_interactions: cannot open %s", path); return -1; }
+    std::vector<char> buf;
+    {
+        char chunk[1 << 16];
+        size_t got;
+        while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+        fclose(f);
+    }
+    buf.push_back('\n');
+    int64_t n = 0, max_u = -1, max_i = -1, line_no = 1;
+    const char* p = buf.data();
+    const char* end = p + buf.size();
+    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+    while (p < end) {
+        // one line
+        int64_t uid = 0; bool have_uid = false; int64_t first_pair = n, line_max = -1;
+        while (p < end && *p != '\n') {
+            if (is_space(*p)) { ++p; continue; }
+            bool neg = false;
+            if (*p == '-' || *p == '+') { neg = (*p == '-'); ++p; }
+            if (p >= end || *p < '0' || *p > '9') { set_error("parse_interactions: %s line %lld: not an integer", path, (long long)line_no); return -2; }
+            int64_t v = 0;
+            while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; }
+            if (p < end && *p != '\n' && !is_space(*p)) { set_error("parse_interactions: %s line %lld: not an integer", path, (long long)line_no); return -2; }
+            if (neg) v = -v;
+            if (!have_uid) { uid = v; have_uid = true; continue; }
+            if (n < capacity && users_out_host && items_out_host) { users_out_host[n] = uid; items_out_host[n] = v; }
+            if (v > line_max) line_max = v;
+            ++n;
+        }
+        if (n > first_pair) { if (uid > max_u) max_u = uid; if (line_max > max_i) max_i = line_max; }
+        ++p; ++line_no;
+    }
+    if (max_user_out_host) *max_user_out_host = max_u;
+    if (max_item_out_host) *max_item_out_host = max_i;
+    return n;
 }

@@ -260,6 +260,17 @@ int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_n
                              int32_t neg_num, int32_t* out_host);
 
 /* ---------------------------------------------------------------------------------------------
+ * Ingest of the reference's interaction files
+ * replaces  the per-line Python parsing in Loader.__init__  code/dataloader.py:82-115
+ * "uid item item ..." per line, whitespace separated; blank lines and lines without items are skipped; every
+ * (uid, item) pair is appended in file order.  HOST pointers.  Returns the number of pairs in the file (< 0 on
+ * error); at most `capacity` pairs are stored (call with capacity 0 / null outputs to size the arrays).
+ * max_user/max_item: largest ids among the lines that have items (-1 for an empty file).
+ * -------------------------------------------------------------------------------------------*/
+int64_t lgcn_parse_interactions(const char* path, int64_t* users_out_host, int64_t* items_out_host, int64_t capacity,
+                                int64_t* max_user_out_host, int64_t* max_item_out_host);
+
+/* ---------------------------------------------------------------------------------------------
  * Device-side BPR sampler + shuffle
  * replaces  utils.UniformSample_original + utils.shuffle  code/utils.py:68-81,142-151 ; code/Procedure.py:50-55
  * indptr/indices: the adjacency CSR (user rows hold n_users + item).  Every user gets train_num/n_users triples

@@ -75,6 +75,47 @@ def test_loader_parses_reference_format(tmp_path):
     assert ds.getUserItemFeedback([0, 1], [1, 1]).tolist() == [1, 0]
 
 
+def test_native_parser_matches_the_references_line_loop(tmp_path):
+    """lgcn_parse_interactions against a restatement of the reference's parsing loop (code/dataloader.py:82-97):
+    tabs, runs of blanks, CRLF, a last line without newline, item-less and empty lines; errors name the line."""
+    import ctypes
+    import lgcn_b200 as lg
+    from lgcn_b200 import dataloader
+    rng = np.random.default_rng(3)
+    lines = []
+    for u in rng.permutation(300):
+        k = int(rng.integers(0, 6))
+        sep = ['  ', ' ', '\t'][int(rng.integers(0, 3))]
+        lines.append(sep.join([str(u)] + [str(int(x)) for x in rng.integers(0, 100000, k)]) + ['', ' ', '\r'][int(rng.integers(0, 3))])
+    lines.insert(5, ''); lines.insert(9, '   ')
+    text = '\n'.join(lines)                                    # no trailing newline
+    f = tmp_path / 'train.txt'
+    f.write_text(text)
+    eu, ei = [], []
+    for l in text.split('\n'):                                  # the reference's loop
+        if not l.strip():
+            continue
+        cols = l.strip().split()
+        items = [int(i) for i in cols[1:]]
+        if not items:
+            continue
+        eu.extend([int(cols[0])] * len(items)); ei.extend(items)
+    users, items = dataloader._parse_interactions(str(f))
+    assert users.tolist() == eu and items.tolist() == ei
+    lib = lg._lib.load()
+    mu, mi = ctypes.c_int64(), ctypes.c_int64()
+    n = lib.lgcn_parse_interactions(str(f).encode(), None, None, 0, ctypes.byref(mu), ctypes.byref(mi))
+    assert n == len(eu) and mu.value == max(eu) and mi.value == max(ei)
+    (tmp_path / 'bad.txt').write_text("0 1 2\n1 x7\n")
+    with pytest.raises(RuntimeError, match="line 2"):
+        dataloader._parse_interactions(str(tmp_path / 'bad.txt'))
+    with pytest.raises(RuntimeError, match="cannot open"):
+        dataloader._parse_interactions(str(tmp_path / 'missing.txt'))
+    (tmp_path / 'empty.txt').write_text("")
+    users, items = dataloader._parse_interactions(str(tmp_path / 'empty.txt'))
+    assert users.size == 0 and items.size == 0
+
+
 def test_test_csr_matches_testDict(monkeypatch):
     """The vectorised test CSR (what the device metric kernel reads) is testDict in key order with sorted items."""
     import torch
