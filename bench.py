@@ -50,14 +50,51 @@ def workload_graph(name):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
+    thread every millisecond (the timed region lasts tens of milliseconds — `nvidia-smi -lms` takes longer than that to
+    start); nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
-        self.proc, self.index = None, index
+        self.proc, self.index, self.thread, self.nvml = None, index, None, None
+        self.sm, self.bits, self.stop_flag = [], 0, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+            for cand in (uuid, "GPU-" + uuid):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+                except Exception:
+                    pass
+        except Exception:
+            pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            import threading
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,6 +102,16 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv, h = self.nvml
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": mx,
+                    "reasons": sorted(n for n, bit in self.REASONS if self.bits & bit), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +132,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm

@@ -31,7 +31,15 @@
 //            their candidate list or have < k unmasked items are flagged and re-done by the exact kernel — the
 //            caller sees one bit-exact result either way.
 //
-// Only d = 64 and k <= 24 take this path.
+// Item layout.  A tile holds the items {b*T + r : b = 0..127} of one residue r (T = number of tiles), block b sitting
+// in slot (b >> 1) + 64*(b & 1), and residue r is tile (r * mul) mod T with mul ~ 0.618 T: neighbouring item ids land
+// in tiles far apart (different splits), and the sampled half (slots 0-63) is the even blocks.  With items in id order a trained model puts most of a user's best items — popular items with small,
+// adjacent ids — into a few 64-item blocks; each block contributes ONE maximum, tau came out far too low and 70 % of
+// the rows overflowed their candidate lists (real gowalla after 10 epochs).  The interleaved layout makes a block a
+// spread-out sample.  A permuted copy of the item table is made per call (m_items * 256 B, a few us); the train-item
+// mask has to be given in the same position space, sorted per row (lgcn_score_topk_tc_item_positions + lgcn_csr_build).
+//
+// Only d = 64, k <= 24 and m_items >= 16384 take this path.
 #include "common.cuh"
 #include <cuda.h>
 #include <float.h>
@@ -59,10 +67,15 @@ constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_A_BYTES + TC_STAGES * TC
 constexpr int TC_CAP = 32;           // hit events (4 neighbouring scores each) per (row, split, column half)
 constexpr int TC_KSEL = 28;          // tau = KSEL-th largest maximum of the 50 % sample: 56 +- 7.5 items reach it (k <= 24)
 constexpr int TC_MAX_SPLITS = 16;
+constexpr int TC_MIN_ITEMS = 16384;  // >= 128 tiles: the holes of the interleaved layout all fall into block 127, and tau needs KSEL tiles
 constexpr float TC_EPS_C = 0.0025f;  // > 2^-9 (both operands truncated to 10 mantissa bits) + accumulation slack
+
+struct TcOrder { int T, mul, inv; };       // item layout, see tc_pos_of_item: inv = mul^-1 mod T
 
 struct TcArgs {
     int Bt; int m_items;
+    TcOrder order;
+    int hole_from_residue;               // tiles of residue >= this have no item in their last slot (128*T - m_items < 128 holes, all in block 127)
     const long long* users;
     const int* mask_indptr; const int* mask_indices; int mask_col_offset;
     int tiles_per_split; int n_splits;
@@ -71,6 +84,29 @@ struct TcArgs {
     float4* cand_val; int* cand_idx;     // pass 2 out: [Bt][2*n_splits][TC_CAP] events: 4 scores | first item id + (masked bits << 28)
     int* cand_cnt;                       //             [Bt][2*n_splits]  (-1: the list overflowed)
 };
+
+// position (tile * 128 + slot) <-> item id.  T = number of item tiles; item i belongs to "residue" r = i % T and block
+// b = i / T; it sits in tile (r * mul) % T (mul coprime to T, about 0.618 T: neighbouring ids land far apart, so a
+// run of popular ids is spread over all the splits of the tile range) and slot (b >> 1) + 64 * (b & 1).
+__host__ __device__ __forceinline__ int tc_pos_of_item(int i, TcOrder o) {
+    const int b = i / o.T, r = i - b * o.T;
+    return (int)(((long long)r * o.mul) % o.T) * TC_N + (b >> 1) + 64 * (b & 1);
+}
+__host__ __device__ __forceinline__ int tc_residue_of_tile(int tile, TcOrder o) { return (int)(((long long)tile * o.inv) % o.T); }
+__host__ __device__ __forceinline__ int tc_item_of_pos(int p, TcOrder o) {
+    const int s = p & (TC_N - 1);
+    return (2 * (s & 63) + (s >> 6)) * o.T + tc_residue_of_tile(p >> 7, o);
+}
+static TcOrder tc_order(int m_items) {
+    TcOrder o; o.T = (m_items + TC_N - 1) / TC_N;
+    auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+    o.mul = (int)(0.6180339887 * o.T); if (o.mul < 1) o.mul = 1;
+    while (gcd(o.mul, o.T) != 1) ++o.mul;
+    long long r0 = o.T, r1 = o.mul, t0 = 0, t1 = 1;                 // extended Euclid: t1 * mul == r1 (mod T)
+    while (r1 != 1) { const long long q = r0 / r1, r2 = r0 - q * r1, t2 = t0 - q * t1; r0 = r1; r1 = r2; t0 = t1; t1 = t2; }
+    o.inv = (int)(((t1 % o.T) + o.T) % o.T);
+    return o;
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,9 +123,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (unsigned spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 28)) __trap();           // a protocol bug must fail, not hang the GPU
+        // the suspend-time hint lets a waiting warp sleep in hardware instead of spinning through issue slots
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        if (spin > (1u << 24)) __trap();           // a protocol bug must fail, not hang the GPU
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -162,11 +199,6 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
-__device__ __forceinline__ unsigned tc_oob_bits(int i0, int m_items) {
-    if (i0 + 32 <= m_items) return 0u;
-    return (i0 < m_items) ? ~((1u << (m_items - i0)) - 1u) : 0xffffffffu;
-}
-
 // the row's train items ("mask"), walked in step with the item tiles: bits of the current 128-item tile
 struct TcMaskCursor {
     const int* row; int cur, end, next, next2, off;
@@ -205,6 +237,8 @@ __device__ __forceinline__ void tc_collect(const uint32_t (&r)[32], int i0, unsi
         const float v0 = __uint_as_float(r[4 * g4]), v1 = __uint_as_float(r[4 * g4 + 1]);
         const float v2 = __uint_as_float(r[4 * g4 + 2]), v3 = __uint_as_float(r[4 * g4 + 3]);
         if (fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) >= hs.tau) {
+            // (events whose only hits are train items are stored too — rescore drops them; testing for that here was
+            // measured at +70 us per pass on the divergent path, for nothing: the lists did not overflow either way)
             if (hs.cnt < TC_CAP) {
                 hs.val[hs.cnt] = make_float4(v0, v1, v2, v3);
                 hs.idx[hs.cnt] = (i0 + 4 * g4) | (int)(((bad >> (4 * g4)) & 0xfu) << 28);
@@ -270,27 +304,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            mbar_wait(BAR(0), 0);
-            for (int it = 0; it < n_tiles; ++it) {
-                const int s = it % TC_STAGES, r = it / TC_STAGES, acc = it & 1, ra = it >> 1;
-                mbar_wait(BAR(B_FULL + s), r & 1);                 // B tile landed
-                mbar_wait(BAR(T_EMPTY + acc), (ra & 1) ^ 1);       // accumulator pair drained by the epilogue
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * TC_B_STAGE_BYTES);
+        // The whole warp runs the loop, so that descriptors and barrier addresses are computed in uniform registers; only
+        // tcgen05.mma / tcgen05.commit are issued by one lane.  (Inside `if (lane == 0)` every MMA carries a chain of vector ALU
+        // ops + R2UR, and this warp shares its scheduler with four epilogue warps.)
+        const bool leader = (lane == 0);
+        mbar_wait(BAR(0), 0);
+        const uint64_t da0 = umma_desc_k_sw128(smem_u32(sA));
+        for (int it = 0; it < n_tiles; ++it) {
+            const int s = it % TC_STAGES, r = it / TC_STAGES, acc = it & 1, ra = it >> 1;
+            mbar_wait(BAR(B_FULL + s), r & 1);                     // B tile landed
+            mbar_wait(BAR(T_EMPTY + acc), (ra & 1) ^ 1);           // accumulator pair drained by the epilogue
+            tc_fence_after();
+            const uint64_t db0 = umma_desc_k_sw128(smem_u32(sB + s * TC_B_STAGE_BYTES));
 #pragma unroll
-                for (int rt = 0; rt < TC_RT; ++rt) {
+            for (int rt = 0; rt < TC_RT; ++rt) {
 #pragma unroll
-                    for (int j = 0; j < TC_D / 8; ++j) {
-                        const uint32_t koff = (j & 3) * 32;               // 32 bytes per K=8 step inside the atom
-                        const uint64_t da = umma_desc_k_sw128(a0 + (rt * 2 + (j >> 2)) * TC_A_ATOM_BYTES + koff);
-                        const uint64_t db = umma_desc_k_sw128(b0 + (j >> 2) * TC_B_ATOM_BYTES + koff);
-                        tc_mma_tf32(tmem_base + (acc * TC_RT + rt) * TC_N, da, db, TC_IDESC, j > 0 ? 1u : 0u);
-                    }
+                for (int j = 0; j < TC_D / 8; ++j) {
+                    // K step j: 32 bytes further inside the swizzle atom, second atom for j >= 4; bases are 1024-aligned and
+                    // below 256 KB, so the offset can be added to the encoded start address without a carry
+                    const uint64_t da = da0 + (uint64_t)(((rt * 2 + (j >> 2)) * TC_A_ATOM_BYTES + (j & 3) * 32) >> 4);
+                    const uint64_t db = db0 + (uint64_t)(((j >> 2) * TC_B_ATOM_BYTES + (j & 3) * 32) >> 4);
+                    if (leader) tc_mma_tf32(tmem_base + (acc * TC_RT + rt) * TC_N, da, db, TC_IDESC, j > 0 ? 1u : 0u);
                 }
+            }
+            if (leader) {
                 tc_commit(BAR(B_EMPTY + s));                       // smem stage free when these MMAs retire
                 tc_commit(BAR(T_FULL + acc));                      // accumulator pair ready
             }
+            __syncwarp();
         }
     } else {
         // ================= epilogue: a thread owns one row; pass 2: one 64-item half of every tile, pass 1: the first half of every
@@ -331,7 +372,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 unsigned long long mb0, mb1;
                 mc.tile_bits(ib, mb0, mb1);                        // before the wait: overlaps the MMA of this tile
                 const unsigned long long mb = half ? mb1 : mb0;
-                const int i0 = ib + half * TC_HALF;
                 mbar_wait(BAR(T_FULL + acc), rph & 1);
                 tc_fence_after();
                 const uint32_t tb = t_row + (uint32_t)(acc * TC_RT * TC_N);
@@ -339,8 +379,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait(ra_); tmem_ld_fence(rb_);
                 tc_fence_before();
                 mbar_arrive(BAR(T_EMPTY + acc));                   // accumulator free: this warp's part is in registers
-                // train items of the row, and the items TMA zero-filled in the ragged last tile, take no part
-                const unsigned bad0 = (unsigned)mb | tc_oob_bits(i0, a.m_items), bad1 = (unsigned)(mb >> 32) | tc_oob_bits(i0 + 32, a.m_items);
+                // train items of the row take no part
+                const unsigned bad0 = (unsigned)mb, bad1 = (unsigned)(mb >> 32);     // (the holes of the layout are all in the other half)
                 if (bad0) tc_kill_columns(ra_, bad0);
                 if (bad1) tc_kill_columns(rb_, bad1);
                 my[lane * TC_STG + ((nbuf + lane) & (TC_STG - 1))] = fmaxf(tc_max32(ra_), tc_max32(rb_));
@@ -354,6 +394,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             hs.cnt = 0; hs.tau = live ? a.tau[row] : FLT_MAX;
             const size_t list = live ? ((size_t)row * a.n_splits + blockIdx.y) * 2 + half : 0;
             hs.val = a.cand_val + list * TC_CAP; hs.idx = a.cand_idx + list * TC_CAP;
+            int residue = tc_residue_of_tile(t_begin, a.order);
             for (int it = 0; it < n_tiles; ++it) {
                 const int acc = it & 1, rph = it >> 1;
                 const int ib = (t_begin + it) * TC_N;
@@ -368,8 +409,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait(ra_); tmem_ld_fence(rb_);
                 tc_fence_before();
                 mbar_arrive(BAR(T_EMPTY + acc));
-                tc_collect(ra_, i0, (unsigned)mb | tc_oob_bits(i0, a.m_items), hs);
-                tc_collect(rb_, i0 + 32, (unsigned)(mb >> 32) | tc_oob_bits(i0 + 32, a.m_items), hs);
+                const unsigned hole = (half == 1 && residue >= a.hole_from_residue) ? 0x80000000u : 0u;   // slot 127 = block 127
+                residue += a.order.inv; if (residue >= a.order.T) residue -= a.order.T;          // residue of the next tile
+                tc_collect(ra_, i0, (unsigned)mb, hs);
+                tc_collect(rb_, i0 + 32, (unsigned)(mb >> 32) | hole, hs);
             }
             if (live) a.cand_cnt[list] = (hs.cnt > TC_CAP) ? -1 : hs.cnt;
         }
@@ -392,6 +435,20 @@ __global__ void gather_rows_kernel(const float4* __restrict__ U, const long long
     out[i] = v;
 }
 
+// B operand: the item table in the interleaved layout (position p holds item tc_item_of_pos(p); holes are zero rows)
+__global__ void permute_items_kernel(const float4* __restrict__ V, int m_items, TcOrder o, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;            // one float4 per thread, 16 per row (d = 64)
+    if (i >= o.T * TC_N * 16) return;
+    const int p = i >> 4, c = i & 15;
+    const int item = tc_item_of_pos(p, o);
+    out[i] = (item < m_items) ? __ldg(V + (size_t)item * 16 + c) : f4_zero();
+}
+
+__global__ void tc_item_positions_kernel(const long long* __restrict__ items, long long n, TcOrder o, long long* __restrict__ pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = tc_pos_of_item((int)items[i], o);
+}
+
 __global__ void item_norm_max_kernel(const float4* __restrict__ V, int m_items, int* __restrict__ vmax_bits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float n2 = 0.f;
@@ -408,9 +465,9 @@ __global__ void item_norm_max_kernel(const float4* __restrict__ V, int m_items, 
 __device__ __forceinline__ unsigned tc_key(float f) { const unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float tc_unkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// select: warp per row — tau = KSEL-th largest sample maximum, to 16 significant key bits (sign, exponent, 7 mantissa
-// bits: tau is the lower edge of the bucket the KSEL-th largest falls into, so at least KSEL sample maxima reach it);
-// radix select, 2 x 8 bits from the top
+// select: warp per row — tau = KSEL-th largest sample maximum, to 24 significant key bits (tau is the lower edge of
+// the bucket the KSEL-th largest falls into, so at least KSEL sample maxima reach it; 16 bits were too coarse for
+// trained models, whose best scores lie within a fraction of a percent of each other); radix select, 3 x 8 bits
 constexpr int SEL_WARPS = 4;
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 tc_select_kernel(int Bt, int n_item_tiles, const float* __restrict__ tile_max, int tile_stride, int ksel, float* __restrict__ tau_out) {
@@ -421,7 +478,7 @@ tc_select_kernel(int Bt, int n_item_tiles, const float* __restrict__ tile_max, i
     const float* M0 = tile_max + (size_t)b * tile_stride;
     const unsigned dead = tc_key(-FLT_MAX);                               // nothing but train items in the sample
     unsigned prefix = 0; int remaining = ksel; bool enough = true;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < 3; ++pass) {
         const int shift = 24 - 8 * pass;
         for (int i = lane; i < 256; i += 32) s_hist[w][i] = 0;
         __syncwarp();
@@ -454,7 +511,7 @@ tc_select_kernel(int Bt, int n_item_tiles, const float* __restrict__ tile_max, i
         prefix |= (unsigned)digit << shift;
         __syncwarp();
     }
-    // smallest float whose key starts with the 16 selected bits (for negative values the low key bits run the other way)
+    // smallest float whose key starts with the 24 selected bits (for negative values the low key bits run the other way)
     if (lane == 0) tau_out[b] = enough ? tc_unkey(prefix) : -FLT_MAX;
 }
 
@@ -463,7 +520,7 @@ constexpr int RS_WARPS = 4;
 constexpr int RS_CAP = 192;
 constexpr int RS_BATCH = 16;         // item rows staged per step
 __global__ void __launch_bounds__(RS_WARPS * 32)
-rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const long long* __restrict__ users, int Bt, int n_lists, int k,
+rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const long long* __restrict__ users, int Bt, int n_lists, int k, TcOrder order,
                const float4* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt,
                const float* __restrict__ tau_row, const int* __restrict__ vmax_bits,
                long long* __restrict__ idx_out, float* __restrict__ val_out, int* __restrict__ flags, int* __restrict__ n_flagged) {
@@ -502,20 +559,20 @@ rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const l
             float4 v = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX); int meta = 0;
             if (have) { const size_t at = ((size_t)b * n_lists + li) * TC_CAP + (f - s_pre[w][li]); v = cand_val[at]; meta = cand_idx[at]; }
             const float vv[4] = {v.x, v.y, v.z, v.w};
-            const int first = meta & 0x0fffffff;
+            const int first = meta & 0x0fffffff;                       // position of the first of the 4 scores
 #pragma unroll
             for (int x = 0; x < 4; ++x) {                              // keep the scores that reach tau and are not train items
                 const bool take = have && vv[x] >= tau && !((meta >> (28 + x)) & 1);
                 const unsigned m = __ballot_sync(0xffffffffu, take);
                 const int pos = n + __popc(m & ((1u << lane) - 1u));
-                if (take && pos < RS_CAP) s_id[w][pos] = first + x;
+                if (take && pos < RS_CAP) s_id[w][pos] = tc_item_of_pos(first + x, order);
                 n += __popc(m);
             }
         }
         if (n > RS_CAP) lost = true;
     }
-    if (lost || n < k) {                                             // the exact kernel redoes this row
-        if (lane == 0) { flags[b] = 1; atomicAdd(n_flagged, 1); }
+    if (lost || n < k) {                                             // the exact kernel redoes this row (flag = why: 3 list overflow, 2 too few)
+        if (lane == 0) { flags[b] = lost ? 3 : 2; atomicAdd(n_flagged, 1); }
         return;
     }
     __syncwarp();
@@ -616,16 +673,18 @@ static int tc_pick_splits(int Bt, int m_items) {
     return best;
 }
 
-struct TcLayout { int bt_pad, item_tiles, tile_stride, n_splits, tiles_per_split; size_t off_mx, off_tau, off_cv, off_ci, off_cc, off_vmax, total; };
+struct TcLayout { int bt_pad, item_tiles, tile_stride, n_splits, tiles_per_split; size_t off_vp, off_mx, off_tau, off_cv, off_ci, off_cc, off_vmax, total; };
 static TcLayout tc_layout(int Bt, int m_items) {
     TcLayout L;
     L.bt_pad = (Bt + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
     L.item_tiles = (m_items + TC_N - 1) / TC_N;
-    L.tile_stride = L.item_tiles;
+
     L.n_splits = tc_pick_splits(Bt, m_items);
     L.tiles_per_split = (L.item_tiles + L.n_splits - 1) / L.n_splits;
     L.n_splits = (L.item_tiles + L.tiles_per_split - 1) / L.tiles_per_split;
+    L.tile_stride = L.item_tiles;
     size_t o = align_up((size_t)L.bt_pad * TC_D * 4, 1024);
+    L.off_vp = o;   o += align_up((size_t)L.item_tiles * TC_N * TC_D * 4, 1024);
     L.off_mx = o;   o += align_up((size_t)L.bt_pad * L.tile_stride * 4, 256);
     L.off_tau = o;  o += align_up((size_t)L.bt_pad * 4, 256);
     L.off_cv = o;   o += align_up((size_t)Bt * 2 * L.n_splits * TC_CAP * 16, 256);
@@ -640,9 +699,9 @@ static TcLayout tc_layout(int Bt, int m_items) {
 
 using namespace lgcn;
 
-// workspace: [A gathered][tile maxima][tau][cand_val][cand_idx][cand_cnt][vmax]
+// workspace: [A gathered][items, interleaved layout][tile maxima][tau][cand_val][cand_idx][cand_cnt][vmax]
 extern "C" size_t lgcn_score_topk_tc_workspace_bytes(int32_t Bt, int32_t m_items, int32_t k) {
-    if (Bt <= 0 || m_items <= 0 || k <= 0) return 0;
+    if (Bt <= 0 || m_items < TC_MIN_ITEMS || k <= 0) return 0;
     return tc_layout(Bt, m_items).total;
 }
 
@@ -655,15 +714,17 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
                                   void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(users_emb && items_emb && idx_out && val_out && flags_out && n_flagged_out, "score_topk_tc: null argument");
     LGCN_CHECK_ARG(lgcn_score_topk_tc_supported(d, k), "score_topk_tc: only d=%d and k<=24 take the tensor-core path", TC_D);
-    LGCN_CHECK_ARG(Bt > 0 && m_items >= k && m_items < (1 << 28), "score_topk_tc: Bt=%d m_items=%d k=%d", Bt, m_items, k);
+    LGCN_CHECK_ARG(Bt > 0 && m_items >= TC_MIN_ITEMS && m_items < (1 << 27), "score_topk_tc: Bt=%d m_items=%d (needs %d <= m_items < 2^27; use lgcn_score_topk)", Bt, m_items, TC_MIN_ITEMS);
     LGCN_CHECK_ARG((mask_indptr == nullptr) == (mask_indices == nullptr), "score_topk_tc: mask arrays must both be set or both null");
     const TcLayout L = tc_layout(Bt, m_items);
+    const TcOrder order = tc_order(m_items);
     LGCN_CHECK_ARG(workspace && ((uintptr_t)workspace % 1024) == 0 && workspace_bytes >= L.total,
                    "score_topk_tc: workspace too small or not 1024-byte aligned");
     LGCN_CHECK_ARG(((uintptr_t)items_emb % 16) == 0 && ((uintptr_t)users_emb % 16) == 0, "score_topk_tc: tables must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     char* w = static_cast<char*>(workspace);
     float* A = reinterpret_cast<float*>(w);
+    float* Vp = reinterpret_cast<float*>(w + L.off_vp);
     float* tile_max = reinterpret_cast<float*>(w + L.off_mx);
     float* tau = reinterpret_cast<float*>(w + L.off_tau);
     float4* cand_val = reinterpret_cast<float4*>(w + L.off_cv);
@@ -677,14 +738,19 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
     LGCN_CHECK_LAUNCH("gather_rows_kernel");
     cudaMemsetAsync(vmax, 0, 16, st);
     cudaMemsetAsync(n_flagged_out, 0, sizeof(int32_t), st);
+    permute_items_kernel<<<(L.item_tiles * TC_N * 16 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(items_emb), m_items, order,
+                                                                                 reinterpret_cast<float4*>(Vp));
+    LGCN_CHECK_LAUNCH("permute_items_kernel");
     item_norm_max_kernel<<<(m_items + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(items_emb), m_items, vmax);
     LGCN_CHECK_LAUNCH("item_norm_max_kernel");
 
     CUtensorMap map_a, map_b;
     if (int rc = make_map(&map_a, A, (uint64_t)L.bt_pad, TC_M)) return rc;
-    if (int rc = make_map(&map_b, items_emb, (uint64_t)m_items, TC_N)) return rc;
+    if (int rc = make_map(&map_b, Vp, (uint64_t)L.item_tiles * TC_N, TC_N)) return rc;
     TcArgs a;
     a.Bt = Bt; a.m_items = m_items; a.users = users_ll;
+    a.order = order;
+    a.hole_from_residue = m_items - 127 * L.item_tiles;    // block 127 = items 127*T + r: present for the residues below this
     a.mask_indptr = mask_indptr; a.mask_indices = mask_indices; a.mask_col_offset = mask_col_offset;
     a.n_splits = L.n_splits; a.tiles_per_split = L.tiles_per_split;
     a.tile_max = tile_max; a.tile_stride = L.tile_stride; a.tau = tau;
@@ -699,7 +765,7 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
     LGCN_CHECK_LAUNCH("tc_select_kernel");
     score_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
     LGCN_CHECK_LAUNCH("score_tc_kernel<2>");
-    rescore_kernel<<<(Bt + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, st>>>(users_emb, items_emb, users_ll, Bt, 2 * L.n_splits, k,
+    rescore_kernel<<<(Bt + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, st>>>(users_emb, items_emb, users_ll, Bt, 2 * L.n_splits, k, order,
         cand_val, cand_idx, cand_cnt, tau, vmax, reinterpret_cast<long long*>(idx_out), val_out, flags_out, n_flagged_out);
     LGCN_CHECK_LAUNCH("rescore_kernel");
     if (getenv("LGCN_TC_DEBUG_MMA_ONLY")) {
@@ -707,5 +773,26 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
         score_tc_kernel<3><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
         LGCN_CHECK_LAUNCH("score_tc_kernel<3>");
     }
+    return 0;
+}
+
+extern "C" int lgcn_score_topk_tc_item_positions(const int64_t* items, int64_t n, int32_t m_items, int64_t* pos_out, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(items && pos_out && n >= 0, "score_topk_tc_item_positions: null argument");
+    LGCN_CHECK_ARG(m_items >= TC_MIN_ITEMS && m_items < (1 << 27), "score_topk_tc_item_positions: m_items=%d", m_items);
+    if (n == 0) return 0;
+    tc_item_positions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(items), n, tc_order(m_items),
+                                                                                          reinterpret_cast<long long*>(pos_out));
+    LGCN_CHECK_LAUNCH("tc_item_positions_kernel");
+    return 0;
+}
+
+extern "C" int32_t lgcn_score_topk_tc_position_space(int32_t m_items) { return m_items >= TC_MIN_ITEMS ? ((m_items + TC_N - 1) / TC_N) * TC_N : 0; }
+
+// diagnostics: where the per-row threshold and the per-list event counts live inside the workspace of the last call shape
+extern "C" int lgcn_score_topk_tc_debug_layout(int32_t Bt, int32_t m_items, int64_t* out8_host) {
+    LGCN_CHECK_ARG(out8_host && Bt > 0 && m_items >= TC_MIN_ITEMS, "score_topk_tc_debug_layout: bad arguments");
+    const TcLayout L = tc_layout(Bt, m_items);
+    out8_host[0] = (int64_t)L.off_tau; out8_host[1] = (int64_t)L.off_cc; out8_host[2] = 2 * L.n_splits; out8_host[3] = L.item_tiles;
+    out8_host[4] = L.tiles_per_split; out8_host[5] = (int64_t)L.off_mx; out8_host[6] = L.tile_stride; out8_host[7] = TC_CAP;
     return 0;
 }

@@ -281,22 +281,54 @@ def score_topk(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=No
     return idx, val
 
 
-TC_MIN_ITEMS = 16384      # below this the row threshold cannot be taken from tile maxima (128 items per tile, 48 tiles needed)
+last_tc_flags = None
+last_tc_workspace = None
+TC_MIN_ITEMS = 16384      # the tensor-core path needs >= 128 item tiles (interleaved layout, row threshold from tile maxima)
+_tc_mask_cache = {}
+
+
+def tc_mask_positions(mask_indptr, mask_indices, mask_col_offset, n_users, m_items):
+    """The train-item mask in the position space of the tensor-core kernel: a CSR over the user rows whose column
+    entries are n_users + position, ascending per row.  Built once per (mask, m_items) with the library's own
+    kernels (lgcn_score_topk_tc_item_positions + lgcn_csr_build over (user, position) pairs) and cached."""
+    key = (mask_indptr.data_ptr(), mask_indices.data_ptr(), int(mask_col_offset), int(n_users), int(m_items))
+    hit = _tc_mask_cache.get(key)
+    if hit is not None and hit[0]() is mask_indices:
+        return hit[1], hit[2]
+    lib = _lib.load()
+    deg = (mask_indptr[1:n_users + 1] - mask_indptr[:n_users]).to(torch.int64)
+    nnz = int(mask_indptr[n_users].item()) - int(mask_indptr[0].item())
+    rows = torch.repeat_interleave(torch.arange(n_users, device=mask_indices.device, dtype=torch.int64), deg, output_size=nnz)
+    start = int(mask_indptr[0].item())
+    items = (mask_indices[start:start + nnz].to(torch.int64) - int(mask_col_offset)).contiguous()
+    pos = torch.empty_like(items)
+    _lib.check(lib.lgcn_score_topk_tc_item_positions(_p(items), nnz, int(m_items), _p(pos), _stream()), "score_topk_tc_item_positions")
+    g = csr_build(rows, pos, int(n_users), int(lib.lgcn_score_topk_tc_position_space(int(m_items))))
+    import weakref
+    if len(_tc_mask_cache) > 8:
+        _tc_mask_cache.clear()
+    _tc_mask_cache[key] = (weakref.ref(mask_indices), g.indptr, g.indices)
+    return g.indptr, g.indices
 
 
 def score_topk_tc(users_emb, items_emb, users, k, mask_indptr=None, mask_indices=None, mask_col_offset=0, min_items=TC_MIN_ITEMS):
     """K3 on tensor cores: same result as score_topk, bit for bit.  Returns (idx, val, n_rows_redone);
-    item tables smaller than `min_items` go to the exact kernel directly (every row counts as redone)."""
+    item tables smaller than `min_items` go to the exact kernel directly (every row counts as redone).
+    The mask is the same id-space CSR score_topk takes; its position-space form is derived and cached."""
     lib = _lib.load()
     _need(users_emb, torch.float32, "users_emb", 2), _need(items_emb, torch.float32, "items_emb", 2)
     Bt = users_emb.shape[0] if users is None else users.numel()
     m_items, d = items_emb.shape
-    if not lib.lgcn_score_topk_tc_supported(d, k) or Bt == 0 or m_items < min_items:
+    if not lib.lgcn_score_topk_tc_supported(d, k) or Bt == 0 or m_items < max(min_items, TC_MIN_ITEMS):
         idx, val = score_topk(users_emb, items_emb, users, k, mask_indptr, mask_indices, mask_col_offset)
         return idx, val, Bt
     dev = items_emb.device
     if users is not None:
         _need(users, torch.int64, "users", 1)
+    pm_indptr = pm_indices = None
+    n_users = users_emb.shape[0]
+    if mask_indptr is not None:
+        pm_indptr, pm_indices = tc_mask_positions(mask_indptr, mask_indices, mask_col_offset, n_users, m_items)
     idx = torch.empty((Bt, k), dtype=torch.int64, device=dev)
     val = torch.empty((Bt, k), dtype=torch.float32, device=dev)
     flags = torch.empty(Bt, dtype=torch.int32, device=dev)
@@ -304,11 +336,14 @@ def score_topk_tc(users_emb, items_emb, users, k, mask_indptr=None, mask_indices
     ws_bytes = lib.lgcn_score_topk_tc_workspace_bytes(Bt, m_items, k)
     ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=dev)
     ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
-    _lib.check(lib.lgcn_score_topk_tc(_p(users_emb), _p(items_emb), _p(users), Bt, m_items, d, _p(mask_indptr), _p(mask_indices),
-                                      int(mask_col_offset), int(k), _p(idx), _p(val), _p(flags), _p(n_flagged),
+    _lib.check(lib.lgcn_score_topk_tc(_p(users_emb), _p(items_emb), _p(users), Bt, m_items, d, _p(pm_indptr), _p(pm_indices),
+                                      int(n_users) if pm_indptr is not None else 0, int(k), _p(idx), _p(val), _p(flags), _p(n_flagged),
                                       c_void_p(ws_ptr), ws_bytes, _stream()), "score_topk_tc")
     n = int(n_flagged.item())
-    if n:   # rows whose certificate failed: exact path, scattered back
+    global last_tc_flags, last_tc_workspace
+    last_tc_workspace = (ws, ws_ptr - ws.data_ptr(), Bt, m_items)      # diagnostics (lgcn_score_topk_tc_debug_layout)
+    last_tc_flags = flags            # per row: 0 certified, 1 certificate failed, 2 fewer than k candidates, 3 candidate list overflowed
+    if n:   # rows that could not be certified: exact path, scattered back
         rows = torch.nonzero(flags, as_tuple=False).flatten()
         sub = rows if users is None else users[rows].contiguous()
         idx2, val2 = score_topk(users_emb, items_emb, sub, k, mask_indptr, mask_indices, mask_col_offset)

@@ -222,12 +222,22 @@ int lgcn_score_topk(const float* users_emb, const float* items_emb, const int64_
 /* Tensor-core path of the same operation (tcgen05 TF32 MMA + TMA + TMEM, d = 64, k <= 24): an approximate
  * two-pass filter (sampled tile maxima -> row threshold -> the ~50 items that reach it) picks candidates, the
  * candidates are rescored with the exact fp32 FMA chain and the top-k is certified against everything that was
- * filtered out.  Meant for item tables of >= 16 k items (fewer tiles than the threshold rank:
- * every row is flagged).  m_items < 2^28.  Rows whose
- * certificate fails get flags_out[b] = 1 (count in n_flagged_out, device int32[1]) and MUST be recomputed with
- * lgcn_score_topk; all other rows are bit-identical to it.  workspace must be 1024-byte aligned. */
+ * filtered out.  16384 <= m_items < 2^27.  Rows that cannot be certified get flags_out[b] != 0
+ * (1 certificate failed, 2 fewer than k candidates, 3 candidate list overflowed; count in n_flagged_out, device
+ * int32[1]) and MUST be recomputed with lgcn_score_topk; all other rows are bit-identical to it.
+ * workspace must be 1024-byte aligned.
+ * THE MASK IS GIVEN IN POSITION SPACE: the kernel scores the items in an interleaved order (so that a block of 64
+ * consecutive positions is a spread-out sample of the ids).  mask_indices[j] - mask_col_offset must be the POSITION
+ * of the train item, ascending within each row; lgcn_score_topk_tc_item_positions maps item ids to positions
+ * (position space = [0, lgcn_score_topk_tc_position_space(m_items))), and lgcn_csr_build over (user, position)
+ * pairs yields exactly such a CSR (user rows, col offset n_users).  idx_out holds item ids as usual. */
 int lgcn_score_topk_tc_supported(int32_t d, int32_t k);
 size_t lgcn_score_topk_tc_workspace_bytes(int32_t Bt, int32_t m_items, int32_t k);
+int32_t lgcn_score_topk_tc_position_space(int32_t m_items);
+/* diagnostics: {offset of tau, offset of the event counts, lists per row, item tiles, tiles per split, offset of the
+ * sample maxima, their row stride, events per list} of the workspace layout for this (Bt, m_items) */
+int lgcn_score_topk_tc_debug_layout(int32_t Bt, int32_t m_items, int64_t* out8_host);
+int lgcn_score_topk_tc_item_positions(const int64_t* items, int64_t n, int32_t m_items, int64_t* pos_out, lgcn_stream_t stream);
 int lgcn_score_topk_tc(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
                        int32_t m_items, int32_t d, const int32_t* mask_indptr, const int32_t* mask_indices,
                        int32_t mask_col_offset, int32_t k, int64_t* idx_out, float* val_out,

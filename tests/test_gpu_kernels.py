@@ -412,9 +412,33 @@ def test_score_topk_tensor_core_is_bit_identical_to_exact(lg, scale):
     assert torch.equal(ti_, ei) and torch.equal(tv, ev)
 
 
+def test_score_topk_tensor_core_popular_items_with_adjacent_ids(lg):
+    """What a trained model looks like: every user's best items are the popular ones, popular items have small ADJACENT
+    ids and large norms, and a user's train items are among its best.  In id order that put most candidates into a few
+    64-item blocks of one split (70 % of the rows overflowed on real gowalla); the interleaved item layout must keep the
+    tensor-core path certified — and bit-identical — here."""
+    rng = np.random.default_rng(21)
+    nu, ni, d, k = 900, 24001, 64, 20
+    c = rng.normal(0, 1, d).astype(np.float32); c /= np.linalg.norm(c)
+    pop = (4.0 / (1.0 + np.arange(ni) / 150.0)).astype(np.float32)                 # popularity decays with the id
+    V = pop[:, None] * (c[None, :] + 0.35 * rng.normal(0, 1, (ni, d)).astype(np.float32) / np.sqrt(d)) \
+        + 0.05 * rng.normal(0, 1, (ni, d)).astype(np.float32)
+    U = (1.0 + rng.random(nu).astype(np.float32))[:, None] * (c[None, :] + 0.5 * rng.normal(0, 1, (nu, d)).astype(np.float32) / np.sqrt(d))
+    deg = rng.integers(5, 120, nu)
+    tu = np.repeat(np.arange(nu), deg)
+    ti = np.concatenate([rng.choice(2000, n, replace=False, p=(pop[:2000] / pop[:2000].sum())) for n in deg])    # train items: popular ones
+    g = build(lg, tu.astype(np.int64), ti.astype(np.int64), nu, ni)
+    o = dev(np.concatenate([U, V]).astype(np.float32))
+    ei, ev = lg.ops.score_topk(o[:nu], o[nu:], None, k, g.indptr, g.indices, nu)
+    ti_, tv, redone = lg.ops.score_topk_tc(o[:nu], o[nu:], None, k, g.indptr, g.indices, nu)
+    assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+    assert redone <= nu // 50, redone
+    assert int(ei[:, 0].max()) < 2000                          # the best items really are the small ids
+
+
 def test_score_topk_tensor_core_too_few_tiles_still_exact(lg):
-    """Fewer item tiles than the threshold rank: no row threshold exists, every candidate list overflows,
-    all rows are flagged and redone — the result is still the exact kernel's."""
+    """Item tables below 16 k items (fewer than 128 tiles) are not taken by the tensor-core path at all: the call is
+    served by the exact kernel, whatever min_items says."""
     rng = np.random.default_rng(11)
     nu, ni, k = 300, 3001, 20
     tu, ti = random_edges(rng, nu, ni, 9000)
