@@ -352,11 +352,20 @@ def run_ours(args):
                             "spmm_share_of_step": (6 * mean_ms) / (ms_dev / K),
                             "l2_gather_gbs": gather_bytes / (mean_ms * 1e-3) / 1e9}
         # ---- evaluation (K3) timing, reported beside the headline -----------------------------------------
+        # (the first Procedure.Test also builds the test CSR and the position-space mask of the tensor-core kernel — once per
+        # graph; the steady-state call is the one a training run repeats every few epochs)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         res = lg.Procedure.Test(ds, model, 0)
-        torch.cuda.synchronize()
-        line["eval"] = {"test_ms": 1e3 * (time.perf_counter() - t0), "users": len(ds.testDict), "recall@20": float(res['recall'][0]),
-                        "score_gflop": 2.0 * len(ds.testDict) * ds.m_items * 64 / 1e9}
+        torch.cuda.synchronize(); first_ms = 1e3 * (time.perf_counter() - t0)
+        warm = []
+        for _ in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            res = lg.Procedure.Test(ds, model, 0)
+            torch.cuda.synchronize(); warm.append(1e3 * (time.perf_counter() - t0))
+        n_test_users = int(ds.test_csr()[0].numel())
+        line["eval"] = {"test_ms": statistics.median(warm), "test_first_call_ms": first_ms, "users": n_test_users,
+                        "recall@20": float(res['recall'][0]), "score_gflop": 2.0 * n_test_users * ds.m_items * 64 / 1e9,
+                        "rows_redone_by_exact_kernel": int(getattr(model, 'last_rank_redone', 0))}
         # ---- CPU baseline on this box's host cores ---------------------------------------------------------
         if not args.no_cpu_baseline:
             r = cpu_port_bench(graph, 12, 2, budget_s=25.0)
