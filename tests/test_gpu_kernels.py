@@ -436,6 +436,28 @@ def test_score_topk_tensor_core_popular_items_with_adjacent_ids(lg):
     assert int(ei[:, 0].max()) < 2000                          # the best items really are the small ids
 
 
+@pytest.mark.parametrize("ni,k", [(16384, 20), (16385, 1), (16511, 24), (16512, 7), (33000, 20), (40961, 20)])
+def test_score_topk_tensor_core_item_count_edges(lg, ni, k):
+    """The interleaved layout has 128*T - m_items holes in its last block and a residue order that depends on T: smallest
+    table (T = 128, no holes), one item more (127 holes), last tile nearly full / exactly full, T even and odd; k = 1 and
+    k = 24; user batches that are not a multiple of anything.  Always bit-identical to the exact kernel, holes never
+    appear as items, nearly all rows certified."""
+    rng = np.random.default_rng(ni + k)
+    nu = 333
+    tu, ti = random_edges(rng, nu, ni, 12000)
+    ti[:400] = ni - 1 - rng.integers(0, 300, 400)              # train items among the last ids (the block next to the holes)
+    g = build(lg, tu, ti, nu, ni)
+    out = rng.normal(0, 0.2, (nu + ni, 64)).astype(np.float32)
+    out[nu + ni - 200:] *= 3.0                                  # ... and the best-scoring items are the last ids
+    o = dev(out)
+    for users in (None, dev(rng.permutation(nu)[:77].astype(np.int64))):
+        ei, ev = lg.ops.score_topk(o[:nu], o[nu:], users, k, g.indptr, g.indices, nu)
+        ti_, tv, redone = lg.ops.score_topk_tc(o[:nu], o[nu:], users, k, g.indptr, g.indices, nu)
+        assert torch.equal(ti_, ei) and torch.equal(tv, ev)
+        assert int(ti_.max()) < ni and int(ti_.min()) >= 0
+        assert redone <= max(2, (nu if users is None else 77) // 25), redone
+
+
 def test_score_topk_tensor_core_too_few_tiles_still_exact(lg):
     """Item tables below 16 k items (fewer than 128 tiles) are not taken by the tensor-core path at all: the call is
     served by the exact kernel, whatever min_items says."""
