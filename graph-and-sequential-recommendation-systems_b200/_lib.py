@@ -23,7 +23,7 @@ class SpmmPlan(Structure):
 
 
 class SpmmPeers(Structure):
-    _fields_ = [("n_peers", c_int32), ("pad", c_int32), ("y", c_void_p * 7), ("p", c_void_p * 7)]
+    _fields_ = [("n_peers", c_int32), ("multicast", c_int32), ("y", c_void_p * 7), ("p", c_void_p * 7)]
 
 
 class AdamScalars(Structure):

@@ -65,6 +65,11 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// NVSwitch multicast store: `p` is a multimem address, the 16 bytes land in every replica of the group (sm_90+)
+__device__ __forceinline__ void st_multicast_f4(float4* p, const float4& v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // vectorised reduction: one 16-byte atomic add, no return value (sm_90+)
 __device__ __forceinline__ void red_add_f4(float4* p, const float4& v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"

@@ -44,6 +44,7 @@ struct SpmmArgs {
     // fused exchange (row partition over GPUs): every finished row is also stored into the peers' copies of Y
     // (and of P in the Adam epilogue) over NVLink, so no separate all-gather pass re-reads and re-sends it
     int n_peers; float4* peerY[LGCN_MAX_PEERS]; float4* peerP[LGCN_MAX_PEERS];
+    int multicast;      // peerY[0] / peerP[0] are NVSwitch multimem addresses: ONE store reaches every replica
 };
 
 __device__ __forceinline__ bool mask_bit(const unsigned* m, int i) { return (__ldg(m + (i >> 5)) >> (i & 31)) & 1u; }
@@ -157,14 +158,17 @@ __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, c
             adam_update1(pw.z, m.z, vv.z, g.z, b2, w1, w2, step_size, bc2s, eps);
             adam_update1(pw.w, m.w, vv.w, g.w, b2, w1, w2, step_size, bc2s, eps);
             a.P[off] = pw; a.M[off] = m; a.V[off] = vv;
-            for (int q = 0; q < a.n_peers; ++q) if (a.peerP[q]) st_stream_f4(a.peerP[q] + off, pw);
+            if (a.multicast) { if (a.peerP[0]) st_multicast_f4(a.peerP[0] + off, pw); }
+            else for (int q = 0; q < a.n_peers; ++q) if (a.peerP[q]) st_stream_f4(a.peerP[q] + off, pw);
             if (a.Y != nullptr) {
                 st_stream_f4(a.Y + off, g);
-                for (int q = 0; q < a.n_peers; ++q) if (a.peerY[q]) st_stream_f4(a.peerY[q] + off, g);
+                if (a.multicast) { if (a.peerY[0]) st_multicast_f4(a.peerY[0] + off, g); }
+                else for (int q = 0; q < a.n_peers; ++q) if (a.peerY[q]) st_stream_f4(a.peerY[q] + off, g);
             }
         } else {
             st_stream_f4(a.Y + off, g);
-            for (int q = 0; q < a.n_peers; ++q) st_stream_f4(a.peerY[q] + off, g);
+            if (a.multicast) st_multicast_f4(a.peerY[0] + off, g);
+            else for (int q = 0; q < a.n_peers; ++q) st_stream_f4(a.peerY[q] + off, g);
         }
     }
 }
@@ -211,8 +215,26 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
     __threadfence();
 #pragma unroll
     for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+    // fixed summation order (part 0, 1, 2, ...), but the loads of several parts are in flight together: with one part per
+    // iteration every partial cost an L2 round trip, which made the tail of a hub row proportional to its part count
+    constexpr int RB = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);    // 8 float4 of partials per lane in flight
+    int q = 0;
 #pragma unroll 1
-    for (int q = 0; q < n_parts; ++q) {
+    for (; q + RB <= n_parts; q += RB) {
+        float4 t[RB][VPL];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const float4* src = a.partials + (size_t)(slot_base + q + u) * VEC + lane;
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) t[u][p] = ld_cg_f4(src + p * LANES);
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) f4_add(acc[p], t[u][p]);
+    }
+#pragma unroll 1
+    for (; q < n_parts; ++q) {
         const float4* src = a.partials + (size_t)(slot_base + q) * VEC + lane;
 #pragma unroll
         for (int p = 0; p < VPL; ++p) f4_add(acc[p], ld_cg_f4(src + p * LANES));
@@ -223,9 +245,11 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
 
 // ---- plan kernels -------------------------------------------------------------------------
 // ws ints: [0]=long cursor, [1]=segment cursor, then bins[seg_len+1], offsets[seg_len+1], cursors[seg_len+1]
-// A hub row is cut into at most kMaxParts segments: the last-arriving segment adds the partials serially, so the
-// number of parts bounds that tail (a 1.5 M-nnz item row: 256 parts of 5.9 k instead of 12 k parts of 128).
-constexpr int kMaxParts = 256;
+// A hub row is cut into at most kMaxParts segments.  One 8-lane group walks a segment (~0.25 us per non-zero with four
+// gathers in flight) and the last-arriving segment adds the partials in part order (~0.08 us each, 8 loads in flight):
+// for a 1.5 M-nnz item row 2048 parts of 732 cost ~0.18 + 0.15 ms; 256 parts of 5.9 k cost 1.5 ms (the tail that made a
+// row-partitioned layer 3x slower than its local SpMM), 12 k parts of 128 cost ~1 ms of serial adds.
+constexpr int kMaxParts = 2048;
 
 __device__ __forceinline__ void split_row(int deg, int seg_len, int& n_parts, int& len) {
     n_parts = (deg + seg_len - 1) / seg_len;
@@ -367,11 +391,12 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
     }
     a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr;
     a.row_mask = row_mask; a.col_mask = col_mask;
-    a.n_peers = 0;
+    a.n_peers = 0; a.multicast = 0;
     for (int q = 0; q < LGCN_MAX_PEERS; ++q) { a.peerY[q] = nullptr; a.peerP[q] = nullptr; }
     if (peers) {
         LGCN_CHECK_ARG(peers->n_peers >= 0 && peers->n_peers <= LGCN_MAX_PEERS, "spmm: n_peers=%d out of range", peers->n_peers);
-        a.n_peers = peers->n_peers;
+        LGCN_CHECK_ARG(!peers->multicast || peers->n_peers == 1, "spmm: a multicast destination is ONE address (n_peers=%d)", peers->n_peers);
+        a.n_peers = peers->n_peers; a.multicast = peers->multicast ? 1 : 0;
         for (int q = 0; q < a.n_peers; ++q) {
             LGCN_CHECK_ARG(((uintptr_t)peers->y[q] % 16) == 0 && ((uintptr_t)peers->p[q] % 16) == 0, "spmm: peer pointers must be 16-byte aligned");
             a.peerY[q] = reinterpret_cast<float4*>(peers->y[q]); a.peerP[q] = reinterpret_cast<float4*>(peers->p[q]);

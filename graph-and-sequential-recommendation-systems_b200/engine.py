@@ -49,6 +49,32 @@ def balanced_row_bounds(indptr_cpu, parts, row_cost=0):
     return bounds
 
 
+def rebalance_by_time(indptr_cpu, bounds, times, row_cost=0):
+    """Move the boundaries so that every block would take the same time, given the time each current block took.
+    Within a block the time is taken to be proportional to the block's cost (nnz + row_cost * rows): the cumulative
+    time over the rows is then piecewise linear in the cumulative cost, and the new boundaries are where it reaches
+    k/parts of the total.  (User rows gather item embeddings and item rows gather user embeddings — tables of very
+    different size and cache residency — so equal cost is not equal time.)"""
+    parts = len(bounds) - 1
+    n_rows = indptr_cpu.numel() - 1
+    cost = indptr_cpu.to(torch.int64) + int(row_cost) * torch.arange(n_rows + 1, dtype=torch.int64)
+    t = [max(float(x), 1e-9) for x in times]
+    total_t = sum(t)
+    c_at = [int(cost[b]) for b in bounds]
+    new = [0]
+    acc_t, blk = 0.0, 0
+    for k in range(1, parts):
+        target = total_t * k / parts
+        while blk < parts - 1 and acc_t + t[blk] < target:
+            acc_t += t[blk]; blk += 1
+        frac = (target - acc_t) / t[blk]
+        c_target = c_at[blk] + frac * (c_at[blk + 1] - c_at[blk])
+        r = int(torch.searchsorted(cost, torch.tensor(int(c_target), dtype=torch.int64), right=False))
+        new.append(max(new[-1], min(r, n_rows)))
+    new.append(n_rows)
+    return new
+
+
 def allgather_rows(buf, bounds, group=None):
     """Uneven in-place all-gather: rank p broadcasts rows [bounds[p], bounds[p+1]) of `buf`.
     Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
@@ -82,6 +108,32 @@ def map_peer_buffers(t, group=None):
     return out
 
 
+def symmetric_tables(n, shape, device, group, mc_out):
+    """n zeroed fp32 tables in torch symmetric memory, rendezvoused over `group`; mc_out[data_ptr] = multicast address.
+    Returns [None]*n when the box has no NVSwitch multicast (or torch no symmetric memory): the caller then uses
+    ordinary tensors and unicast peer stores."""
+    try:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        g = dist.group.WORLD if group is None else group
+        tabs, ptrs = [], []
+        for _ in range(n):
+            t = symm_mem.empty(shape, dtype=torch.float32, device=device)
+            h = symm_mem.rendezvous(t, g)
+            if not h.multicast_ptr:
+                return [None] * n
+            t.zero_()
+            tabs.append(t); ptrs.append(int(h.multicast_ptr))
+        for t, mp in zip(tabs, ptrs):
+            mc_out[t.data_ptr()] = mp
+        return tabs
+    except Exception as e:          # noqa: BLE001 — any failure here means "no multicast", not an error
+        import warnings
+        warnings.warn(f"rowpart: symmetric memory unavailable ({type(e).__name__}: {e}); using unicast peer stores")
+        mc_out.clear()
+        return [None] * n
+
+
 def shard_batch(n, rank, world):
     """Contiguous shard [lo,hi) of a batch of n triples for data-parallel rank `rank`."""
     per = (n + world - 1) // world
@@ -91,7 +143,7 @@ def shard_batch(n, rank, world):
 
 class Engine:
     def __init__(self, csr, n_users, m_items, d, n_layers, device, *, lr=1e-3, decay=1e-4, B_cap=2048,
-                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True, row_cost=None):
+                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True, row_cost=None, multicast=True, rebalance=2):
         if n_layers > 8:
             raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
         self.csr = csr
@@ -111,9 +163,16 @@ class Engine:
             self.B_cap = self.B_cap * self.world          # the static batch buffers hold the GLOBAL batch
         N, L = self.N, self.L
         f32 = dict(dtype=torch.float32, device=device)
-        self.E0 = torch.zeros((N, d), **f32)
-        self.X = [torch.zeros((N, d), **f32) for _ in range(max(L - 1, 0))]
-        self.out = torch.zeros((N, d), **f32)
+        # exchanged tables of the row partition: NVSwitch multicast (symmetric memory) when the box offers it — one
+        # multimem store per 16 bytes reaches every replica instead of world-1 unicast stores
+        self.p2p = bool(p2p) and dist_mode == 'rowpart' and self.world > 1 and self.world - 1 <= 7
+        self._mc = {}
+        exchanged = [None] * (2 + max(L - 1, 0))
+        if self.p2p and multicast:
+            exchanged = symmetric_tables(len(exchanged), (N, d), device, group, self._mc)
+        self.E0 = exchanged[0] if exchanged[0] is not None else torch.zeros((N, d), **f32)
+        self.X = [exchanged[2 + i] if exchanged[2 + i] is not None else torch.zeros((N, d), **f32) for i in range(max(L - 1, 0))]
+        self.out = exchanged[1] if exchanged[1] is not None else torch.zeros((N, d), **f32)
         self.G = torch.zeros((N, d), **f32)
         self.M = torch.zeros((N, d), **f32)
         self.V = torch.zeros((N, d), **f32)
@@ -134,26 +193,50 @@ class Engine:
         if dist_mode == 'rowpart':
             if row_cost is None:
                 row_cost = d if (p2p and self.world > 1) else 0
-            self.bounds = balanced_row_bounds(csr.indptr.cpu(), self.world, row_cost)
+            indptr_cpu = csr.indptr.cpu()
+            self.bounds = balanced_row_bounds(indptr_cpu, self.world, row_cost)
             self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
             self.local = csr.rows(self.r0, self.r1)
+            for _ in range(int(rebalance)):                 # equal cost is not equal time: measure, move the boundaries
+                self.bounds = self._rebalance(indptr_cpu, row_cost)
+                self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+                self.local = csr.rows(self.r0, self.r1)
         # fused exchange: map the peers' copies of every exchanged buffer
-        self.p2p = bool(p2p) and dist_mode == 'rowpart' and self.world > 1 and self.world - 1 <= 7
         self._peer = {}
         self._e0_synced = False
         if self.p2p:
             import torch.distributed as dist
             from . import _lib
-            for p_dev in range(torch.cuda.device_count()):
-                _lib.load().lgcn_enable_peer_access(p_dev)
-            for buf in [self.E0, self.out] + self.X:
-                self._peer[buf.data_ptr()] = map_peer_buffers(buf, group)
+            if not self._mc:
+                for p_dev in range(torch.cuda.device_count()):
+                    _lib.load().lgcn_enable_peer_access(p_dev)
+                for buf in [self.E0, self.out] + self.X:
+                    self._peer[buf.data_ptr()] = map_peer_buffers(buf, group)
             self._flag = torch.zeros(1, dtype=torch.float32, device=device)
             dist.barrier(group)
         # batch staging: [ctl(4 x int32) | users | pos | neg] in one block so that a host batch is one H2D
         self._alloc_batch(self.B_cap)
         self._epoch = None          # (S tensor [3,cap], ctl) for epoch-resident mode
         self._graphs = {}
+
+    def _rebalance(self, indptr_cpu, row_cost):
+        """One round of time-based re-partitioning: every rank times its local product (same launch the layers use,
+        without the exchange), the times are all-gathered, the boundaries recomputed identically on every rank."""
+        import torch.distributed as dist
+        Y = self.out[self.r0:self.r1]
+        ops.spmm(self.local, self.E0, Y)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            ops.spmm(self.local, self.E0, Y)
+        b.record(); b.synchronize()
+        mine = torch.tensor([a.elapsed_time(b) / 3], dtype=torch.float64, device=self.device)
+        allt = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allt, mine, group=self.group)
+        self.out.zero_()
+        return rebalance_by_time(indptr_cpu, self.bounds, [float(x.item()) for x in allt], row_cost)
 
     # ------------------------------------------------------------------ batch staging
     def _alloc_batch(self, B_cap):
@@ -220,7 +303,11 @@ class Engine:
         r0, r1 = self.r0, self.r1
         if self.dist_mode == 'rowpart':
             peers = self._peer.get(Y.data_ptr()) if self.p2p else None
-            if peers is not None:
+            mc = self._mc.get(Y.data_ptr(), 0) if self.p2p else 0
+            if mc:
+                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None, mc_y=mc + r0 * self.d * 4)
+                self._rank_barrier()
+            elif peers is not None:
                 ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None,
                          peer_y=[peers[p][r0:r1] for p in range(self.world) if p != self.rank])
                 self._rank_barrier()
@@ -332,12 +419,14 @@ class Engine:
             g = self.local if self.dist_mode == 'rowpart' else self.csr
 
             peers_e0 = self._peer.get(self.E0.data_ptr()) if self.p2p else None
+            mc_e0 = self._mc.get(self.E0.data_ptr(), 0) if self.p2p else 0
 
             def last(X, alpha, beta, zs, col_mask):
                 ops.spmm_adam(g, X, self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.scalars, alpha, beta,
                               [z[r0:r1] for z in zs], col_mask=col_mask,
-                              peer_p=None if peers_e0 is None else [peers_e0[p][r0:r1] for p in range(self.world) if p != self.rank])
-                if peers_e0 is not None:        # the updated parameter rows are already in every replica
+                              peer_p=None if (peers_e0 is None or mc_e0) else [peers_e0[p][r0:r1] for p in range(self.world) if p != self.rank],
+                              mc_p=(mc_e0 + r0 * self.d * 4) if mc_e0 else 0)
+                if peers_e0 is not None or mc_e0:        # the updated parameter rows are already in every replica
                     self._rank_barrier()
                     self._e0_synced = True
             self._backward_chain(self.G, last)

@@ -160,20 +160,28 @@ def _z_array(zs):
     return arr, len(zs)
 
 
-def _peers_struct(peer_y=None, peer_p=None):
+def _peers_struct(peer_y=None, peer_p=None, mc_y=0, mc_p=0):
+    """peer_y / peer_p: the peers' copies of the destination row block (tensors, unicast stores);
+    mc_y / mc_p: instead, the NVSwitch multicast ADDRESS of the row block (int): one store reaches every replica."""
+    if mc_y or mc_p:
+        st = _lib.SpmmPeers()
+        st.n_peers, st.multicast = 1, 1
+        st.y[0] = int(mc_y) if mc_y else None
+        st.p[0] = int(mc_p) if mc_p else None
+        return byref(st)
     ys, ps = list(peer_y or []), list(peer_p or [])
     n = max(len(ys), len(ps))
     if n == 0:
         return None
     st = _lib.SpmmPeers()
-    st.n_peers = n
+    st.n_peers, st.multicast = n, 0
     for i in range(n):
         st.y[i] = ys[i].data_ptr() if i < len(ys) and ys[i] is not None else None
         st.p[i] = ps[i].data_ptr() if i < len(ps) and ps[i] is not None else None
     return byref(st)
 
 
-def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None, peer_y=None):
+def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None, peer_y=None, mc_y=0):
     """Y = alpha * (A @ X) + beta * sum(zs)  — K1.  X is indexed by column id, Y/zs by local row."""
     lib = _lib.load()
     d = X.shape[1]
@@ -186,11 +194,11 @@ def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None, pe
     for z in (zs or []):
         _need(z, torch.float32, "z", 2)
     _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
-                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(peer_y), _stream()), "spmm")
+                                 float(alpha), float(beta), arr, nz, g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(peer_y, None, mc_y), _stream()), "spmm")
     return Y
 
 
-def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None, peer_p=None):
+def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None, peer_p=None, mc_p=0):
     """K1 with the Adam epilogue: grad = alpha*(A@X) + beta*sum(zs); P,M,V updated in place."""
     lib = _lib.load()
     d = X.shape[1]
@@ -199,7 +207,7 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_
     arr, nz = _z_array(zs)
     _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                       float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
-                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p), _stream()), "spmm_adam")
+                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p, 0, mc_p), _stream()), "spmm_adam")
 
 
 def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):

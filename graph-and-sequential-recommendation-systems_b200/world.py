@@ -55,6 +55,8 @@ config = {
     'score_tensor_core': True,  # evaluation scores on tcgen05 (exact result; rows failing the certificate are redone)
     'device_sampler': False,    # True: K5 device sampler+shuffle (distributional parity); False: the reference's rand() stream
     'rowpart_p2p': True,        # dist_mode='rowpart': K1 stores its rows into the peers' buffers (fused exchange)
+    'rowpart_rebalance': 2,     # rounds of time-based re-partitioning at start-up (0: balance nnz + row cost only)
+    'rowpart_multicast': True,  # ... through one NVSwitch multicast store (symmetric memory) when the box offers it
     'spmm_seg_len': 128,        # degree-binning threshold of K1
 }
 

@@ -109,12 +109,14 @@ typedef struct {
  * the Adam epilogue), mapped into this process (CUDA IPC) and pre-offset to this rank's row block like Y itself.  The
  * epilogue stores every finished row locally and into each peer over NVLink; the ranks then only need a barrier. */
 typedef struct {
-    int32_t n_peers; int32_t pad;
+    int32_t n_peers;
+    int32_t multicast;            /* != 0: n_peers == 1 and y[0] / p[0] are NVSwitch MULTICAST addresses (multimem) of the
+                                     row block — one multimem.st per 16 bytes reaches every replica, this GPU's included */
     void* y[LGCN_MAX_PEERS];      /* NULL entries are skipped by the Adam variant when Y is not written */
     void* p[LGCN_MAX_PEERS];      /* Adam variant only */
 } lgcn_spmm_peers_t;
 
-/* counts_out int32[4] = {n_long, n_segs, longest item, -} (device).  A row is cut into at most 256 segments. */
+/* counts_out int32[4] = {n_long, n_segs, longest item, -} (device).  A row is cut into at most 2048 segments. */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
                          int32_t* counts_out, lgcn_stream_t stream);
 size_t lgcn_spmm_plan_workspace_bytes(int32_t max_len);

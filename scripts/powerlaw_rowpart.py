@@ -21,6 +21,8 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--row_cost", type=int, default=-1)
 ap.add_argument("--no_p2p", action="store_true")
+ap.add_argument("--no_multicast", action="store_true")
+ap.add_argument("--rebalance", type=int, default=2)
 a = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr_ = int(os.environ.get("LOCAL_RANK", "0"))
@@ -30,7 +32,7 @@ if world > 1:
 lg.world.configure(device=f"cuda:{lr_}")
 cfg = dict(lg.world.config)
 cfg.update(dist_mode='rowpart' if world > 1 else None, cuda_graph=False, bpr_batch_size=2048,
-           rowpart_row_cost=None if a.row_cost < 0 else a.row_cost, rowpart_p2p=not a.no_p2p)
+           rowpart_row_cost=None if a.row_cost < 0 else a.row_cost, rowpart_p2p=not a.no_p2p, rowpart_multicast=not a.no_multicast, rowpart_rebalance=a.rebalance)
 t0 = time.perf_counter()
 tu, ti = lg.synth.make_powerlaw_device(a.users, a.items, a.edges, seed=2020)
 torch.cuda.synchronize(); t_gen = time.perf_counter() - t0
@@ -77,14 +79,58 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 spmm_ms = e0.elapsed_time(e1) / 5
 loss = float(eng.loss_to_host()[2])
+# where a step's time goes: the forward propagation alone (L layers with their exchanges), one exchanged layer alone
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(reps):
+        fn()
+    a1.record(); torch.cuda.synchronize()
+    t = torch.tensor([a0.elapsed_time(a1) / reps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+r0_, r1_ = eng.r0, eng.r1
+def _spmm_only():
+    mc = eng._mc.get(eng.X[0].data_ptr(), 0) if getattr(eng, "_mc", None) else 0
+    peers = eng._peer.get(eng.X[0].data_ptr()) if eng.p2p else None
+    if mc:
+        lg.ops.spmm(eng.local, eng.E0, eng.X[0][r0_:r1_], mc_y=mc + r0_ * eng.d * 4)
+    elif peers is not None:
+        lg.ops.spmm(eng.local, eng.E0, eng.X[0][r0_:r1_], peer_y=[peers[p][r0_:r1_] for p in range(world) if p != rank])
+    else:
+        lg.ops.spmm(eng.local, eng.E0, eng.X[0][r0_:r1_])
+def timed_local(fn, reps=5):          # this rank's own time, no max over ranks
+    fn(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(reps):
+        fn()
+    a1.record(); torch.cuda.synchronize()
+    return a0.elapsed_time(a1) / reps
+mine = torch.tensor([timed_local(_spmm_only), timed_local(lambda: lg.ops.spmm(eng.local, eng.E0, Y)),
+                     timed_local(eng._rank_barrier) if world > 1 and eng.p2p else 0.0], device="cuda", dtype=torch.float64)
+per_rank = [torch.zeros_like(mine) for _ in range(world)]
+if world > 1:
+    dist.all_gather(per_rank, mine)
+else:
+    per_rank = [mine]
+per_rank = [[round(float(x), 3) for x in t.tolist()] for t in per_rank]
+fwd_ms = timed(lambda: eng.forward())
+layer_ms = timed(lambda: eng._layer(eng.E0, eng.X[0], 1.0, 0.0, None))
 if rank == 0:
     nnz_local = eng.local.nnz
     alg = 8 * nnz_local + 4 * (eng.local.n_rows + 1) + 4 * eng.N * 64 + 4 * eng.local.n_rows * 64
     print(json.dumps({"config": f"power-law {a.users} x {a.items}, {a.edges} edges, rowpart over {world} GPUs", "n_gpus": world,
                       "nnz": g.nnz, "n_long": g.n_long, "n_segs": g.n_segs, "gen_s": t_gen, "csr_build_s": t_build,
                       "ms_per_step": float(ms.item()), "samples_per_s": B / (float(ms.item()) * 1e-3), "loss": loss,
-                      "local_spmm_ms": spmm_ms, "local_spmm_alg_gbs": alg / (spmm_ms * 1e-3) / 1e9,
-                      "rows_local": eng.local.n_rows, "nnz_local": nnz_local, "bounds": eng.bounds, "p2p": eng.p2p,
+                      "per_rank_ms_[spmm+stores, spmm_local, barrier]": per_rank, "forward_ms": fwd_ms, "exchanged_layer_ms": layer_ms, "local_spmm_ms": spmm_ms, "local_spmm_alg_gbs": alg / (spmm_ms * 1e-3) / 1e9,
+                      "rows_local": eng.local.n_rows, "nnz_local": nnz_local, "bounds": eng.bounds, "p2p": eng.p2p, "multicast": bool(getattr(eng, "_mc", None)),
                       "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
 if world > 1:
     dist.destroy_process_group()

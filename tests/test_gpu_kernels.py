@@ -110,7 +110,7 @@ def test_spmm_vs_oracle(lg, orc, d, seg_len):
     if seg_len <= 8:
         assert g.n_segs > 0 and g.n_long > 0
     if seg_len == 2:
-        assert g.max_item_len >= 3                       # the hub row hit the 256-segment cap: longer segments
+        assert g.max_item_len == 2                       # 400 parts for the hub row: below the 2048-part cap
     N = nu + ni
     X = rng.normal(0, 0.1, (N, d)).astype(np.float32)
     Z1 = rng.normal(0, 0.1, (N, d)).astype(np.float32); Z2 = rng.normal(0, 0.1, (N, d)).astype(np.float32)
@@ -124,6 +124,26 @@ def test_spmm_vs_oracle(lg, orc, d, seg_len):
     # second launch on the same plan: arrival counters must have reset themselves
     lg.ops.spmm(g, dev(X), Y)
     assert rel_err(Y.cpu().numpy(), AX) < TOL
+
+
+def test_spmm_hub_row_hits_the_part_cap(lg, orc):
+    """A row is cut into at most 2048 parts (the last-arriving part adds the partials in part order, several loads in
+    flight): with seg_len 2 a 5000-non-zero row gets 3-element parts, and the result still matches the oracle."""
+    rng = np.random.default_rng(77)
+    nu, ni, d = 40, 6000, 64
+    tu = np.concatenate([np.full(5000, 7), rng.integers(0, nu, 3000)]).astype(np.int64)
+    ti = np.concatenate([rng.permutation(ni)[:5000], rng.integers(0, ni, 3000)]).astype(np.int64)
+    g = build(lg, tu, ti, nu, ni, seg_len=2)
+    assert g.max_item_len == 3 and g.n_long > 0
+    N = nu + ni
+    X = rng.normal(0, 0.1, (N, d)).astype(np.float32)
+    indptr, indices, vals = (t.cpu().numpy() for t in (g.indptr, g.indices, g.vals))
+    ref = orc.spmm_scipy(indptr, indices, vals.astype(np.float64), X.astype(np.float64))
+    Y = torch.empty((N, d), device='cuda')
+    lg.ops.spmm(g, dev(X), Y)
+    assert rel_err(Y.cpu().numpy(), ref) < TOL
+    Y2 = torch.empty_like(Y); lg.ops.spmm(g, dev(X), Y2)
+    assert torch.equal(Y, Y2)                                    # fixed summation order: bitwise repeatable
 
 
 def test_spmm_empty_rows_and_zero_degree_nodes(lg, orc):

@@ -213,3 +213,22 @@ def test_world_has_reference_defaults():
     c = lg.world.config
     assert (c['latent_dim_rec'], c['lightGCN_n_layers'], c['bpr_batch_size'], c['test_u_batch_size']) == (64, 3, 2048, 100)
     assert (c['lr'], c['decay'], lg.world.topks, lg.world.seed) == (0.001, 1e-4, [20], 2020)
+
+
+def test_rebalance_by_time_moves_boundaries_toward_equal_time():
+    """Row partition: equal cost is not equal time (item rows gather from the larger table); given measured block times
+    the boundaries move so that, with time proportional to cost inside a block, every block takes the same time."""
+    import torch
+    from lgcn_b200.engine import balanced_row_bounds, rebalance_by_time
+    indptr = torch.arange(0, 101 * 10, 10, dtype=torch.int64)             # 100 rows, 10 non-zeros each
+    b = balanced_row_bounds(indptr, 2)
+    assert b == [0, 50, 100]
+    nb = rebalance_by_time(indptr, b, [1.0, 3.0])                         # block 1 is 3x slower per unit of cost
+    assert nb[0] == 0 and nb[-1] == 100 and 65 <= nb[1] <= 68             # 50 + (1/3) * 50
+    # predicted times after the move are equal
+    t0 = 1.0 + 3.0 * (nb[1] - 50) / 50; t1 = 3.0 * (100 - nb[1]) / 50
+    assert abs(t0 - t1) < 0.15
+    assert rebalance_by_time(indptr, b, [2.0, 2.0]) == b                  # already balanced: unchanged
+    b4 = balanced_row_bounds(indptr, 4, row_cost=5)
+    nb4 = rebalance_by_time(indptr, b4, [1.0, 1.0, 1.0, 5.0], row_cost=5)
+    assert nb4[0] == 0 and nb4[-1] == 100 and all(x <= y for x, y in zip(nb4, nb4[1:])) and nb4[3] > b4[3]
