@@ -26,6 +26,10 @@ Multi-GPU (one process per GPU, torch.distributed):
                   each other's buffers (CUDA IPC) and K1's epilogue stores each finished row into all peers
                   over NVLink while the gathers of the following rows are in flight; a 4-byte all-reduce is the
                   only collective left per layer.  p2p=False falls back to NCCL broadcasts after the kernel.
+                  multicast=True (default): the exchanged tables live in torch symmetric memory and the epilogue
+                  issues ONE NVSwitch multicast store (multimem.st) per 16 bytes instead of world-1 unicast stores.
+                  rebalance=2 (default): the block boundaries are moved to equal measured time at start-up —
+                  item rows gather from the larger table, so equal nnz (+ row cost) is not equal time.
 """
 import torch
 
