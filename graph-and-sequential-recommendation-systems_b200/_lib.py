@@ -70,6 +70,8 @@ _SIGNATURES = {
     "lgcn_score_topk_tc": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32,
                                           _P, _P, _P, _P, _P, c_size_t, _P]),
     "lgcn_score_topk_tc_debug_layout": (ctypes.c_int, [c_int32, c_int32, _P]),
+    "lgcn_score_topk_tc_host_position": (c_int32, [c_int32, c_int32]),
+    "lgcn_score_topk_tc_host_item": (c_int32, [c_int32, c_int32]),
     "lgcn_score_topk_tc_position_space": (c_int32, [c_int32]),
     "lgcn_score_topk_tc_item_positions": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P]),
     "lgcn_score_dense": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),

@@ -796,3 +796,14 @@ extern "C" int lgcn_score_topk_tc_debug_layout(int32_t Bt, int32_t m_items, int6
     out8_host[4] = L.tiles_per_split; out8_host[5] = (int64_t)L.off_mx; out8_host[6] = L.tile_stride; out8_host[7] = TC_CAP;
     return 0;
 }
+
+// host-side view of the item layout (no device needed): position of an item, item at a position (-1 for a hole)
+extern "C" int32_t lgcn_score_topk_tc_host_position(int32_t item, int32_t m_items) {
+    if (m_items < TC_MIN_ITEMS || item < 0 || item >= m_items) return -1;
+    return tc_pos_of_item(item, tc_order(m_items));
+}
+extern "C" int32_t lgcn_score_topk_tc_host_item(int32_t pos, int32_t m_items) {
+    if (m_items < TC_MIN_ITEMS || pos < 0 || pos >= lgcn_score_topk_tc_position_space(m_items)) return -1;
+    const int item = tc_item_of_pos(pos, tc_order(m_items));
+    return item < m_items ? item : -1;
+}

@@ -239,6 +239,9 @@ int32_t lgcn_score_topk_tc_position_space(int32_t m_items);
 /* diagnostics: {offset of tau, offset of the event counts, lists per row, item tiles, tiles per split, offset of the
  * sample maxima, their row stride, events per list} of the workspace layout for this (Bt, m_items) */
 int lgcn_score_topk_tc_debug_layout(int32_t Bt, int32_t m_items, int64_t* out8_host);
+/* the same mapping on the host (no device needed): position of an item; item at a position, -1 for a hole */
+int32_t lgcn_score_topk_tc_host_position(int32_t item, int32_t m_items);
+int32_t lgcn_score_topk_tc_host_item(int32_t pos, int32_t m_items);
 int lgcn_score_topk_tc_item_positions(const int64_t* items, int64_t n, int32_t m_items, int64_t* pos_out, lgcn_stream_t stream);
 int lgcn_score_topk_tc(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
                        int32_t m_items, int32_t d, const int32_t* mask_indptr, const int32_t* mask_indices,

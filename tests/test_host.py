@@ -232,3 +232,31 @@ def test_rebalance_by_time_moves_boundaries_toward_equal_time():
     b4 = balanced_row_bounds(indptr, 4, row_cost=5)
     nb4 = rebalance_by_time(indptr, b4, [1.0, 1.0, 1.0, 5.0], row_cost=5)
     assert nb4[0] == 0 and nb4[-1] == 100 and all(x <= y for x, y in zip(nb4, nb4[1:])) and nb4[3] > b4[3]
+
+
+@pytest.mark.parametrize("m", [16384, 16385, 16511, 16512, 20011, 38048, 40981, 91599])
+def test_tensor_core_item_layout_is_a_bijection_with_holes_in_the_last_slot(m):
+    """The interleaved item order of the tensor-core ranking (host view of the mapping the kernels use): every item has
+    one position, positions map back, the 128*T - m unused positions are all slot 127 (the only place the kernel masks
+    holes), the sampled half of a tile (slots 0-63) holds exactly the items of the even blocks, and neighbouring item
+    ids never share a tile."""
+    import lgcn_b200 as lg
+    lib = lg._lib.load()
+    space = lib.lgcn_score_topk_tc_position_space(m)
+    T = (m + 127) // 128
+    assert space == 128 * T
+    pos = np.array([lib.lgcn_score_topk_tc_host_position(i, m) for i in range(m)], dtype=np.int64)
+    assert pos.min() >= 0 and pos.max() < space and np.unique(pos).size == m
+    back = np.array([lib.lgcn_score_topk_tc_host_item(int(p), m) for p in pos[:: max(1, m // 4000)]])
+    assert np.array_equal(back, np.arange(m)[:: max(1, m // 4000)])
+    used = np.zeros(space, dtype=bool); used[pos] = True
+    holes = np.nonzero(~used)[0]
+    assert holes.size == space - m and np.all(holes % 128 == 127)
+    assert all(lib.lgcn_score_topk_tc_host_item(int(h), m) == -1 for h in holes[:50])
+    blk = np.arange(m) // T
+    assert np.array_equal((pos % 128) < 64, blk % 2 == 0)                       # sampled half = even blocks
+    tile = pos // 128
+    assert np.all(tile[1:][blk[1:] == blk[:-1]] != tile[:-1][blk[1:] == blk[:-1]])   # neighbours in different tiles
+    far = np.abs(tile[1:] - tile[:-1])[blk[1:] == blk[:-1]]
+    assert np.median(far) > T // 4                                              # ... and far apart
+    assert lib.lgcn_score_topk_tc_host_position(0, 1000) == -1                  # small tables are not laid out at all
