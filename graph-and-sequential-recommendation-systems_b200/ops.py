@@ -4,6 +4,7 @@ torch is used for device memory and streams only; every computation below is a k
 liblgcn_b200.so launched on torch's current CUDA stream.  Nothing here falls back to torch ops.
 """
 import ctypes
+import os
 from ctypes import byref, c_void_p
 
 import torch
@@ -349,7 +350,8 @@ def score_topk_tc(users_emb, items_emb, users, k, mask_indptr=None, mask_indices
                                       c_void_p(ws_ptr), ws_bytes, _stream()), "score_topk_tc")
     n = int(n_flagged.item())
     global last_tc_flags, last_tc_workspace
-    last_tc_workspace = (ws, ws_ptr - ws.data_ptr(), Bt, m_items)      # diagnostics (lgcn_score_topk_tc_debug_layout)
+    # diagnostics (lgcn_score_topk_tc_debug_layout): the workspace is several hundred MB, so it is only kept on request
+    last_tc_workspace = (ws, ws_ptr - ws.data_ptr(), Bt, m_items) if os.environ.get("LGCN_TC_KEEP_WORKSPACE") else None
     last_tc_flags = flags            # per row: 0 certified, 1 certificate failed, 2 fewer than k candidates, 3 candidate list overflowed
     if n:   # rows that could not be certified: exact path, scattered back
         rows = torch.nonzero(flags, as_tuple=False).flatten()

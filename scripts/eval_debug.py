@@ -1,4 +1,5 @@
 import os, sys, numpy as np, torch
+os.environ["LGCN_TC_KEEP_WORKSPACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import lgcn_b200 as lg
 z = np.load(os.path.join(ROOT, "tests", "golden", "gowalla.npz"))
