@@ -139,7 +139,10 @@ def Test(dataset, Recmodel, epoch, w=None, multicore=0):
         n_users_eval = users_dev.numel()
         if n_users_eval:
             if hasattr(Recmodel, 'rank_topk'):
-                topk = rank_all(dataset, Recmodel, max_K, user_tile=max(int(world.config.get('test_u_batch_size', 100)), 8192))
+                # one call ranks a whole tile of users; the tensor-core path takes everybody at once (its workspace is a few
+                # hundred MB for 64 k users), the exact kernel works in tiles of 8192
+                tc = bool(getattr(Recmodel, 'config', world.config).get('score_tensor_core', True)) and dataset.m_items >= ops.TC_MIN_ITEMS
+                topk = rank_all(dataset, Recmodel, max_K, user_tile=max(int(world.config.get('test_u_batch_size', 100)), 65536 if tc else 8192))
             else:   # a foreign model: the reference's unfused recipe, one user tile at a time
                 parts = []
                 u_bs = world.config['test_u_batch_size']
