@@ -260,3 +260,35 @@ def test_tensor_core_item_layout_is_a_bijection_with_holes_in_the_last_slot(m):
     far = np.abs(tile[1:] - tile[:-1])[blk[1:] == blk[:-1]]
     assert np.median(far) > T // 4                                              # ... and far apart
     assert lib.lgcn_score_topk_tc_host_position(0, 1000) == -1                  # small tables are not laid out at all
+
+
+def test_native_parser_fuzz_against_python_split(tmp_path):
+    """Property test (hypothesis): any file made of non-negative integers separated by blanks/tabs and line ends parses
+    to the same pairs as Python's line.split() loop, and the id maxima come from lines that have items."""
+    import ctypes
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    import lgcn_b200 as lg
+    from lgcn_b200 import dataloader
+    lib = lg._lib.load()
+    sep = st.sampled_from([" ", "  ", "\t", " \t "])
+    line = st.tuples(st.lists(st.integers(0, 2**31 - 1), min_size=0, max_size=6), sep, st.sampled_from(["", " ", "\r"]))
+    path = tmp_path / "f.txt"
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(line, min_size=0, max_size=30), st.sampled_from(["\n", ""]))
+    def check(lines, tail):
+        text = "\n".join(s.join(str(v) for v in vals) + end for vals, s, end in lines) + tail
+        path.write_text(text)
+        eu, ei = [], []
+        for l in text.split("\n"):
+            cols = l.split()
+            if len(cols) >= 2:
+                eu.extend([int(cols[0])] * (len(cols) - 1)); ei.extend(int(c) for c in cols[1:])
+        u, i = dataloader._parse_interactions(str(path))
+        assert u.tolist() == eu and i.tolist() == ei
+        mu, mi = ctypes.c_int64(), ctypes.c_int64()
+        n = lib.lgcn_parse_interactions(str(path).encode(), None, None, 0, ctypes.byref(mu), ctypes.byref(mi))
+        assert n == len(eu) and mu.value == (max(eu) if eu else -1) and mi.value == (max(ei) if ei else -1)
+
+    check()
