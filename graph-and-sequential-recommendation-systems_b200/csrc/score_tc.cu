@@ -6,38 +6,40 @@
 // Replaces torch.matmul (reference code/model.py:122), the -(1<<10) mask (code/Procedure.py:177-181)
 // and torch.topk (code/Procedure.py:183).
 //
-// The B x M score matrix is produced twice on the tensor pipe and never written.  Both passes run at the rate at
-// which the accumulators can be read out of TMEM (tcgen05.ld, 4 B per score), which for K = 64 is about half the
-// tensor-pipe rate — the epilogues are arranged to stay under that:
+// The B x M score matrix is produced twice on the tensor pipe and never written.  What sets the pace (measured,
+// profiles/README.md): with both operands in shared memory an M128 N128 K8 tf32 MMA needs the whole 128 B/clk of
+// shared memory (100 cycles per MMA instead of 64), and pass 2 reads every score out of TMEM (64 B/clk).
 //
 //   pass 1   score_tc_kernel<1>: CTA = 256 users (two 128-row MMA tiles sharing every B tile) x a split of the
 //            item tiles.  warp 0 = TMA producer (4-stage ring of 128-item tiles), warp 1 = MMA issuer
-//            (16 x tcgen05.mma.kind::tf32 M128 N128 K8 per tile, double-buffered TMEM accumulators), warps 2-9 =
-//            epilogue (two groups of 8 warps taking alternate tiles): a thread owns one row and reads the FIRST 64
-//            items of the tile (tcgen05.ld 32x32b.x32) — a 50 % sample, which halves the TMEM traffic — and reduces them
-//            to ONE number, the largest approximate score among the sampled items that are NOT train items of the
-//            row (a cursor walks the sorted CSR row) -> sample-maxima matrix Mx[row][tile].
+//            (16 x tcgen05.mma.kind::tf32 M128 N128 K8 per tile, double-buffered TMEM accumulators), warps 2-17 =
+//            epilogue, in pass 1 two groups of 8 warps taking alternate tiles: a thread owns one row and reads the
+//            FIRST 64 items of the tile (tcgen05.ld 32x32b.x32) — a 50 % sample, which halves the TMEM traffic — and
+//            reduces them to ONE number, the largest approximate score among the sampled items that are NOT train
+//            items of the row (a cursor walks the sorted position-space mask row) -> sample maxima Mx[row][tile].
 //   select   tc_select_kernel: warp per row, radix select: the KSEL-th largest sample maximum is the row threshold
 //            tau.  KSEL unmasked sampled items score >= tau, hence about 2*KSEL +- sqrt(2*KSEL) items overall (any
 //            tau is SAFE — the certificate below does not depend on how it was chosen; a poor tau only costs time).
-//   pass 2   score_tc_kernel<2>: the same GEMM; the epilogue compares against the now FIXED tau (4 scores per
-//            compare), and the rare hits are mask-checked (cursor through the sorted train row) and appended to
-//            the row's candidate list in global memory.  No sorting, no cooperation between lanes.
-//   rescore  rescore_kernel: warp per row recomputes the candidates' scores as the fp32 FMA chain of the exact
-//            contract, selects the top-k (score desc, item id asc) and CERTIFIES it: every item that is not a
-//            candidate is masked or has approx < tau, hence exact < tau + eps with
-//            eps = c * |u| * max|v| (TF32 truncation bound, Cauchy-Schwarz); if tau + eps < (k-th exact score)
-//            nothing outside the candidate set can enter the top-k.  Rows that fail the certificate, overflow
-//            their candidate list or have < k unmasked items are flagged and re-done by the exact kernel — the
-//            caller sees one bit-exact result either way.
+//   pass 2   score_tc_kernel<2>: the same GEMM; 16 epilogue warps, a thread owns one row and one 64-item half of
+//            every tile and compares 4 scores at a time against the now FIXED tau.  A hit (rare per lane) stores the
+//            4 scores, their position and the mask bits of the group as one event in the list of its (row, split,
+//            half) in global memory.  No sorting, no cooperation between lanes, no running threshold.
+//   rescore  rescore_kernel: warp per row keeps the event scores that reach tau and are not train items, recomputes
+//            them as the fp32 FMA chain of the exact contract (item rows staged through shared memory), ranks by
+//            counting (score desc, item id asc) and CERTIFIES: every item that is not a candidate is masked or
+//            has approx < tau, hence exact < tau + eps with eps = c * |u| * max|v| (TF32 truncation bound,
+//            Cauchy-Schwarz); if tau + eps < (k-th exact score) nothing outside the candidate set can enter the
+//            top-k.  Rows that fail the certificate, overflow an event list or have < k candidates are flagged
+//            and re-done by the exact kernel — the caller sees one bit-exact result either way.
 //
 // Item layout.  A tile holds the items {b*T + r : b = 0..127} of one residue r (T = number of tiles), block b sitting
 // in slot (b >> 1) + 64*(b & 1), and residue r is tile (r * mul) mod T with mul ~ 0.618 T: neighbouring item ids land
-// in tiles far apart (different splits), and the sampled half (slots 0-63) is the even blocks.  With items in id order a trained model puts most of a user's best items — popular items with small,
-// adjacent ids — into a few 64-item blocks; each block contributes ONE maximum, tau came out far too low and 70 % of
-// the rows overflowed their candidate lists (real gowalla after 10 epochs).  The interleaved layout makes a block a
-// spread-out sample.  A permuted copy of the item table is made per call (m_items * 256 B, a few us); the train-item
-// mask has to be given in the same position space, sorted per row (lgcn_score_topk_tc_item_positions + lgcn_csr_build).
+// in tiles far apart (different splits), and the sampled half (slots 0-63) is the even blocks.  With items in id
+// order a trained model puts most of a user's best items — popular items with small, adjacent ids — into a few
+// 64-item blocks of one split; each block contributes ONE maximum, tau came out far too low and 70 % of the rows
+// overflowed their lists (real gowalla after 10 epochs).  The interleaved layout makes a block a spread-out sample.
+// A permuted copy of the item table is made per call (m_items * 256 B, a few us); the train-item mask has to be
+// given in the same position space, sorted per row (lgcn_score_topk_tc_item_positions + lgcn_csr_build).
 //
 // Only d = 64, k <= 24 and m_items >= 16384 take this path.
 #include "common.cuh"
