@@ -33,8 +33,8 @@
 //            and re-done by the exact kernel — the caller sees one bit-exact result either way.
 //
 // Item layout.  A tile holds the items {b*T + r : b = 0..127} of one residue r (T = number of tiles), block b sitting
-// in slot (b >> 1) + 64*(b & 1), and residue r is tile (r * mul) mod T with mul ~ 0.618 T: neighbouring item ids land
-// in tiles far apart (different splits), and the sampled half (slots 0-63) is the even blocks.  With items in id
+// in slot (b >> 1) + 64*((b + r) & 1), and residue r is tile (r * mul) mod T with mul ~ 0.618 T: neighbouring item ids
+// land in tiles far apart (different splits), and the sampled half (slots 0-63) alternates from one id to the next.  With items in id
 // order a trained model puts most of a user's best items — popular items with small, adjacent ids — into a few
 // 64-item blocks of one split; each block contributes ONE maximum, tau came out far too low and 70 % of the rows
 // overflowed their lists (real gowalla after 10 epochs).  The interleaved layout makes a block a spread-out sample.
@@ -77,7 +77,7 @@ struct TcOrder { int T, mul, inv; };       // item layout, see tc_pos_of_item: i
 struct TcArgs {
     int Bt; int m_items;
     TcOrder order;
-    int hole_from_residue;               // tiles of residue >= this have no item in their last slot (128*T - m_items < 128 holes, all in block 127)
+    int hole_from_residue;               // tiles of residue >= this have no item of block 127 (128*T - m_items < 128 holes): slot 127 (even residue) or 63 (odd)
     const long long* users;
     const int* mask_indptr; const int* mask_indices; int mask_col_offset;
     int tiles_per_split; int n_splits;
@@ -89,15 +89,19 @@ struct TcArgs {
 
 // position (tile * 128 + slot) <-> item id.  T = number of item tiles; item i belongs to "residue" r = i % T and block
 // b = i / T; it sits in tile (r * mul) % T (mul coprime to T, about 0.618 T: neighbouring ids land far apart, so a
-// run of popular ids is spread over all the splits of the tile range) and slot (b >> 1) + 64 * (b & 1).
+// run of popular ids is spread over all the splits of the tile range) and slot (b >> 1) + 64 * ((b + r) & 1): the
+// sampled half of a tile (slots 0-63) is the items with b + r even, so whether an item is sampled alternates from one
+// id to the next (with (b & 1) alone it was constant over runs of T ids — a model whose best items all had ids in
+// [T, 2T) would have had none of them in the sample).  Block 127 is the only one with holes (ids >= m_items): slot 127
+// in the tiles of even residue, slot 63 in those of odd residue.
 __host__ __device__ __forceinline__ int tc_pos_of_item(int i, TcOrder o) {
     const int b = i / o.T, r = i - b * o.T;
-    return (int)(((long long)r * o.mul) % o.T) * TC_N + (b >> 1) + 64 * (b & 1);
+    return (int)(((long long)r * o.mul) % o.T) * TC_N + (b >> 1) + 64 * ((b ^ r) & 1);
 }
 __host__ __device__ __forceinline__ int tc_residue_of_tile(int tile, TcOrder o) { return (int)(((long long)tile * o.inv) % o.T); }
 __host__ __device__ __forceinline__ int tc_item_of_pos(int p, TcOrder o) {
-    const int s = p & (TC_N - 1);
-    return (2 * (s & 63) + (s >> 6)) * o.T + tc_residue_of_tile(p >> 7, o);
+    const int s = p & (TC_N - 1), r = tc_residue_of_tile(p >> 7, o);
+    return (2 * (s & 63) + (((s >> 6) ^ r) & 1)) * o.T + r;
 }
 static TcOrder tc_order(int m_items) {
     TcOrder o; o.T = (m_items + TC_N - 1) / TC_N;
@@ -382,7 +386,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tc_fence_before();
                 mbar_arrive(BAR(T_EMPTY + acc));                   // accumulator free: this warp's part is in registers
                 // train items of the row take no part
-                const unsigned bad0 = (unsigned)mb, bad1 = (unsigned)(mb >> 32);     // (the holes of the layout are all in the other half)
+                const int res1 = tc_residue_of_tile(t_begin + it, a.order);
+                const unsigned hole1 = ((res1 & 1) && res1 >= a.hole_from_residue) ? 0x80000000u : 0u;      // slot 63 of an odd residue
+                const unsigned bad0 = (unsigned)mb, bad1 = (unsigned)(mb >> 32) | hole1;
                 if (bad0) tc_kill_columns(ra_, bad0);
                 if (bad1) tc_kill_columns(rb_, bad1);
                 my[lane * TC_STG + ((nbuf + lane) & (TC_STG - 1))] = fmaxf(tc_max32(ra_), tc_max32(rb_));
@@ -411,7 +417,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait(ra_); tmem_ld_fence(rb_);
                 tc_fence_before();
                 mbar_arrive(BAR(T_EMPTY + acc));
-                const unsigned hole = (half == 1 && residue >= a.hole_from_residue) ? 0x80000000u : 0u;   // slot 127 = block 127
+                // block 127 is missing in this tile: slot 127 (half 1) if the residue is even, slot 63 (half 0) if it is odd
+                const unsigned hole = (residue >= a.hole_from_residue && ((residue & 1) ^ half)) ? 0x80000000u : 0u;
                 residue += a.order.inv; if (residue >= a.order.T) residue -= a.order.T;          // residue of the next tile
                 tc_collect(ra_, i0, (unsigned)mb, hs);
                 tc_collect(rb_, i0 + 32, (unsigned)(mb >> 32) | hole, hs);
