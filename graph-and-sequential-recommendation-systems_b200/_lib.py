@@ -43,12 +43,18 @@ _SIGNATURES = {
     "lgcn_debug_poke": (ctypes.c_int, [_P, c_float, c_int32, POINTER(c_int32), _P]),
     "lgcn_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "lgcn_csr_build": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "lgcn_degree_accumulate": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, _P]),
+    "lgcn_degree_finalize": (ctypes.c_int, [_P, c_int32, _P, _P, _P]),
+    "lgcn_csr_rows_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "lgcn_csr_rows_emit": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
+    "lgcn_csr_rows_finish": (ctypes.c_int, [c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "lgcn_rank_barrier": (ctypes.c_int, [_P, POINTER(c_void_p), c_int32, c_int32, _P, _P, c_int32, _P]),
     "lgcn_coo_to_csr": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
     "lgcn_spmm_plan_count": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P]),
     "lgcn_spmm_plan_workspace_bytes": (c_size_t, [c_int32]),
     "lgcn_spmm_plan_fill": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_size_t, _P]),
     "lgcn_spmm_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
-                                     POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P]),
+                                     POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
     "lgcn_spmm_adam_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                           POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
     "lgcn_debug_spmm_variant": (ctypes.c_int, [ctypes.c_int]),

@@ -148,6 +148,7 @@ radix_scatter_kernel(const u64* __restrict__ keys, u64* __restrict__ out, long l
 // ------------------------------------------------------------------ CSR assembly
 struct BuildArgs {
     const long long* tu; const long long* ti; long long E; int nu; int ni; int N; int cb;
+    int row_base; int n_rows;      // rows [row_base, row_base + n_rows) are assembled (a row block); keys hold LOCAL rows
     int* indptr; int* indices; float* vals; float* deg; float* dinv; long long* nnz_out; int* status;
     int* excl; int* headpos; int* erow; int* rawptr; int* total;
 };
@@ -184,7 +185,7 @@ __global__ void assemble_kernel(BuildArgs a, const u64* __restrict__ keys, long 
     for (int r = prev_row + 1; r <= row; ++r) { a.indptr[r] = ui; a.rawptr[r] = (int)j; }   // ui == excl[j] here
     if (j == n - 1) {
         const int U = *a.total;
-        for (int r = row + 1; r <= a.N; ++r) { a.indptr[r] = U; a.rawptr[r] = (int)n; }
+        for (int r = row + 1; r <= a.n_rows; ++r) { a.indptr[r] = U; a.rawptr[r] = (int)n; }
         a.headpos[U] = (int)n;
         *a.nnz_out = (long long)U;
     }
@@ -209,7 +210,57 @@ __global__ void values_kernel(BuildArgs a, long long n) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n || e >= *a.total) return;
     const float w = (float)(a.headpos[e + 1] - a.headpos[e]);
-    a.vals[e] = __fmul_rn(__fmul_rn(a.dinv[a.erow[e]], w), a.dinv[a.indices[e]]);
+    a.vals[e] = __fmul_rn(__fmul_rn(a.dinv[a.row_base + a.erow[e]], w), a.dinv[a.indices[e]]);
+}
+
+// ---- row-block build (multi-GPU row partition: every rank assembles only the rows it owns) ----------------------
+// weighted degrees of ALL nodes from an edge chunk (duplicates counted, like the row sums of code/dataloader.py:230)
+__global__ void degree_count_kernel(const long long* __restrict__ tu, const long long* __restrict__ ti, long long E,
+                                    int nu, int ni, int* __restrict__ counts, int* status) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const long long u = tu[e], i = ti[e];
+    if (u < 0 || u >= nu || i < 0 || i >= ni) { atomicExch(status, 1); return; }
+    atomicAdd(counts + u, 1);
+    atomicAdd(counts + nu + i, 1);
+}
+
+__global__ void degree_finalize_kernel(const int* __restrict__ counts, int N, float* __restrict__ deg, float* __restrict__ dinv) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int dw = counts[r];
+    deg[r] = (float)dw;
+    dinv[r] = dw > 0 ? (float)(1.0 / sqrt((double)dw)) : 0.f;
+}
+
+// both directions of every edge whose ROW lies in [row_begin, row_end): key = (row - row_begin) << cb | col, appended at
+// a device cursor (the order is irrelevant: the keys are sorted next)
+__global__ void emit_block_keys_kernel(const long long* __restrict__ tu, const long long* __restrict__ ti, long long E,
+                                       int nu, int ni, int cb, int row_begin, int row_end, u64* __restrict__ keys,
+                                       long long cap, unsigned long long* cursor, int* status) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 k0 = 0, k1 = 0; int n = 0;
+    if (e < E) {
+        const long long u = tu[e], i = ti[e];
+        if (u < 0 || u >= nu || i < 0 || i >= ni) atomicExch(status, 1);
+        else {
+            const int r = (int)u, c = nu + (int)i;
+            if (r >= row_begin && r < row_end) { k0 = ((u64)(r - row_begin) << cb) | (u64)c; n = 1; }
+            if (c >= row_begin && c < row_end) { const u64 k = ((u64)(c - row_begin) << cb) | (u64)r; if (n) k1 = k; else k0 = k; ++n; }
+        }
+    }
+    // warp-aggregated append
+    const unsigned lane = threadIdx.x & 31;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const long long at = (long long)base + incl - n;
+    if (n >= 1) { if (at < cap) keys[at] = k0; else atomicExch(status, 2); }
+    if (n == 2) { if (at + 1 < cap) keys[at + 1] = k1; else atomicExch(status, 2); }
 }
 
 __global__ void coo_to_csr_kernel(const long long* __restrict__ rows, const long long* __restrict__ cols,
@@ -232,8 +283,8 @@ static int bits_for(long long max_value) { int b = 1; while ((1LL << b) <= max_v
 
 struct Layout { size_t keysA, keysB, hist, scan_tmp, excl, headpos, erow, rawptr, total, end; long long nblk; };
 
-static Layout make_layout(long long E, int N) {
-    Layout L; const long long n = 2 * E;
+static Layout make_layout_keys(long long n, int N) {
+    Layout L;
     L.nblk = (n + kSortTile - 1) / kSortTile; if (L.nblk < 1) L.nblk = 1;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
@@ -249,6 +300,34 @@ static Layout make_layout(long long E, int N) {
     L.total = take(16);
     L.end = o;
     return L;
+}
+
+static Layout make_layout(long long E, int N) { return make_layout_keys(2 * E, N); }
+
+// sorted keys -> indptr/indices (+ erow/headpos/rawptr for the value pass); `bits` = significant key bits
+static int sort_and_assemble(BuildArgs& a, const Layout& L, char* w, long long n, int bits, u64** sorted_out, cudaStream_t st) {
+    u64* kA = reinterpret_cast<u64*>(w + L.keysA);
+    u64* kB = reinterpret_cast<u64*>(w + L.keysB);
+    int* hist = reinterpret_cast<int*>(w + L.hist);
+    int* scan_tmp = reinterpret_cast<int*>(w + L.scan_tmp);
+    const int passes = (bits + 7) / 8;
+    const int nblk = (int)((n + kSortTile - 1) / kSortTile);
+    for (int p = 0; p < passes; ++p) {
+        radix_hist_kernel<<<nblk, kSortThreads, 0, st>>>(kA, n, 8 * p, hist, nblk);
+        LGCN_CHECK_LAUNCH("radix_hist_kernel");
+        if (int rc = scan_exclusive(hist, hist, (long long)kRadix * nblk, scan_tmp, a.total, st)) return rc;
+        radix_scatter_kernel<<<nblk, kSortThreads, 0, st>>>(kA, kB, n, 8 * p, hist, nblk);
+        LGCN_CHECK_LAUNCH("radix_scatter_kernel");
+        u64* t = kA; kA = kB; kB = t;
+    }
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    head_flags_kernel<<<nb, 256, 0, st>>>(kA, n, a.excl);
+    LGCN_CHECK_LAUNCH("head_flags_kernel");
+    if (int rc = scan_exclusive(a.excl, a.excl, n, scan_tmp, a.total, st)) return rc;
+    assemble_kernel<<<nb, 256, 0, st>>>(a, kA, n);
+    LGCN_CHECK_LAUNCH("assemble_kernel");
+    *sorted_out = kA;
+    return 0;
 }
 
 }  // namespace lgcn
@@ -286,36 +365,97 @@ extern "C" int lgcn_csr_build(const int64_t* train_user, const int64_t* train_it
     a.total = reinterpret_cast<int*>(w + L.total);
     cudaMemsetAsync(status_out, 0, sizeof(int32_t), st);
     if (E == 0) {
+        a.row_base = 0; a.n_rows = N;
         empty_graph_kernel<<<(N + 1 + 255) / 256, 256, 0, st>>>(a);
         LGCN_CHECK_LAUNCH("empty_graph_kernel");
         return 0;
     }
     const long long n = 2 * E;
-    u64* kA = reinterpret_cast<u64*>(w + L.keysA);
-    u64* kB = reinterpret_cast<u64*>(w + L.keysB);
-    int* hist = reinterpret_cast<int*>(w + L.hist);
-    int* scan_tmp = reinterpret_cast<int*>(w + L.scan_tmp);
-    emit_keys_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(a, kA);
+    a.row_base = 0; a.n_rows = N;
+    emit_keys_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(a, reinterpret_cast<u64*>(w + L.keysA));
     LGCN_CHECK_LAUNCH("emit_keys_kernel");
-    const int passes = (2 * a.cb + 7) / 8;
-    const int nblk = (int)L.nblk;
-    for (int p = 0; p < passes; ++p) {
-        radix_hist_kernel<<<nblk, kSortThreads, 0, st>>>(kA, n, 8 * p, hist, nblk);
-        LGCN_CHECK_LAUNCH("radix_hist_kernel");
-        if (int rc = scan_exclusive(hist, hist, (long long)kRadix * nblk, scan_tmp, a.total, st)) return rc;
-        radix_scatter_kernel<<<nblk, kSortThreads, 0, st>>>(kA, kB, n, 8 * p, hist, nblk);
-        LGCN_CHECK_LAUNCH("radix_scatter_kernel");
-        u64* t = kA; kA = kB; kB = t;
-    }
+    u64* kA = nullptr;
+    if (int rc = sort_and_assemble(a, L, w, n, 2 * a.cb, &kA, st)) return rc;
     const unsigned nb = (unsigned)((n + 255) / 256);
-    head_flags_kernel<<<nb, 256, 0, st>>>(kA, n, a.excl);
-    LGCN_CHECK_LAUNCH("head_flags_kernel");
-    if (int rc = scan_exclusive(a.excl, a.excl, n, scan_tmp, a.total, st)) return rc;
-    assemble_kernel<<<nb, 256, 0, st>>>(a, kA, n);
-    LGCN_CHECK_LAUNCH("assemble_kernel");
     degree_kernel<<<(N + 255) / 256, 256, 0, st>>>(a);
     LGCN_CHECK_LAUNCH("degree_kernel");
     values_kernel<<<nb, 256, 0, st>>>(a, n);
+    LGCN_CHECK_LAUNCH("values_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_degree_accumulate(const int64_t* train_user, const int64_t* train_item, int64_t E, int32_t n_users, int32_t m_items,
+                                      int32_t* deg_counts, int32_t* status_out, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(E >= 0 && n_users > 0 && m_items > 0 && deg_counts && status_out, "degree_accumulate: bad arguments");
+    LGCN_CHECK_ARG(E == 0 || (train_user && train_item), "degree_accumulate: null edge arrays");
+    if (E == 0) return 0;
+    degree_count_kernel<<<(unsigned)((E + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(train_user), reinterpret_cast<const long long*>(train_item), E, n_users, m_items, deg_counts, status_out);
+    LGCN_CHECK_LAUNCH("degree_count_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_degree_finalize(const int32_t* deg_counts, int32_t n_nodes, float* deg, float* dinv, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(deg_counts && deg && dinv && n_nodes > 0, "degree_finalize: bad arguments");
+    degree_finalize_kernel<<<(n_nodes + 255) / 256, 256, 0, as_stream(stream)>>>(deg_counts, n_nodes, deg, dinv);
+    LGCN_CHECK_LAUNCH("degree_finalize_kernel");
+    return 0;
+}
+
+extern "C" size_t lgcn_csr_rows_workspace_bytes(int64_t n_keys, int32_t n_rows_local) {
+    if (n_keys < 0 || n_rows_local < 0) return 0;
+    return make_layout_keys(n_keys > 0 ? n_keys : 1, n_rows_local).end;
+}
+
+extern "C" int lgcn_csr_rows_emit(const int64_t* train_user, const int64_t* train_item, int64_t E, int32_t n_users, int32_t m_items,
+                                  int32_t row_begin, int32_t row_end, int64_t n_keys_cap, uint64_t* cursor_dev, int32_t* status_out,
+                                  void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(E >= 0 && n_users > 0 && m_items > 0 && cursor_dev && status_out, "csr_rows_emit: bad arguments");
+    const int N = n_users + m_items;
+    LGCN_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "csr_rows_emit: bad row block [%d,%d)", row_begin, row_end);
+    LGCN_CHECK_ARG(n_keys_cap >= 0 && n_keys_cap < 0x7fffffffLL, "csr_rows_emit: n_keys_cap=%lld exceeds int32 CSR offsets", (long long)n_keys_cap);
+    const Layout L = make_layout_keys(n_keys_cap > 0 ? n_keys_cap : 1, row_end - row_begin);
+    LGCN_CHECK_ARG(workspace && workspace_bytes >= L.end && ((uintptr_t)workspace % 256) == 0, "csr_rows_emit: workspace too small or misaligned");
+    if (E == 0) return 0;
+    LGCN_CHECK_ARG(train_user && train_item, "csr_rows_emit: null edge arrays");
+    emit_block_keys_kernel<<<(unsigned)((E + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(train_user), reinterpret_cast<const long long*>(train_item), E, n_users, m_items,
+        bits_for(N - 1), row_begin, row_end, reinterpret_cast<u64*>(static_cast<char*>(workspace) + L.keysA), n_keys_cap,
+        reinterpret_cast<unsigned long long*>(cursor_dev), status_out);
+    LGCN_CHECK_LAUNCH("emit_block_keys_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_csr_rows_finish(int64_t n_keys, int64_t n_keys_cap, int32_t n_users, int32_t m_items, int32_t row_begin, int32_t row_end,
+                                    const float* dinv, int32_t* indptr, int32_t* indices, float* vals, int64_t* nnz_out,
+                                    void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    const int N = n_users + m_items;
+    LGCN_CHECK_ARG(n_users > 0 && m_items > 0 && 0 <= row_begin && row_begin <= row_end && row_end <= N, "csr_rows_finish: bad row block");
+    LGCN_CHECK_ARG(n_keys >= 0 && n_keys <= n_keys_cap && n_keys_cap < 0x7fffffffLL, "csr_rows_finish: bad key count %lld (cap %lld)", (long long)n_keys, (long long)n_keys_cap);
+    LGCN_CHECK_ARG(dinv && indptr && nnz_out && (n_keys == 0 || (indices && vals)), "csr_rows_finish: null output");
+    const int n_rows = row_end - row_begin;
+    const Layout L = make_layout_keys(n_keys_cap > 0 ? n_keys_cap : 1, n_rows);
+    LGCN_CHECK_ARG(workspace && workspace_bytes >= L.end && ((uintptr_t)workspace % 256) == 0, "csr_rows_finish: workspace too small or misaligned");
+    cudaStream_t st = as_stream(stream);
+    char* w = static_cast<char*>(workspace);
+    BuildArgs a;
+    a.tu = nullptr; a.ti = nullptr; a.E = 0; a.nu = n_users; a.ni = m_items; a.N = N; a.cb = bits_for(N - 1);
+    a.row_base = row_begin; a.n_rows = n_rows;
+    a.indptr = indptr; a.indices = indices; a.vals = vals; a.deg = nullptr; a.dinv = const_cast<float*>(dinv);
+    a.nnz_out = reinterpret_cast<long long*>(nnz_out); a.status = nullptr;
+    a.excl = reinterpret_cast<int*>(w + L.excl); a.headpos = reinterpret_cast<int*>(w + L.headpos);
+    a.erow = reinterpret_cast<int*>(w + L.erow); a.rawptr = reinterpret_cast<int*>(w + L.rawptr);
+    a.total = reinterpret_cast<int*>(w + L.total);
+    if (n_keys == 0) {
+        fill_i32_kernel<<<(n_rows + 1 + 255) / 256, 256, 0, st>>>(indptr, n_rows + 1, 0);
+        LGCN_CHECK_LAUNCH("fill_i32_kernel");
+        cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), st);
+        return 0;
+    }
+    u64* kA = nullptr;
+    const int bits = a.cb + bits_for(n_rows > 1 ? n_rows - 1 : 1);
+    if (int rc = sort_and_assemble(a, L, w, n_keys, bits, &kA, st)) return rc;
+    values_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(a, n_keys);
     LGCN_CHECK_LAUNCH("values_kernel");
     return 0;
 }

@@ -19,21 +19,38 @@ from .dataloader import Loader
 from .model import LightGCN
 
 
-def save_checkpoint(path, epoch, model, bpr, best):
+def make_scheduler(bpr, cfg):
+    """The reference's optional MultiStepLR on bpr.opt (code/main.py:38-44); the fused step re-reads
+    param_groups[0]['lr'] every step, so stepping the scheduler is all that is needed."""
+    if not cfg.get('use_scheduler', False):
+        return None
+    milestones = cfg.get('sched_milestones', [120, 240, 360, 480])
+    if isinstance(milestones, str):
+        import ast
+        milestones = ast.literal_eval(milestones)
+    return torch.optim.lr_scheduler.MultiStepLR(bpr.opt, milestones=[int(m) for m in milestones],
+                                                gamma=float(cfg.get('sched_gamma', 0.5)))
+
+
+def save_checkpoint(path, epoch, model, bpr, best, scheduler=None):
     os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
     tmp = path + '.tmp'
     torch.save({'epoch': epoch, 'model_state': model.state_dict(), 'optimizer_state': bpr.opt.state_dict(),
-                'scheduler_state': None, 'best_metric': best}, tmp)
+                'scheduler_state': scheduler.state_dict() if scheduler is not None else None,
+                'best_metric': float(best) if best is not None and best >= 0 else None}, tmp)   # code/main.py:58-64
     os.replace(tmp, path)                               # atomic, like code/main.py:65-67
 
 
-def load_checkpoint(path, model, bpr):
+def load_checkpoint(path, model, bpr, scheduler=None):
     ck = torch.load(path, map_location='cpu', weights_only=False)
-    if 'model_state' in ck:                             # new schema
+    if isinstance(ck, dict) and 'model_state' in ck:    # new schema
         model.load_state_dict(ck['model_state'], strict=True)
         if ck.get('optimizer_state') is not None:
             bpr.opt.load_state_dict(ck['optimizer_state'])
-        return int(ck.get('epoch', 0)), ck.get('best_metric', -1.0)
+        if scheduler is not None and ck.get('scheduler_state') is not None:
+            scheduler.load_state_dict(ck['scheduler_state'])
+        best = ck.get('best_metric')                    # the reference stores None until a best exists (code/main.py:63)
+        return int(ck.get('epoch', 0)), (-1.0 if best is None else float(best))
     model.load_state_dict(ck, strict=True)              # legacy raw state_dict (code/main.py:80-86)
     return 0, -1.0
 
@@ -56,22 +73,25 @@ def main(argv=None):
     utils.sampler_seed(world.seed)
     model = LightGCN(cfg, ds)
     bpr = utils.BPRLoss(model, cfg)
+    scheduler = make_scheduler(bpr, cfg)
     start, best = 0, -1.0
     last = os.path.join(world.PATH, 'last.pth.tar')
     if known.resume:
-        start, best = load_checkpoint(known.resume, model, bpr)
+        start, best = load_checkpoint(known.resume, model, bpr, scheduler)
     for epoch in range(start + 1, world.TRAIN_epochs + 1):
         t0 = time.time()
         if (epoch - 1) % known.eval_every == 0:
             res = Procedure.Test(ds, model, epoch)
             if float(res['ndcg'][0]) > best:
                 best = float(res['ndcg'][0])
-                save_checkpoint(os.path.join(world.PATH, f'best-epoch{epoch}.pth.tar'), epoch, model, bpr, best)
+                save_checkpoint(os.path.join(world.PATH, f'best-epoch{epoch}.pth.tar'), epoch, model, bpr, best, scheduler)
         info = Procedure.BPR_train_original(ds, model, bpr, epoch)
+        if scheduler is not None:
+            scheduler.step()                            # per epoch, code/main.py:222-223
         torch.cuda.synchronize()
         print(f'EPOCH[{epoch}/{world.TRAIN_epochs}] {info} | {time.time() - t0:.3f}s')
         if epoch % a.save_every == 0 or epoch == world.TRAIN_epochs:
-            save_checkpoint(last, epoch, model, bpr, best)
+            save_checkpoint(last, epoch, model, bpr, best, scheduler)
     return model
 
 

@@ -64,6 +64,27 @@ int lgcn_csr_build(const int64_t* train_user, const int64_t* train_item, int64_t
                    int64_t* nnz_out, int32_t* status_out /* int32[1]: !=0 -> id out of range */,
                    void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 
+/* Row-block build for the multi-GPU row partition ("a CSR block per rank"): every rank assembles ONLY the
+ * rows [row_begin,row_end) of the same normalised adjacency, from an edge stream it may see in chunks.
+ *   1. lgcn_degree_accumulate over every chunk: deg_counts int32[N] += weighted degree of every node (zero it first);
+ *      lgcn_degree_finalize -> deg/dinv float32[N] exactly as lgcn_csr_build computes them.
+ *   2. lgcn_csr_rows_emit over every chunk: both directions of each edge whose row is owned are appended as packed keys
+ *      inside `workspace` at *cursor_dev (uint64[1], zero it first); n_keys_cap = sum of deg_counts over the owned rows.
+ *   3. lgcn_csr_rows_finish(n_keys = *cursor_dev read back by the host): sort, merge duplicates, write the block's
+ *      indptr int32[rows+1] (LOCAL offsets), indices (GLOBAL column ids), vals; nnz_out int64[1].
+ * The block equals rows [row_begin,row_end) of lgcn_csr_build's output bit for bit.
+ * status_out: 1 = id out of range, 2 = more keys than n_keys_cap. */
+int lgcn_degree_accumulate(const int64_t* train_user, const int64_t* train_item, int64_t E, int32_t n_users, int32_t m_items,
+                           int32_t* deg_counts, int32_t* status_out, lgcn_stream_t stream);
+int lgcn_degree_finalize(const int32_t* deg_counts, int32_t n_nodes, float* deg, float* dinv, lgcn_stream_t stream);
+size_t lgcn_csr_rows_workspace_bytes(int64_t n_keys_cap, int32_t n_rows_local);
+int lgcn_csr_rows_emit(const int64_t* train_user, const int64_t* train_item, int64_t E, int32_t n_users, int32_t m_items,
+                       int32_t row_begin, int32_t row_end, int64_t n_keys_cap, uint64_t* cursor_dev, int32_t* status_out,
+                       void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+int lgcn_csr_rows_finish(int64_t n_keys, int64_t n_keys_cap, int32_t n_users, int32_t m_items, int32_t row_begin, int32_t row_end,
+                         const float* dinv, int32_t* indptr, int32_t* indices, float* vals, int64_t* nnz_out,
+                         void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+
 /* Row-major sorted COO (torch coalesced layout, code/dataloader.py:183-190,244) -> int32 CSR.
  * rows/cols int64[nnz] sorted by (row,col); writes indptr int32[n_rows+1] and indices int32[nnz]. */
 int lgcn_coo_to_csr(const int64_t* rows, const int64_t* cols, int64_t nnz, int32_t n_rows,
@@ -115,6 +136,18 @@ typedef struct {
     void* y[LGCN_MAX_PEERS];      /* NULL entries are skipped by the Adam variant when Y is not written */
     void* p[LGCN_MAX_PEERS];      /* Adam variant only */
 } lgcn_spmm_peers_t;
+
+/* Device-side rendezvous of the ranks of one NVSwitch box (replaces a 4-byte NCCL all-reduce per exchanged layer, so the
+ * whole row-partitioned step is capturable in ONE CUDA graph and has no collective launch on its path).
+ * flags_local uint32[world] lives on this GPU; peer_flags_host[p] is rank p's flags array mapped into this process
+ * (symmetric memory / CUDA IPC; entry `rank` = flags_local).  The kernel (one CTA, one thread per rank) does
+ * fence.sys, stores the new epoch into slot `rank` of every rank's array (st.release.sys) and spins (ld.acquire.sys)
+ * until all `world` local slots have reached it: every store any rank issued BEFORE its barrier — K1's peer / multimem
+ * row stores included — is visible to the kernels enqueued after it.  epoch_dev uint32[1] counts the barriers of this
+ * rank (device-resident, so graph replays keep counting); all ranks must enqueue the same sequence of barriers.
+ * A rank that waits longer than timeout_ms sets err_dev[0] = 1 + the rank it waited for and gives up (no hang). */
+int lgcn_rank_barrier(uint32_t* flags_local, void* const* peer_flags_host, int32_t rank, int32_t world,
+                      uint32_t* epoch_dev, int32_t* err_dev, int32_t timeout_ms, lgcn_stream_t stream);
 
 /* counts_out int32[4] = {n_long, n_segs, longest item, -} (device).  A row is cut into at most 2048 segments. */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,

@@ -325,3 +325,63 @@ def test_model_variants_match_reference(lg, tmp_path, kind):
     res = lg.Procedure.Test(ds, m, 0)
     for name in ('precision', 'recall', 'ndcg'):
         assert np.allclose(res[name], g[name], rtol=0, atol=1e-4)
+
+
+def _train_epochs(lg, ds, cfg, epochs, tmp_path):
+    lg.utils.set_seed(2020)
+    lg.utils.sampler_seed(2020)
+    m = lg.LightGCN(cfg, ds)
+    bpr = lg.utils.BPRLoss(m, cfg)
+    infos = [lg.Procedure.BPR_train_original(ds, m, bpr, e) for e in range(1, epochs + 1)]
+    res = lg.Procedure.Test(ds, m, epochs)
+    return m, np.array([float(s[4:s.index('-')]) for s in infos]), res
+
+
+@pytest.mark.parametrize('deterministic', [True, False])
+def test_fixed_epochs_match_the_reference_procedure(lg, tmp_path, deterministic):
+    """north_star: "Recall@20 and NDCG@20 must match to within 1e-4 after a fixed number of epochs".  Golden =
+    the REAL reference's set_seed(2020) -> LightGCN -> 20 x Procedure.BPR_train_original (its own C++ sampler seeded
+    2020, its numpy shuffle) -> Procedure.Test on the tiny dataset (oracle/gen_epochs_golden.py;
+    code/Procedure.py:28-83,127-206, code/utils.py:38-64).  Here: the same calls on this package."""
+    g, t = load_golden('tiny_epochs'), load_golden('tiny')
+    lg.world.configure(checkpoint_dir=str(tmp_path), bpr_batch_size=int(g['batch']), topks=[20])
+    try:
+        cfg = dict(lg.world.config)
+        cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), decay=float(g['decay']), lr=float(g['lr']),
+                   deterministic=deterministic)
+        ds = lg.InteractionDataset(int(t['n_users']), int(t['m_items']), t['train_user'], t['train_item'],
+                                   t['test_user'], t['test_item'], config=cfg)
+        m, losses, res = _train_epochs(lg, ds, cfg, int(g['epochs']), tmp_path)
+        assert np.allclose(losses, g['epoch_loss_3dp'], atol=1.01e-3)
+        assert rel_err(params(m), g['params']) < 1e-3
+        assert abs(float(res['recall'][0]) - float(g['recall'][0])) <= 1e-4
+        assert abs(float(res['ndcg'][0]) - float(g['ndcg'][0])) <= 1e-4
+        assert abs(float(res['precision'][0]) - float(g['precision'][0])) <= 1e-4
+    finally:
+        lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048)
+
+
+def test_gowalla_one_epoch_matches_the_reference_procedure(lg, gowalla, tmp_path):
+    """The same on the reference's bundled gowalla data: ONE full epoch (395 steps of 2048 triples from the reference's
+    sampler stream) + full-ranking Test, against what the real reference produced on the CPU
+    (tests/golden/gowalla_epoch.npz, oracle/gen_epochs_golden.py --case gowalla_epoch)."""
+    g = load_golden('gowalla_epoch')
+    nu, ni = int(gowalla['n_users']), int(gowalla['m_items'])
+    tu = np.repeat(np.arange(nu), np.diff(gowalla['train_indptr'])).astype(np.int64)
+    ti = gowalla['train_items'].astype(np.int64)
+    su = np.repeat(gowalla['test_users'].astype(np.int64), np.diff(gowalla['test_indptr']))
+    si = gowalla['test_items'].astype(np.int64)
+    lg.world.configure(checkpoint_dir=str(tmp_path), bpr_batch_size=int(g['batch']), topks=[20])
+    try:
+        cfg = dict(lg.world.config)
+        cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), decay=float(g['decay']), lr=float(g['lr']), deterministic=True)
+        ds = lg.InteractionDataset(nu, ni, tu, ti, su, si, config=cfg, name='gowalla')
+        m, losses, res = _train_epochs(lg, ds, cfg, int(g['epochs']), tmp_path)
+        assert np.allclose(losses, g['epoch_loss_3dp'], atol=1.01e-3)
+        P = params(m)
+        assert rel_err(P[:256], g['params_head']) < 1e-3
+        assert rel_err(np.linalg.norm(P[::97], axis=1), g['params_row_norms_sample']) < 1e-4
+        for k in ('recall', 'ndcg', 'precision'):
+            assert abs(float(res[k][0]) - float(g[k][0])) <= 1e-4, (k, res[k], g[k])
+    finally:
+        lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048)

@@ -21,6 +21,43 @@ def test_library_exports_every_declared_symbol():
     assert lib.lgcn_abi_version() == 1
 
 
+def _header_prototypes():
+    """{name: [parameter declarations]} of every function prototype in include/lgcn_b200.h."""
+    header = open(os.path.join(ROOT, 'include', 'lgcn_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    header = re.sub(r'typedef\s+struct\s*\{.*?\}\s*\w+\s*;', '', header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(lgcn_[a-z0-9_]+)\s*\(([^()]*)\)\s*;', header):
+        params = [p.strip() for p in m.group(2).split(',')]
+        if params == ['void'] or params == ['']:
+            params = []
+        protos[m.group(1)] = params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_arity_and_kinds():
+    """Every export's ctypes argtypes list has exactly the header's parameter count, and pointer / integer /
+    floating kinds agree position by position (a missing argtype lets ctypes pass a Python int as a 32-bit C int)."""
+    import ctypes
+    import lgcn_b200 as lg
+    protos = _header_prototypes()
+    assert set(protos) == set(lg._lib.EXPORTED_SYMBOLS)
+    lg._lib.load()
+    for name, params in protos.items():
+        _, argtypes = lg._lib._SIGNATURES[name]
+        assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters, _lib.py declares {len(argtypes)}"
+        for i, (decl, at) in enumerate(zip(params, argtypes)):
+            is_ptr_decl = '*' in decl or 'lgcn_stream_t' in decl
+            is_ptr_ct = at in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(at, 'contents')
+            assert is_ptr_decl == is_ptr_ct, f"{name} arg {i}: '{decl}' vs {at}"
+            if not is_ptr_decl:
+                is_float_decl = bool(re.match(r'(float|double)\b', decl))
+                assert is_float_decl == (at in (ctypes.c_float, ctypes.c_double)), f"{name} arg {i}: '{decl}' vs {at}"
+                if not is_float_decl:
+                    want64 = bool(re.match(r'(int64_t|uint64_t|size_t)\b', decl))
+                    assert want64 == (ctypes.sizeof(at) == 8), f"{name} arg {i}: '{decl}' vs {at}"
+
+
 def test_host_side_queries_without_gpu():
     import lgcn_b200 as lg
     lib = lg._lib.load()

@@ -150,3 +150,51 @@ def test_gowalla_step0_kat(gowalla):
     assert abs(hits_p / n - float(gowalla['kat_precision'])) < 2e-9
     assert abs(hits_r / n - float(gowalla['kat_recall'])) < 2e-9
     assert abs(ndcg / n - float(gowalla['kat_ndcg'])) < 2e-7      # two author runs differ in the 4th digit
+
+
+def _replay_epochs_with_port(g, train_user, train_item, test_user, test_item, nu, ni, epochs, B):
+    """Replays the reference's epoch loop (code/Procedure.py:28-83) with oracle/ref_port on the CPU: the library's C
+    sampler (bit-identical to sources/sampling.cpp, tests/test_host.py) seeded 2020, numpy shuffle, minibatch."""
+    import torch
+    import lgcn_b200 as lg
+    from oracle import ref_port
+    ds = lg.InteractionDataset(nu, ni, train_user, train_item, test_user, test_item, config=dict(lg.world.config))
+    graph, _, _ = ref_port.build_graph(ds.trainUser, ds.trainItem, nu, ni)
+    lg.utils.set_seed(2020)
+    lg.utils.sampler_seed(2020)
+    m = ref_port.RefLightGCN(nu, ni, int(g['d']), int(g['L']), graph)
+    bpr = ref_port.RefBPRLoss(m, float(g['decay']), float(g['lr']))
+    losses, first_S = [], None
+    for _ in range(epochs):
+        S = lg.utils.UniformSample_original(ds)
+        if first_S is None:
+            first_S = S.copy()
+        u, p, n = (torch.from_numpy(S[:, j].astype(np.int64)) for j in range(3))
+        u, p, n = lg.utils.shuffle(u, p, n)
+        tot = 0.0
+        for bu, bp, bn in lg.utils.minibatch(u, p, n, batch_size=B):
+            tot += bpr.stageOne(bu, bp, bn)
+        losses.append(tot / (len(u) // B + 1))
+    return ds, m, np.array(losses), first_S
+
+
+def test_fixed_epochs_port_reproduces_the_reference_procedure():
+    """north_star: Recall@20 / NDCG@20 within 1e-4 after a fixed number of epochs.  tests/golden/tiny_epochs.npz holds
+    what the REAL reference's BPR_train_original x 20 + Test produced (oracle/gen_epochs_golden.py); the CPU port with
+    the library's sampler/shuffle/minibatch glue must land on the same triples, losses, parameters and metrics."""
+    import torch
+    from conftest import load_golden
+    from oracle import ref_port
+    torch.set_num_threads(1)
+    g, t = load_golden('tiny_epochs'), load_golden('tiny')
+    E, B = int(g['epochs']), int(g['batch'])
+    ds, m, losses, first_S = _replay_epochs_with_port(g, t['train_user'], t['train_item'], t['test_user'], t['test_item'],
+                                                      int(t['n_users']), int(t['m_items']), E, B)
+    assert np.array_equal(first_S[:64], g['first_epoch_triples_head'])
+    assert np.array_equal(first_S.astype(np.int64).sum(axis=0), g['first_epoch_triples_sum'])
+    assert np.allclose(np.round(losses, 3), g['epoch_loss_3dp'], atol=1.01e-3)
+    P = torch.cat([m.embedding_user.weight, m.embedding_item.weight]).detach().numpy()
+    assert rel_err(P, g['params']) < 1e-6
+    res, _ = ref_port.ref_test(m, ds.testDict, ds.allPos, [20])
+    for k in ('precision', 'recall', 'ndcg'):
+        assert abs(float(res[k][0]) - float(g[k][0])) < 1e-9, (k, res[k], g[k])
