@@ -39,14 +39,39 @@ def _append_csv(name, header, row):
         csv.writer(f).writerow(row)
 
 
+def _dist_info(Recmodel):
+    """(mode, rank, world, group) of the model's engine; (None, 0, 1, None) for a single GPU or a foreign model."""
+    eng = getattr(Recmodel, '_engine', None)
+    if eng is None or eng.dist_mode is None:
+        return None, 0, 1, None
+    return eng.dist_mode, eng.rank, eng.world, eng.group
+
+
+def _assert_same_on_every_rank(t, group, what):
+    """The row partition replicates the batch: every rank must feed the same triples (same sampler and shuffle seeds)."""
+    import torch.distributed as dist
+    h = (t.to(torch.int64) * torch.arange(1, t.numel() + 1, dtype=torch.int64, device=t.device).view(t.shape)).sum().view(1)
+    lo, hi = h.clone(), h.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group); dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if int(lo.item()) != int(hi.item()):
+        raise RuntimeError(f"{what} differ between ranks: seed the sampler and numpy identically on every rank (dist_mode='rowpart')")
+
+
 def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=None):
     Recmodel = recommend_model
     Recmodel.train()
     bpr = loss_class
     bs = world.config['bpr_batch_size']
+    mode, rank, nranks, group = _dist_info(Recmodel)
+    if mode in ('dp', 'dp_idx'):
+        raise NotImplementedError("BPR_train_original drives one GPU or the row partition (dist_mode='rowpart'); the "
+                                  "replicated modes 'dp'/'dp_idx' are driven per rank through Engine.step")
     if world.config.get('device_sampler', False) and getattr(bpr, 'fused', False):
         # K5: sample + shuffle on the device, straight into the layout the step reads (no host phase, no H2D)
         eng = Recmodel._engine
+        if Recmodel._csr is None:
+            raise NotImplementedError("the device sampler reads the user rows of the whole adjacency; the memory-partitioned "
+                                      "row partition keeps no such copy — use the (bit-exact) host sampler")
         with timer(name="Sample"):
             S_dev = ops.sample_bpr(Recmodel._csr, dataset.n_users, dataset.m_items, dataset.trainDataSize,
                                    world.seed, epoch)
@@ -59,7 +84,8 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
             eng.epoch_step()
         total_batch = S_dev.shape[1] // bs + 1
         aver_loss = float(eng.loss_to_host()[3]) / total_batch
-        _append_csv('train_epoch_metrics.csv', ['epoch', 'loss'], [epoch, aver_loss])
+        if rank == 0:
+            _append_csv('train_epoch_metrics.csv', ['epoch', 'loss'], [epoch, aver_loss])
         time_info = timer.dict()
         timer.zero()
         return f"loss{aver_loss:.3f}-{time_info}"
@@ -75,13 +101,16 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
     total_batch = n // bs + 1
     if getattr(bpr, 'fused', False):
         eng = Recmodel._engine
-        if eng.dist_mode is not None:
-            raise NotImplementedError("BPR_train_original drives one GPU; use Engine.step per rank for dist_mode")
         if eng.B_cap != bs:
             eng._alloc_batch(bs)
         eng.set_lr(bpr.opt.param_groups[0]['lr'])
         eng.decay = float(bpr.weight_decay)
-        steps = eng.begin_epoch(S_t.to(world.device))
+        S_dev = S_t.to(world.device)
+        if mode == 'rowpart' and nranks > 1:
+            # every rank replays the SAME epoch (the batch is replicated, the rows of A are what is split); the loss and
+            # the returned string are identical on every rank
+            _assert_same_on_every_rank(S_dev, group, "the epoch's sampled triples")
+        steps = eng.begin_epoch(S_dev)
         for batch_i in range(steps):
             eng.epoch_step()
             if world.tensorboard and w is not None:
@@ -96,7 +125,8 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
             if world.tensorboard and w is not None:
                 w.add_scalar('BPRLoss/BPR', cri, epoch * total_batch + batch_i)
     aver_loss = aver_loss / total_batch          # code/Procedure.py:57,68 (keeps the +1 quirk)
-    _append_csv('train_epoch_metrics.csv', ['epoch', 'loss'], [epoch, aver_loss])
+    if rank == 0:
+        _append_csv('train_epoch_metrics.csv', ['epoch', 'loss'], [epoch, aver_loss])
     time_info = timer.dict()
     timer.zero()
     return f"loss{aver_loss:.3f}-{time_info}"
@@ -121,10 +151,29 @@ def test_one_batch(X):
 
 
 def rank_all(dataset, Recmodel, k, user_tile=8192):
-    """Top-k item ids for every user of testDict (key order) -> int64 device tensor [n_test_users, k]."""
+    """Top-k item ids for every user of testDict (key order) -> int64 device tensor [n_test_users, k].
+    Multi-GPU: the users are sharded over the ranks in contiguous blocks, the item table is replicated (it
+    is the exchanged `out`), every rank ranks its block and the blocks are all-gathered — the result is the same tensor
+    on every rank and the same bits as the single-GPU call (each row is ranked by the same kernel on the same data)."""
     users_dev, _, _ = dataset.test_csr()
+    mode, rank, nranks, group = _dist_info(Recmodel)
+    n = users_dev.numel()
+    if nranks > 1:
+        import torch.distributed as dist
+        from .engine import shard_batch
+        Recmodel.computer()                              # collective (exchanged layers): every rank, before the shards diverge
+        per = (n + nranks - 1) // nranks
+        lo_r, hi_r = shard_batch(n, rank, nranks)
+        mine = torch.zeros((per, k), dtype=torch.int64, device=users_dev.device)
+        for lo in range(lo_r, hi_r, user_tile):
+            hi = min(hi_r, lo + user_tile)
+            idx, _ = Recmodel.rank_topk(users_dev[lo:hi], k)
+            mine[lo - lo_r:hi - lo_r] = idx
+        allb = torch.empty((nranks, per, k), dtype=torch.int64, device=users_dev.device)
+        dist.all_gather_into_tensor(allb, mine, group=group)
+        return allb.view(nranks * per, k)[:n].contiguous()
     out = []
-    for lo in range(0, users_dev.numel(), user_tile):
+    for lo in range(0, n, user_tile):
         idx, _ = Recmodel.rank_topk(users_dev[lo:lo + user_tile], k)
         out.append(idx)
     return torch.cat(out, dim=0) if len(out) > 1 else out[0]
@@ -160,6 +209,9 @@ def Test(dataset, Recmodel, epoch, w=None, multicore=0):
             results['recall'] = sums[:, 1] / n_users_eval
             results['ndcg'] = sums[:, 2] / n_users_eval
     prec, rec, nd = float(results['precision'][0]), float(results['recall'][0]), float(results['ndcg'][0])
+    rank = _dist_info(Recmodel)[1]
+    if rank != 0:
+        return results
     _append_csv('valid_epoch_metrics.csv', ['epoch', 'precision', 'recall', 'ndcg'], [epoch, prec, rec, nd])
     if world.tensorboard and w is not None:
         w.add_scalars(f'Test/Recall@{world.topks}', {str(world.topks[i]): results['recall'][i] for i in range(len(world.topks))}, epoch)

@@ -203,34 +203,48 @@ topk_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ pa
     }
 }
 
-// thread per row; block partial sums -> double atomics
+// Deterministic metric sums (the same bits for any launch geometry, any number of calls and — because the multi-GPU Test
+// gathers the ranked lists before calling this — any number of ranks): kernel 1 writes each row's 3*nk values to the
+// workspace ([3*nk][Bt], coalesced), kernel 2 adds every column in a fixed order (one CTA per column: thread t adds
+// rows t, t+T, ... then a fixed shared-memory tree).
 __global__ void __launch_bounds__(256)
-rank_metrics_kernel(const long long* __restrict__ topk, int Bt, int k_max, const int* __restrict__ t_indptr,
-                    const int* __restrict__ t_indices, const int* __restrict__ ks, int nk, double* __restrict__ sums) {
-    extern __shared__ double sh[];                     // [3*nk]
-    for (int i = threadIdx.x; i < 3 * nk; i += blockDim.x) sh[i] = 0.0;
-    __syncthreads();
+rank_metrics_rows_kernel(const long long* __restrict__ topk, int Bt, int k_max, const int* __restrict__ t_indptr,
+                         const int* __restrict__ t_indices, const int* __restrict__ ks, int nk, double* __restrict__ rows) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < Bt) {
-        const int lo = t_indptr[b], hi = t_indptr[b + 1], ngt = hi - lo;
+    if (b >= Bt) return;
+    const int lo = t_indptr[b], hi = t_indptr[b + 1], ngt = hi - lo;
+    for (int m = 0; m < nk; ++m) {
+        double p = 0.0, r = 0.0, nd = 0.0;
         if (ngt > 0) {
-            for (int m = 0; m < nk; ++m) {
-                const int k = ks[m] < k_max ? ks[m] : k_max;
-                int hits = 0; double dcg = 0.0, idcg = 0.0;
-                for (int q = 0; q < k; ++q) {
-                    const double disc = 1.0 / log2((double)(q + 2));
-                    if (row_has(t_indices, lo, hi, (int)topk[(size_t)b * k_max + q])) { ++hits; dcg += disc; }
-                    if (q < ngt) idcg += disc;
-                }
-                if (idcg == 0.0) idcg = 1.0;
-                atomicAdd(&sh[3 * m + 0], (double)hits / (double)ks[m]);
-                atomicAdd(&sh[3 * m + 1], (double)hits / (double)ngt);
-                atomicAdd(&sh[3 * m + 2], dcg / idcg);
+            const int k = ks[m] < k_max ? ks[m] : k_max;
+            int hits = 0; double dcg = 0.0, idcg = 0.0;
+            for (int q = 0; q < k; ++q) {
+                const double disc = 1.0 / log2((double)(q + 2));
+                if (row_has(t_indices, lo, hi, (int)topk[(size_t)b * k_max + q])) { ++hits; dcg += disc; }
+                if (q < ngt) idcg += disc;
             }
+            if (idcg == 0.0) idcg = 1.0;
+            p = (double)hits / (double)ks[m]; r = (double)hits / (double)ngt; nd = dcg / idcg;
         }
+        rows[(size_t)(3 * m + 0) * Bt + b] = p;
+        rows[(size_t)(3 * m + 1) * Bt + b] = r;
+        rows[(size_t)(3 * m + 2) * Bt + b] = nd;
     }
+}
+
+__global__ void __launch_bounds__(1024)
+rank_metrics_sum_kernel(const double* __restrict__ rows, int Bt, double* __restrict__ sums) {
+    __shared__ double sh[1024];
+    const double* col = rows + (size_t)blockIdx.x * Bt;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < Bt; b += 1024) acc += col[b];
+    sh[threadIdx.x] = acc;
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * nk; i += blockDim.x) if (sh[i] != 0.0) atomicAdd(sums + i, sh[i]);
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] += sh[0];
 }
 
 static int pick_splits(int Bt, int m_items) {
@@ -322,13 +336,24 @@ extern "C" int lgcn_score_dense(const float* users_emb, const float* items_emb, 
     return 0;
 }
 
+extern "C" size_t lgcn_rank_metrics_workspace_bytes(int32_t Bt, int32_t nk) {
+    if (Bt < 0 || nk < 0) return 0;
+    return sizeof(double) * 3 * (size_t)nk * (size_t)(Bt > 0 ? Bt : 1);
+}
+
 extern "C" int lgcn_rank_metrics(const int64_t* topk_idx, int32_t Bt, int32_t k_max,
                                  const int32_t* test_indptr, const int32_t* test_indices,
-                                 const int32_t* ks, int32_t nk, double* sums_out, lgcn_stream_t stream) {
+                                 const int32_t* ks, int32_t nk, double* sums_out,
+                                 void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(topk_idx && test_indptr && test_indices && ks && sums_out, "rank_metrics: null argument");
     LGCN_CHECK_ARG(Bt > 0 && k_max > 0 && nk > 0 && nk <= 16, "rank_metrics: Bt=%d k_max=%d nk=%d", Bt, k_max, nk);
-    rank_metrics_kernel<<<(Bt + 255) / 256, 256, 3 * nk * sizeof(double), as_stream(stream)>>>(
-        reinterpret_cast<const long long*>(topk_idx), Bt, k_max, test_indptr, test_indices, ks, nk, sums_out);
-    LGCN_CHECK_LAUNCH("rank_metrics_kernel");
+    LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_rank_metrics_workspace_bytes(Bt, nk) && ((uintptr_t)workspace % 8) == 0,
+                   "rank_metrics: workspace too small or misaligned");
+    double* rows = static_cast<double*>(workspace);
+    rank_metrics_rows_kernel<<<(Bt + 255) / 256, 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const long long*>(topk_idx), Bt, k_max, test_indptr, test_indices, ks, nk, rows);
+    LGCN_CHECK_LAUNCH("rank_metrics_rows_kernel");
+    rank_metrics_sum_kernel<<<3 * nk, 1024, 0, as_stream(stream)>>>(rows, Bt, sums_out);
+    LGCN_CHECK_LAUNCH("rank_metrics_sum_kernel");
     return 0;
 }

@@ -155,6 +155,28 @@ class InteractionDataset(BasicDataset):
             self._csr = ops.csr_build(tu, ti, self.n_user, self.m_item, seg_len=self.seg_len)
         return self._csr
 
+    def getRowBlockBuilder(self):
+        """Graph source of the memory-partitioned row partition (dist_mode='rowpart'): an ops.RowBlockBuilder over the
+        train edges; each rank assembles only the rows it owns (K4 on the owned keys)."""
+        if getattr(self, '_builder', None) is None:
+            dev = world.device
+            if dev.type != 'cuda':
+                raise RuntimeError("building the adjacency needs a CUDA device (K4 has no CPU path)")
+
+            def chunks():
+                yield torch.from_numpy(self.trainUser).to(dev), torch.from_numpy(self.trainItem).to(dev)
+            self._builder = ops.RowBlockBuilder(self.n_user, self.m_item, chunks, seg_len=self.seg_len, device=dev)
+        return self._builder
+
+    def train_mask_csr(self):
+        """(indptr int32[n_users+1], items int32[nnz]) on the device: every user's sorted train items (= allPos), the
+        mask of the full-ranking evaluation when no rank holds the whole adjacency."""
+        if getattr(self, '_mask_csr', None) is None:
+            indptr, items = self.allPos_csr()
+            dev = world.device
+            self._mask_csr = (torch.from_numpy(indptr.astype(np.int32)).to(dev), torch.from_numpy(np.ascontiguousarray(items, dtype=np.int32)).to(dev))
+        return self._mask_csr
+
     def getSparseGraph(self):
         """D^-1/2 [[0,R],[R^T,0]] D^-1/2 as a torch sparse tensor on world.device (accepted by
         torch.sparse.mm like the reference's coalesced COO); shares storage with getCSRGraph()."""

@@ -21,11 +21,15 @@ Multi-GPU (one process per GPU, torch.distributed):
                   so every rank scatters the global batch itself (K2 is ~10 us).  Same result, and the
                   compute part stays inside the single-GPU CUDA graph.
   mode 'rowpart'  rows of A partitioned in contiguous nnz-balanced blocks; K2 runs redundantly on the full
-                  batch so no gradient collective is needed; Adam only touches owned rows.  Exchange of every
-                  layer's output block: FUSED into K1 (p2p=True, default on one NVSwitch box) — the ranks map
-                  each other's buffers (CUDA IPC) and K1's epilogue stores each finished row into all peers
-                  over NVLink while the gathers of the following rows are in flight; a 4-byte all-reduce is the
-                  only collective left per layer.  p2p=False falls back to NCCL broadcasts after the kernel.
+                  batch so no gradient collective is needed; Adam only touches owned rows.  Given an
+                  ops.RowBlockBuilder instead of a whole CSRGraph, a rank holds ONLY its CSR block and only its rows of
+                  the Adam moments M, V; replicated per rank: the exchanged tables E0, X_k, out and the (sparse) G.
+                  Exchange of every layer's output block: FUSED into K1 (p2p=True, default on one NVSwitch box) —
+                  K1's epilogue stores each finished row into all peers over NVLink while the gathers of the
+                  following rows are in flight; the layers are ordered by a DEVICE-SIDE flag barrier
+                  (ops.RankBarrier, csrc/exchange.cu), so the step has no collective launch at all and is captured
+                  in one CUDA graph like the single-GPU step.  p2p=False falls back to NCCL broadcasts after the
+                  kernel (eager, any backend — what the gloo tests exercise).
                   multicast=True (default): the exchanged tables live in torch symmetric memory and the epilogue
                   issues ONE NVSwitch multicast store (multimem.st) per 16 bytes instead of world-1 unicast stores.
                   rebalance=2 (default): the block boundaries are moved to equal measured time at start-up —
@@ -150,7 +154,10 @@ class Engine:
                  deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True, row_cost=None, multicast=True, rebalance=2):
         if n_layers > 8:
             raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
-        self.csr = csr
+        self.builder = csr if isinstance(csr, ops.RowBlockBuilder) else None
+        if self.builder is not None and dist_mode != 'rowpart':
+            raise RuntimeError("a RowBlockBuilder is the graph source of dist_mode='rowpart' only")
+        self.csr = None if self.builder is not None else csr
         self.nu, self.ni, self.N, self.d, self.L = n_users, m_items, n_users + m_items, d, n_layers
         self.device = device
         self.decay, self.lr = float(decay), float(lr)
@@ -162,14 +169,16 @@ class Engine:
         if dist_mode is not None:
             import torch.distributed as dist
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.use_graph = bool(use_graph) and dist_mode in (None, 'dp_idx')
+        # fused exchange (K1 stores into the peers + device-side barrier): one NVSwitch box, CUDA only
+        self.p2p = bool(p2p) and dist_mode == 'rowpart' and self.world > 1 and self.world - 1 <= 7 and torch.device(device).type == 'cuda'
+        self.use_graph = bool(use_graph) and (dist_mode in (None, 'dp_idx') or (dist_mode == 'rowpart' and (self.p2p or self.world == 1)))
         if dist_mode == 'dp_idx':
             self.B_cap = self.B_cap * self.world          # the static batch buffers hold the GLOBAL batch
+            self.deterministic = True                     # replicas are never re-synchronised: they must not drift in rounding
         N, L = self.N, self.L
         f32 = dict(dtype=torch.float32, device=device)
         # exchanged tables of the row partition: NVSwitch multicast (symmetric memory) when the box offers it — one
         # multimem store per 16 bytes reaches every replica instead of world-1 unicast stores
-        self.p2p = bool(p2p) and dist_mode == 'rowpart' and self.world > 1 and self.world - 1 <= 7
         self._mc = {}
         exchanged = [None] * (2 + max(L - 1, 0))
         if self.p2p and multicast:
@@ -178,12 +187,9 @@ class Engine:
         self.X = [exchanged[2 + i] if exchanged[2 + i] is not None else torch.zeros((N, d), **f32) for i in range(max(L - 1, 0))]
         self.out = exchanged[1] if exchanged[1] is not None else torch.zeros((N, d), **f32)
         self.G = torch.zeros((N, d), **f32)
-        self.M = torch.zeros((N, d), **f32)
-        self.V = torch.zeros((N, d), **f32)
         self._gradE0 = None
         self._scratch = None
         self.loss_out = torch.zeros(4, **f32)
-        self.scalars = ops.adam_scalars(device, self.lr)
         self._host_step = 0
         self.param_epoch = 0
         # dead-row pruning of the training step (see _enqueue_step): bitmaps over the N nodes
@@ -193,35 +199,73 @@ class Engine:
         # row partition
         self.r0, self.r1 = 0, N
         self.bounds = [0, N]
-        self.local = csr
+        self.local = self.csr
+        self._mv_local = False
         if dist_mode == 'rowpart':
             if row_cost is None:
-                row_cost = d if (p2p and self.world > 1) else 0
-            indptr_cpu = csr.indptr.cpu()
-            self.bounds = balanced_row_bounds(indptr_cpu, self.world, row_cost)
-            self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
-            self.local = csr.rows(self.r0, self.r1)
-            for _ in range(int(rebalance)):                 # equal cost is not equal time: measure, move the boundaries
-                self.bounds = self._rebalance(indptr_cpu, row_cost)
-                self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
-                self.local = csr.rows(self.r0, self.r1)
-        # fused exchange: map the peers' copies of every exchanged buffer
+                row_cost = d if (self.p2p and self.world > 1) else 0
+            cost_cpu = self.builder.cost_prefix if self.builder is not None else self.csr.indptr.cpu()
+            self.bounds = balanced_row_bounds(cost_cpu, self.world, row_cost)
+            self._take_block()
+            for _ in range(int(rebalance) if self.world > 1 else 0):      # equal cost is not equal time: measure, move the boundaries
+                new = self._rebalance(cost_cpu, row_cost)
+                if new != self.bounds:
+                    self.bounds = new
+                    self._take_block()
+            self._mv_local = self.builder is not None
+        rows_mv = (self.r1 - self.r0) if self._mv_local else N
+        self.M = torch.zeros((rows_mv, d), **f32)
+        self.V = torch.zeros((rows_mv, d), **f32)
+        self.scalars = ops.adam_scalars(device, self.lr)
+        # fused exchange: map the peers' copies of every exchanged buffer, and the flags of the device-side barrier
         self._peer = {}
         self._e0_synced = False
+        self._barrier = None
         if self.p2p:
             import torch.distributed as dist
             from . import _lib
+            for p_dev in range(torch.cuda.device_count()):
+                _lib.load().lgcn_enable_peer_access(p_dev)
             if not self._mc:
-                for p_dev in range(torch.cuda.device_count()):
-                    _lib.load().lgcn_enable_peer_access(p_dev)
                 for buf in [self.E0, self.out] + self.X:
                     self._peer[buf.data_ptr()] = map_peer_buffers(buf, group)
-            self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+            self._flags = torch.zeros(64, dtype=torch.int32, device=device)
+            torch.cuda.synchronize()
+            self._barrier = ops.RankBarrier(self._flags, map_peer_buffers(self._flags, group), self.rank, self.world)
             dist.barrier(group)
         # batch staging: [ctl(4 x int32) | users | pos | neg] in one block so that a host batch is one H2D
         self._alloc_batch(self.B_cap)
         self._epoch = None          # (S tensor [3,cap], ctl) for epoch-resident mode
         self._graphs = {}
+
+    def _take_block(self):
+        """(Re)build this rank's row block for the current bounds: its own CSR from the builder (memory-partitioned), or
+        views into the replicated CSR when the caller handed the whole graph."""
+        self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.local = None
+        self.local = self.builder.build(self.r0, self.r1) if self.builder is not None else self.csr.rows(self.r0, self.r1)
+
+    def adam_state_full(self):
+        """Full (N,d) Adam moments on every rank (collective in the memory-partitioned row partition: checkpoints)."""
+        if not self._mv_local:
+            if self.dist_mode == 'rowpart' and self.world > 1:
+                M, V = self.M.clone(), self.V.clone()
+                allgather_rows(M, self.bounds, self.group); allgather_rows(V, self.bounds, self.group)
+                return M, V
+            return self.M, self.V
+        full = []
+        for loc in (self.M, self.V):
+            t = torch.zeros((self.N, self.d), dtype=torch.float32, device=self.device)
+            t[self.r0:self.r1].copy_(loc)
+            allgather_rows(t, self.bounds, self.group)
+            full.append(t)
+        return full[0], full[1]
+
+    def load_adam_state(self, M_full, V_full):
+        if self._mv_local:
+            self.M.copy_(M_full[self.r0:self.r1]); self.V.copy_(V_full[self.r0:self.r1])
+        else:
+            self.M.copy_(M_full); self.V.copy_(V_full)
 
     def _rebalance(self, indptr_cpu, row_cost):
         """One round of time-based re-partitioning: every rank times its local product (same launch the layers use,
@@ -240,7 +284,10 @@ class Engine:
         allt = [torch.zeros_like(mine) for _ in range(self.world)]
         dist.all_gather(allt, mine, group=self.group)
         self.out.zero_()
-        return rebalance_by_time(indptr_cpu, self.bounds, [float(x.item()) for x in allt], row_cost)
+        times = [float(x.item()) for x in allt]
+        if max(times) < 1.15 * min(times):          # already balanced to within the timing noise
+            return list(self.bounds)
+        return rebalance_by_time(indptr_cpu, self.bounds, times, row_cost)
 
     # ------------------------------------------------------------------ batch staging
     def _alloc_batch(self, B_cap):
@@ -298,10 +345,10 @@ class Engine:
         allgather_rows(buf, self.bounds, self.group)
 
     def _rank_barrier(self):
-        """Stream-ordered rendezvous of the ranks (4-byte all-reduce): every rank's stores into my buffers are complete
-        and visible once the kernels enqueued after it start.  Does not block the host."""
-        import torch.distributed as dist
-        dist.all_reduce(self._flag, group=self.group)
+        """Stream-ordered rendezvous of the ranks ON THE DEVICE (flag barrier in peer-mapped memory, csrc/exchange.cu):
+        every rank's stores into my buffers are complete and visible once the kernels enqueued after it start.  No
+        collective launch, capturable in the step's CUDA graph; does not block the host."""
+        self._barrier()
 
     def _layer(self, X, Y, alpha, beta, zs, row_mask=None, col_mask=None):
         r0, r1 = self.r0, self.r1
@@ -327,8 +374,11 @@ class Engine:
         masks=(m0, m1): only the rows a training step reads are produced — `out` on the batch rows m0, X_{L-1}
         on m0 + neighbours m1; earlier layers are complete.  The skipped rows are simply not written."""
         L, s = self.L, 1.0 / (self.L + 1)
-        if self.dist_mode == 'rowpart' and not (self.p2p and self._e0_synced):
+        if self.dist_mode == 'rowpart' and self.world > 1 and not (self.p2p and self._e0_synced):
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("internal: parameter rows must be synchronised before the step is captured")
             self._allgather_rows(self.E0)       # owners publish their updated parameter rows
+            self._e0_synced = self.p2p          # from here on the Adam epilogue publishes them itself
         if L == 0:
             self.out.copy_(self.E0)
             return self.out
@@ -417,8 +467,9 @@ class Engine:
             ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
                             self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
         r0, r1 = self.r0, self.r1
+        Mo, Vo = (self.M, self.V) if self._mv_local else (self.M[r0:r1], self.V[r0:r1])
         if self.L == 0:
-            ops.adam(self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.G[r0:r1], self.scalars)
+            ops.adam(self.E0[r0:r1], Mo, Vo, self.G[r0:r1], self.scalars)
         else:
             g = self.local if self.dist_mode == 'rowpart' else self.csr
 
@@ -426,13 +477,12 @@ class Engine:
             mc_e0 = self._mc.get(self.E0.data_ptr(), 0) if self.p2p else 0
 
             def last(X, alpha, beta, zs, col_mask):
-                ops.spmm_adam(g, X, self.E0[r0:r1], self.M[r0:r1], self.V[r0:r1], self.scalars, alpha, beta,
+                ops.spmm_adam(g, X, self.E0[r0:r1], Mo, Vo, self.scalars, alpha, beta,
                               [z[r0:r1] for z in zs], col_mask=col_mask,
                               peer_p=None if (peers_e0 is None or mc_e0) else [peers_e0[p][r0:r1] for p in range(self.world) if p != self.rank],
                               mc_p=(mc_e0 + r0 * self.d * 4) if mc_e0 else 0)
                 if peers_e0 is not None or mc_e0:        # the updated parameter rows are already in every replica
                     self._rank_barrier()
-                    self._e0_synced = True
             self._backward_chain(self.G, last)
         if self.dist_mode == 'dp':
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
@@ -472,9 +522,25 @@ class Engine:
             users, pos, neg = self._gather_indices(users, pos, neg)
             B_global = 0
         self._stage_batch(users, pos, neg, B_global)
+        self._sync_params_across_ranks()
         self._run('direct', self.bu, self.bp, self.bn, self.ctl)
         self._host_step += 1
         self.param_epoch += 1
+
+    def _sync_params_across_ranks(self):
+        """Row partition with the fused exchange: after the parameters were set from outside (init, load_state_dict) every
+        rank's replica of E0 must be the same before the (captured) step sequence starts; afterwards the Adam epilogue
+        keeps the replicas in step by itself."""
+        if self.dist_mode == 'rowpart' and self.p2p and not self._e0_synced:
+            self._allgather_rows(self.E0)
+            self._e0_synced = True
+
+    def sync_params_for_read(self):
+        """Make this rank's replica of the parameter table complete (collective; no-op when the fused exchange already
+        keeps the replicas in step or when nothing is partitioned)."""
+        if self.dist_mode == 'rowpart' and self.world > 1 and not (self.p2p and self._e0_synced):
+            self._allgather_rows(self.E0)
+            self._e0_synced = self.p2p
 
     def _gather_indices(self, users, pos, neg):
         """dp_idx: all-gather every rank's (users,pos,neg) shard -> the global batch on every rank."""
@@ -520,6 +586,7 @@ class Engine:
 
     def epoch_step(self):
         S, ctl = self._epoch
+        self._sync_params_across_ranks()
         ops.batch_advance(ctl, self.B_cap)
         self._run('epoch', S[0], S[1], S[2], ctl)
         self._host_step += 1

@@ -148,12 +148,21 @@ class LightGCN(nn.Module):
         nn.init.normal_(self.embedding_user.weight, std=0.1)
         nn.init.normal_(self.embedding_item.weight, std=0.1)
 
-        self.Graph = dataset.getSparseGraph()
-        self._csr = as_csr_graph(dataset, self.Graph, int(config.get('spmm_seg_len', ops.DEFAULT_SEG_LEN)))
         N = self.n_users + self.m_items
-        if self._csr.n_rows != N or self._csr.n_cols != N:
-            raise RuntimeError(f"adjacency is {self._csr.n_rows}x{self._csr.n_cols}, expected {N}x{N}")
-        self._engine = Engine(self._csr, self.n_users, self.m_items, self.latent_dim, self.n_layers, self.device,
+        if (config.get('dist_mode') == 'rowpart' and config.get('rowpart_partition_memory', True)
+                and hasattr(dataset, 'getRowBlockBuilder')):
+            # row partition: this rank assembles and keeps ONLY its row block of the adjacency; the
+            # whole-graph tensor the reference hands to torch.sparse.mm does not exist on any rank
+            self.Graph = None
+            self._csr = None
+            graph_src = dataset.getRowBlockBuilder()
+        else:
+            self.Graph = dataset.getSparseGraph()
+            self._csr = as_csr_graph(dataset, self.Graph, int(config.get('spmm_seg_len', ops.DEFAULT_SEG_LEN)))
+            graph_src = self._csr
+        if graph_src.n_rows != N or graph_src.n_cols != N:
+            raise RuntimeError(f"adjacency is {graph_src.n_rows}x{graph_src.n_cols}, expected {N}x{N}")
+        self._engine = Engine(graph_src, self.n_users, self.m_items, self.latent_dim, self.n_layers, self.device,
                               lr=config.get('lr', 1e-3), decay=config.get('decay', 1e-4),
                               B_cap=config.get('bpr_batch_size', 2048),
                               deterministic=config.get('deterministic', False),
@@ -291,12 +300,21 @@ class LightGCN(nn.Module):
             all_users, all_items = self.computer()
             all_items = self._items_for_scoring(all_items)
             users = users.to(self.device, dtype=torch.int64).contiguous()
-            g = self._csr
-            mi, mx = (g.indptr, g.indices) if mask else (None, None)
+            mi, mx, off = self._train_mask() if mask else (None, None, 0)
             if self.config.get('score_tensor_core', True):
-                idx, val, self.last_rank_redone = ops.score_topk_tc(all_users, all_items, users, k, mi, mx, self.n_users)
+                idx, val, self.last_rank_redone = ops.score_topk_tc(all_users, all_items, users, k, mi, mx, off)
                 return idx, val
-            return ops.score_topk(all_users, all_items, users, k, mi, mx, self.n_users)
+            return ops.score_topk(all_users, all_items, users, k, mi, mx, off)
+
+    def _train_mask(self):
+        """(indptr, indices, column offset) of the train-item mask over the user rows: the user rows of the adjacency
+        when this rank holds them, else the dataset's own user->items CSR (memory-partitioned row partition)."""
+        if self._csr is not None:
+            return self._csr.indptr, self._csr.indices, self.n_users
+        if not hasattr(self.dataset, 'train_mask_csr'):
+            raise RuntimeError("this dataset cannot supply the train-item mask without the whole adjacency")
+        ip, it = self.dataset.train_mask_csr()
+        return ip, it, 0
 
     def getEmbedding(self, users, pos_items, neg_items):
         all_users, all_items = self.computer()

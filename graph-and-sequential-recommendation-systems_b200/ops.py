@@ -138,6 +138,92 @@ def csr_build(train_user, train_item, n_users, m_items, seg_len=DEFAULT_SEG_LEN)
     return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], N, deg=deg, dinv=dinv, seg_len=seg_len)
 
 
+class RowBlockBuilder:
+    """Row blocks of the normalised adjacency straight from an edge stream (multi-GPU row partition):
+    a rank never holds more of the CSR than the rows it owns.  `chunks` is a zero-argument callable returning an
+    iterable of (train_user, train_item) int64 CUDA tensor pairs — the whole edge list in one piece, or pieces that are
+    re-generated on every pass — and is walked once for the degrees and once per build().  Only setup code: a few host
+    syncs (key counts) are fine here."""
+
+    def __init__(self, n_users, m_items, chunks, seg_len=DEFAULT_SEG_LEN, device=None):
+        lib = _lib.load()
+        self.n_users, self.m_items, self.N = int(n_users), int(m_items), int(n_users) + int(m_items)
+        self.chunks, self.seg_len = chunks, int(seg_len)
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.counts = torch.zeros(self.N, dtype=torch.int32, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.n_edges = 0
+        for tu, ti in chunks():
+            _need(tu, torch.int64, "train_user", 1), _need(ti, torch.int64, "train_item", 1)
+            _lib.check(lib.lgcn_degree_accumulate(_p(tu), _p(ti), tu.numel(), self.n_users, self.m_items, _p(self.counts), _p(status), _stream()),
+                       "degree_accumulate")
+            self.n_edges += tu.numel()
+        if int(status.item()) != 0:
+            raise RuntimeError("row-block build: a user or item id is outside [0,n_users) x [0,m_items)")
+        self.deg = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        self.dinv = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        _lib.check(lib.lgcn_degree_finalize(_p(self.counts), self.N, _p(self.deg), _p(self.dinv), _stream()), "degree_finalize")
+        c = self.counts.cpu().to(torch.int64)
+        # cumulative stored entries per row (duplicates counted): what the partition is balanced on — plays the role of indptr
+        self.cost_prefix = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(c, 0)])
+        self.n_rows = self.n_cols = self.N
+
+    def build(self, r0, r1):
+        """CSRGraph of rows [r0, r1): local indptr, GLOBAL column ids, n_cols = N."""
+        lib = _lib.load()
+        r0, r1 = int(r0), int(r1)
+        cap = int(self.cost_prefix[r1] - self.cost_prefix[r0])
+        ws_bytes = lib.lgcn_csr_rows_workspace_bytes(cap, r1 - r0)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=self.device)
+        ws_ptr = c_void_p((ws.data_ptr() + 255) // 256 * 256)
+        cursor = torch.zeros(1, dtype=torch.int64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for tu, ti in self.chunks():
+            _lib.check(lib.lgcn_csr_rows_emit(_p(tu), _p(ti), tu.numel(), self.n_users, self.m_items, r0, r1, cap, _p(cursor), _p(status),
+                                              ws_ptr, ws_bytes, _stream()), "csr_rows_emit")
+        n_keys, st = int(cursor.item()), int(status.item())
+        if st != 0 or n_keys != cap:
+            raise RuntimeError(f"row-block build: edge stream changed between passes (status {st}, {n_keys} keys, expected {cap})")
+        indptr = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=self.device)
+        indices = torch.empty(max(n_keys, 1), dtype=torch.int32, device=self.device)
+        vals = torch.empty(max(n_keys, 1), dtype=torch.float32, device=self.device)
+        nnz = torch.zeros(1, dtype=torch.int64, device=self.device)
+        _lib.check(lib.lgcn_csr_rows_finish(n_keys, cap, self.n_users, self.m_items, r0, r1, _p(self.dinv), _p(indptr), _p(indices), _p(vals),
+                                            _p(nnz), ws_ptr, ws_bytes, _stream()), "csr_rows_finish")
+        nnz_h = int(nnz.item())
+        del ws
+        if nnz_h < int(0.9 * n_keys):           # many duplicates: do not keep the slack alive
+            indices, vals = indices[:nnz_h].clone(), vals[:nnz_h].clone()
+        return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], self.N, seg_len=self.seg_len)
+
+
+class RankBarrier:
+    """Device-side rendezvous of the ranks (lgcn_rank_barrier): flags in peer-mapped memory, no collective launch, capturable
+    in a CUDA graph.  `peer_flags` = every rank's flags tensor as seen from this process (own entry included)."""
+
+    def __init__(self, flags_local, peer_flags, rank, world, timeout_ms=20000):
+        self.flags, self.peers, self.rank, self.world = flags_local, list(peer_flags), int(rank), int(world)
+        self.timeout_ms = int(timeout_ms)
+        dev = flags_local.device
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._arr = (c_void_p * self.world)()
+        for p, t in enumerate(self.peers):
+            self._arr[p] = t.data_ptr()
+        self.count = 0
+
+    def __call__(self):
+        _lib.check(_lib.load().lgcn_rank_barrier(_p(self.flags), self._arr, self.rank, self.world, _p(self.epoch), _p(self.err),
+                                                 self.timeout_ms, _stream()), "rank_barrier")
+        self.count += 1
+
+    def check(self):
+        """Host-side (synchronising) check that no barrier timed out."""
+        e = int(self.err.item())
+        if e:
+            raise RuntimeError(f"rank {self.rank}: device barrier timed out waiting for rank {e - 1}")
+
+
 def coo_to_csr(rows, cols, vals, n_rows, n_cols, seg_len=DEFAULT_SEG_LEN):
     """Row-major-sorted COO (torch coalesced layout) -> CSRGraph."""
     lib = _lib.load()
@@ -382,9 +468,11 @@ def rank_metrics(topk_idx, test_indptr, test_indices, ks):
     Bt, k_max = topk_idx.shape
     ks_t = torch.tensor(list(ks), dtype=torch.int32, device=topk_idx.device)
     sums = torch.zeros(len(ks) * 3, dtype=torch.float64, device=topk_idx.device)
+    ws_bytes = lib.lgcn_rank_metrics_workspace_bytes(Bt, len(ks))
+    ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=topk_idx.device)
     _lib.check(lib.lgcn_rank_metrics(_p(topk_idx), Bt, k_max, _p(_need(test_indptr, torch.int32, "test_indptr", 1)),
                                      _p(_need(test_indices, torch.int32, "test_indices", 1)), _p(ks_t), len(ks),
-                                     _p(sums), _stream()), "rank_metrics")
+                                     _p(sums), _p(ws), ws_bytes, _stream()), "rank_metrics")
     return sums.view(len(ks), 3)
 
 

@@ -3,6 +3,11 @@ every 10th epoch Test + best-NDCG checkpoint, then one BPR epoch, CSV rows, atom
 
     python -m lgcn_b200.train --dataset gowalla --data_path data/gowalla --epochs 50
     python -m lgcn_b200.train --synthetic yelp2018 --epochs 20 --device_sampler
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m lgcn_b200.train --synthetic amazon-book --epochs 20
+
+Under torchrun (WORLD_SIZE > 1) the adjacency is row-partitioned over the ranks (dist_mode='rowpart'): every rank runs the
+same loop on the same sampled triples (same seeds), holds only its block of the CSR and of the Adam moments, evaluates its
+shard of the test users, and rank 0 alone prints and writes checkpoints (the optimizer state is gathered for that).
 
 Checkpoint schema = the reference's (code/main.py:56-67): {'epoch','model_state','optimizer_state','best_metric'} with
 parameter keys embedding_user.weight / embedding_item.weight, so files are interchangeable.
@@ -32,10 +37,15 @@ def make_scheduler(bpr, cfg):
                                                 gamma=float(cfg.get('sched_gamma', 0.5)))
 
 
-def save_checkpoint(path, epoch, model, bpr, best, scheduler=None):
+def save_checkpoint(path, epoch, model, bpr, best, scheduler=None, rank=0):
+    if hasattr(model, '_engine'):
+        model._engine.sync_params_for_read()            # row partition without the fused exchange: owners publish their rows
+    opt_state = bpr.opt.state_dict()                    # collective under the row partition (gathers the moments): every rank
+    if rank != 0:
+        return
     os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
     tmp = path + '.tmp'
-    torch.save({'epoch': epoch, 'model_state': model.state_dict(), 'optimizer_state': bpr.opt.state_dict(),
+    torch.save({'epoch': epoch, 'model_state': model.state_dict(), 'optimizer_state': opt_state,
                 'scheduler_state': scheduler.state_dict() if scheduler is not None else None,
                 'best_metric': float(best) if best is not None and best >= 0 else None}, tmp)   # code/main.py:58-64
     os.replace(tmp, path)                               # atomic, like code/main.py:65-67
@@ -64,6 +74,14 @@ def main(argv=None):
     known, rest = ap.parse_known_args(argv)
     a = world.from_args(rest)
     world.configure(device_sampler=known.device_sampler)
+    nranks, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+    if nranks > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        world.configure(device=f'cuda:{local}', dist_mode='rowpart')
     cfg = world.config
     if known.synthetic:
         ds = synth.make_dataset(known.synthetic, seed=world.seed, config=cfg)
@@ -84,14 +102,15 @@ def main(argv=None):
             res = Procedure.Test(ds, model, epoch)
             if float(res['ndcg'][0]) > best:
                 best = float(res['ndcg'][0])
-                save_checkpoint(os.path.join(world.PATH, f'best-epoch{epoch}.pth.tar'), epoch, model, bpr, best, scheduler)
+                save_checkpoint(os.path.join(world.PATH, f'best-epoch{epoch}.pth.tar'), epoch, model, bpr, best, scheduler, rank)
         info = Procedure.BPR_train_original(ds, model, bpr, epoch)
         if scheduler is not None:
             scheduler.step()                            # per epoch, code/main.py:222-223
         torch.cuda.synchronize()
-        print(f'EPOCH[{epoch}/{world.TRAIN_epochs}] {info} | {time.time() - t0:.3f}s')
+        if rank == 0:
+            print(f'EPOCH[{epoch}/{world.TRAIN_epochs}] {info} | {time.time() - t0:.3f}s')
         if epoch % a.save_every == 0 or epoch == world.TRAIN_epochs:
-            save_checkpoint(last, epoch, model, bpr, best, scheduler)
+            save_checkpoint(last, epoch, model, bpr, best, scheduler, rank)
     return model
 
 

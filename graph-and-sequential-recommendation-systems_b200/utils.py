@@ -24,18 +24,26 @@ class _AdamStateView(optim.Adam):
         self._model = model
         self._bind()
 
-    def _bind(self):
+    def _bind(self, full=None):
         m = self._model
         eng, nu = m._engine, m.n_users
+        # single GPU / replicas: the state tensors ALIAS the engine's buffers.  Row partition: a rank holds only its rows of
+        # M and V, so the aliases are replaced by gathered full tables whenever a state_dict is asked for.
+        sharded = eng.dist_mode == 'rowpart' and eng.world > 1
+        M, V = full if full is not None else ((None, None) if sharded else (eng.M, eng.V))
         for p, sl in ((m.embedding_user.weight, slice(0, nu)), (m.embedding_item.weight, slice(nu, None))):
             st = self.state[p]
             st['step'] = torch.tensor(float(eng._host_step))
-            st['exp_avg'] = eng.M[sl]
-            st['exp_avg_sq'] = eng.V[sl]
+            if M is not None:
+                st['exp_avg'] = M[sl]
+                st['exp_avg_sq'] = V[sl]
 
     def state_dict(self):
+        eng = self._model._engine
+        if eng.dist_mode == 'rowpart' and eng.world > 1:
+            self._bind(full=eng.adam_state_full())          # collective: every rank must call state_dict()
         for st in self.state.values():
-            st['step'] = torch.tensor(float(self._model._engine._host_step))
+            st['step'] = torch.tensor(float(eng._host_step))
         return super().state_dict()
 
     def load_state_dict(self, state_dict):
@@ -43,12 +51,15 @@ class _AdamStateView(optim.Adam):
         m = self._model
         eng, nu = m._engine, m.n_users
         step = 0
+        parts = []
         for p, sl in ((m.embedding_user.weight, slice(0, nu)), (m.embedding_item.weight, slice(nu, None))):
             st = self.state.get(p, {})
             if 'exp_avg' in st:
-                eng.M[sl].copy_(st['exp_avg'])
-                eng.V[sl].copy_(st['exp_avg_sq'])
+                parts.append((st['exp_avg'], st['exp_avg_sq']))
                 step = int(float(st['step']))
+        if len(parts) == 2:
+            dev = eng.M.device
+            eng.load_adam_state(torch.cat([parts[0][0].to(dev), parts[1][0].to(dev)]), torch.cat([parts[0][1].to(dev), parts[1][1].to(dev)]))
         eng.set_lr(self.param_groups[0]['lr'])
         eng.set_adam_step(step)
         self._bind()

@@ -290,11 +290,15 @@ int lgcn_score_dense(const float* users_emb, const float* items_emb, const int64
  * replaces  test_one_batch/getLabel/RecallPrecision_ATk/NDCGatK_r
  *           code/Procedure.py:89-121 ; code/utils.py:173-200,212-217
  * topk_idx int64[Bt,k_max]; test CSR over the same Bt rows (sorted item ids); ks int32[nk];
- * sums_out float64[3*nk] += {precision, recall, ndcg} summed over rows.
+ * sums_out float64[3*nk] += {precision, recall, ndcg} summed over rows, in a FIXED order (per-row values go through the
+ * workspace, then one fixed-shape reduction per column): the result has the same bits on every call, which is what lets
+ * the multi-GPU Test (ranked lists gathered, metrics computed on every rank) equal the single-GPU one bit for bit.
  * -------------------------------------------------------------------------------------------*/
+size_t lgcn_rank_metrics_workspace_bytes(int32_t Bt, int32_t nk);
 int lgcn_rank_metrics(const int64_t* topk_idx, int32_t Bt, int32_t k_max,
                       const int32_t* test_indptr, const int32_t* test_indices,
-                      const int32_t* ks, int32_t nk, double* sums_out, lgcn_stream_t stream);
+                      const int32_t* ks, int32_t nk, double* sums_out,
+                      void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-side negative sampler with the semantics of code/sources/sampling.cpp:27-56 (per user

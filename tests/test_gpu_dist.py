@@ -1,5 +1,6 @@
-"""GPU, 2 ranks over NCCL (skipped with fewer than 2 devices): the data-parallel and row-partitioned
-engines must reproduce the single-GPU / reference result."""
+"""GPU, N ranks over NCCL (skipped with fewer than 2 devices; LGCN_TEST_RANKS picks N, default 2): the data-parallel
+and row-partitioned engines must reproduce the single-GPU / reference result, the row partition must really partition
+memory, and the reference-facing procedures must run under it."""
 import os
 import socket
 
@@ -11,33 +12,76 @@ from conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
+NRANKS = int(os.environ.get('LGCN_TEST_RANKS', '2'))
+
 
 def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, mode, q):
-    p2p = mode != 'rowpart_nccl'
-    mode = 'rowpart' if mode.startswith('rowpart') else mode
+def _spawn(worker, world, *args, timeout=500):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q) + args) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout)
+        assert p.exitcode == 0
+    return sorted(q.get(timeout=10) for _ in range(world))
+
+
+def _init(rank, world, port):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    import lgcn_b200 as lg
+    lg.world.configure(device=f'cuda:{rank}')
+    return dist, lg
+
+
+def _tiny_model(lg, g, **over):
+    cfg = dict(lg.world.config)
+    cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), bpr_batch_size=len(g['users']),
+               decay=float(g['decay']), lr=float(g['lr']), deterministic=True)
+    cfg.update(over)
+    ds = lg.InteractionDataset(int(g['n_users']), int(g['m_items']), g['train_user'], g['train_item'],
+                               g['test_user'], g['test_item'], config=cfg)
+    m = lg.LightGCN(cfg, ds)
+    nu = int(g['n_users'])
+    with torch.no_grad():
+        m.embedding_user.weight.copy_(torch.from_numpy(g['E0'][:nu])); m.embedding_item.weight.copy_(torch.from_numpy(g['E0'][nu:]))
+    return cfg, ds, m
+
+
+def _worker(rank, world, port, q, mode):
+    variant = mode
+    p2p = mode not in ('rowpart_nccl',)
+    part_mem = mode != 'rowpart_shared'
+    multicast = mode != 'rowpart_unicast'
+    mode = 'rowpart' if mode.startswith('rowpart') else mode
+    dist, lg = _init(rank, world, port)
     try:
-        import lgcn_b200 as lg
-        lg.world.configure(device=f'cuda:{rank}')
         g = load_golden('tiny')
-        cfg = dict(lg.world.config)
-        cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), bpr_batch_size=len(g['users']),
-                   decay=float(g['decay']), lr=float(g['lr']), dist_mode=mode, deterministic=True, rowpart_p2p=p2p)
-        ds = lg.InteractionDataset(int(g['n_users']), int(g['m_items']), g['train_user'], g['train_item'],
-                                   g['test_user'], g['test_item'], config=cfg)
-        m = lg.LightGCN(cfg, ds)
-        nu = int(g['n_users'])
-        with torch.no_grad():
-            m.embedding_user.weight.copy_(torch.from_numpy(g['E0'][:nu])); m.embedding_item.weight.copy_(torch.from_numpy(g['E0'][nu:]))
+        cfg, ds, m = _tiny_model(lg, g, dist_mode=mode, rowpart_p2p=p2p, rowpart_partition_memory=part_mem, rowpart_multicast=multicast)
         eng = m._engine
         assert eng.p2p == (mode == 'rowpart' and p2p)
+        if mode == 'rowpart':
+            N, d = eng.N, eng.d
+            nnz_local = torch.tensor([eng.local.nnz], device='cuda')
+            dist.all_reduce(nnz_local)
+            full_nnz = 2 * np.unique(g['train_user'] * int(g['m_items']) + g['train_item']).size
+            assert int(nnz_local.item()) == full_nnz                                     # the blocks tile the matrix
+            if part_mem:                                                                 # ... and nobody holds more than its block
+                assert eng.csr is None and m._csr is None and m.Graph is None
+                assert eng.M.shape == (eng.r1 - eng.r0, d) and eng.V.shape == (eng.r1 - eng.r0, d)
+                assert eng.local.indptr.numel() == eng.r1 - eng.r0 + 1
+            assert eng.use_graph == bool(eng.p2p)
         B = len(g['users'])
         losses = []
         for s in range(3):
@@ -49,8 +93,7 @@ def _worker(rank, world, port, mode, q):
             else:
                 eng.step(u, p, n)
             losses.append(float(eng.loss_to_host()[2]))
-        if mode == 'rowpart' and not eng.p2p:
-            eng._allgather_rows(eng.E0)
+        eng.sync_params_for_read()
         params = eng.E0.cpu().numpy()
         with torch.no_grad():
             out = torch.cat(m.computer()).cpu().numpy()
@@ -61,25 +104,111 @@ def _worker(rank, world, port, mode, q):
         lst = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(lst, chk)
         same = all(float(x) == float(lst[0]) for x in lst)
-        q.put((rank, bool(ok), bool(same), [float(x) for x in losses]))
+        bitwise = True
+        if mode == 'rowpart':
+            # the partition changes who computes a row, not how: bit-identical to the single-GPU engine (deterministic mode)
+            _, _, m1 = _tiny_model(lg, g, dist_mode=None)
+            for s in range(3):
+                sh = (s * 17) % B
+                m1._engine.step(*(torch.from_numpy(np.roll(g[k], sh)).long().cuda() for k in ('users', 'pos', 'neg')))
+            bitwise = bool(np.array_equal(m1._engine.E0.cpu().numpy(), params))
+            Mf, Vf = eng.adam_state_full()
+            bitwise = bitwise and torch.equal(Mf, m1._engine.M) and torch.equal(Vf, m1._engine.V)
+            if eng._barrier is not None:
+                eng._barrier.check()
+        q.put((rank, bool(ok), bool(same), bool(bitwise), variant))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["dp", "dp_idx", "rowpart", "rowpart_nccl"])
+@pytest.mark.parametrize("mode", ["dp", "dp_idx", "rowpart", "rowpart_unicast", "rowpart_shared", "rowpart_nccl"])
 @pytest.mark.timeout(600)
-def test_two_rank_training_matches_reference(mode):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(500)
-        assert p.exitcode == 0
-    res = sorted(q.get(timeout=10) for _ in range(2))
+def test_n_rank_training_matches_reference(mode):
+    res = _spawn(_worker, NRANKS, mode)
+    assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def _procedure_worker(rank, world, port, q, tmp):
+    dist, lg = _init(rank, world, port)
+    try:
+        g, t = load_golden('tiny_epochs'), load_golden('tiny')
+        lg.world.configure(checkpoint_dir=os.path.join(tmp, f'r{rank}'), bpr_batch_size=int(g['batch']), topks=[20])
+
+        def run(dist_mode):
+            cfg = dict(lg.world.config)
+            cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), decay=float(g['decay']), lr=float(g['lr']),
+                       deterministic=True, dist_mode=dist_mode)
+            ds = lg.InteractionDataset(int(t['n_users']), int(t['m_items']), t['train_user'], t['train_item'],
+                                       t['test_user'], t['test_item'], config=cfg)
+            lg.utils.set_seed(2020); lg.utils.sampler_seed(2020)
+            m = lg.LightGCN(cfg, ds)
+            bpr = lg.utils.BPRLoss(m, cfg)
+            infos = [lg.Procedure.BPR_train_original(ds, m, bpr, e) for e in range(1, int(g['epochs']) + 1)]
+            res = lg.Procedure.Test(ds, m, int(g['epochs']))
+            sd = bpr.opt.state_dict()
+            return m, infos, res, sd
+        m, infos, res, sd = run('rowpart')
+        m1, infos1, res1, sd1 = run(None)                       # the same procedures on this GPU alone
+        P, P1 = m._engine.E0.cpu().numpy(), m1._engine.E0.cpu().numpy()
+        same_as_single = (np.array_equal(P, P1) and all(np.array_equal(res[k], res1[k]) for k in res)
+                          and [s.split('-')[0] for s in infos] == [s.split('-')[0] for s in infos1]
+                          and all(torch.equal(sd['state'][i][k].cpu(), sd1['state'][i][k].cpu()) for i in (0, 1) for k in ('exp_avg', 'exp_avg_sq')))
+        vs_ref = (abs(float(res['recall'][0]) - float(g['recall'][0])) <= 1e-4 and abs(float(res['ndcg'][0]) - float(g['ndcg'][0])) <= 1e-4
+                  and rel_err(P, g['params']) < 1e-3)
+        if m._engine._barrier is not None:
+            m._engine._barrier.check()
+        q.put((rank, bool(same_as_single), bool(vs_ref), float(res['recall'][0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_procedures_under_the_row_partition(tmp_path):
+    """BPR_train_original x 20 epochs + Test under dist_mode='rowpart' (users sharded for the ranking, ranked lists gathered):
+    metrics, losses, parameters and optimizer state equal the single-GPU run BIT FOR BIT, and the reference's fixed-epoch
+    golden to 1e-4 (code/Procedure.py:28-83,127-206)."""
+    res = _spawn(_procedure_worker, NRANKS, str(tmp_path))
     assert all(r[1] and r[2] for r in res), res
+
+
+def _barrier_worker(rank, world, port, q):
+    dist, lg = _init(rank, world, port)
+    try:
+        from lgcn_b200.engine import map_peer_buffers
+        lib = lg._lib.load()
+        for p_dev in range(torch.cuda.device_count()):
+            lib.lgcn_enable_peer_access(p_dev)
+        flags = torch.zeros(64, dtype=torch.int32, device='cuda')
+        box = torch.zeros(world, 1 << 16, dtype=torch.float32, device='cuda')      # box[src] is written by rank src
+        torch.cuda.synchronize()
+        bar = lg.ops.RankBarrier(flags, map_peer_buffers(flags), rank, world, timeout_ms=5000)
+        peers = map_peer_buffers(box)
+        dist.barrier()
+        ok = True
+        for it in range(1, 201):
+            for p in range(world):                       # put: my slice of every rank's box (peer stores over NVLink)
+                peers[p][rank].fill_(float(it * 10 + rank))
+            bar()                                        # device-side: all puts of round `it` are visible after this
+            got = box[:, ::4097].clone()
+            bar()                                        # nobody overwrites before everybody has read
+            want = torch.tensor([float(it * 10 + s) for s in range(world)], device='cuda').view(world, 1).expand_as(got)
+            ok = ok and bool(torch.equal(got, want))
+        bar.check()
+        # the same inside a CUDA graph, replayed: the epoch counter lives on the device
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(6):
+                bar()
+        for _ in range(50):
+            g.replay()
+        torch.cuda.synchronize()
+        bar.check()
+        q.put((rank, ok, int(bar.epoch.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_device_side_rank_barrier():
+    res = _spawn(_barrier_worker, NRANKS, timeout=200)
+    assert all(r[1] for r in res) and len({r[2] for r in res}) == 1 and res[0][2] == 400 + 300, res

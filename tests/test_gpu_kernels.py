@@ -90,6 +90,62 @@ def test_csr_build_full_size_properties(lg, orc):
     assert indices[:indptr[nu]].min() >= nu and indices[indptr[nu]:].max() < nu
 
 
+@pytest.mark.parametrize("parts,chunked", [(1, False), (2, False), (3, True), (8, True)])
+def test_row_block_build_equals_rows_of_the_full_build(lg, orc, parts, chunked):
+    """Memory-partitioned row partition: a rank assembles ONLY its rows (lgcn_degree_accumulate / lgcn_csr_rows_emit /
+    lgcn_csr_rows_finish) — each block must be the corresponding rows of lgcn_csr_build's CSR and of the oracle's, bit for bit,
+    also when the edge stream arrives in chunks, with duplicate pairs, zero-degree nodes and an empty block."""
+    rng = np.random.default_rng(parts)
+    nu, ni = 700, 900
+    tu, ti = random_edges(rng, nu, ni - 40, 9000, dup=300)            # last 40 items: zero-degree rows
+    full = build(lg, tu, ti, nu, ni)
+    o_indptr, o_indices, o_vals, o_deg, o_dinv = orc.build_norm_adj(tu, ti, nu, ni)
+    dtu, dti = dev(tu), dev(ti)
+
+    def chunks():
+        if not chunked:
+            yield dtu, dti
+        else:
+            for lo in range(0, tu.size, 2500):
+                yield dtu[lo:lo + 2500].contiguous(), dti[lo:lo + 2500].contiguous()
+    b = lg.ops.RowBlockBuilder(nu, ni, chunks)
+    assert np.array_equal(b.deg.cpu().numpy(), o_deg) and np.array_equal(b.dinv.cpu().numpy(), full.dinv.cpu().numpy())
+    bounds = lg.engine.balanced_row_bounds(b.cost_prefix, parts)
+    if parts == 3:
+        bounds[1] = bounds[2]                                           # an empty block in the middle
+    N = nu + ni
+    assert bounds[0] == 0 and bounds[-1] == N
+    tot = 0
+    for r0, r1 in zip(bounds, bounds[1:]):
+        g = b.build(r0, r1)
+        ip = g.indptr.cpu().numpy()
+        assert g.n_rows == r1 - r0 and g.n_cols == N
+        assert np.array_equal(ip, o_indptr[r0:r1 + 1] - o_indptr[r0])
+        assert np.array_equal(g.indices.cpu().numpy(), o_indices[o_indptr[r0]:o_indptr[r1]])
+        assert np.array_equal(g.vals.cpu().numpy(), o_vals[o_indptr[r0]:o_indptr[r1]])
+        tot += g.nnz
+        if r1 > r0:                                                     # and the block drives K1 like the view of the full CSR
+            X = torch.randn(N, 64, device='cuda')
+            ya, yb = torch.empty(r1 - r0, 64, device='cuda'), torch.empty(r1 - r0, 64, device='cuda')
+            lg.ops.spmm(g, X, ya); lg.ops.spmm(full.rows(r0, r1), X, yb)
+            assert torch.equal(ya, yb)
+    assert tot == full.nnz
+
+
+def test_rank_metrics_is_bitwise_repeatable_and_split_invariant(lg):
+    """lgcn_rank_metrics adds the per-row values in a fixed order: the same bits on every call — the property the multi-GPU
+    Test relies on (ranked lists gathered from the ranks, then this kernel on every rank)."""
+    rng = np.random.default_rng(0)
+    Bt, k, ni = 5000, 20, 3000
+    topk = np.stack([rng.choice(ni, k, replace=False) for _ in range(Bt)]).astype(np.int64)
+    lens = rng.integers(0, 30, Bt)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    items = np.concatenate([np.sort(rng.choice(ni, l, replace=False)) for l in lens]).astype(np.int32)
+    a = lg.ops.rank_metrics(dev(topk), dev(indptr), dev(items), [5, 20]).cpu().numpy()
+    for _ in range(5):
+        assert np.array_equal(lg.ops.rank_metrics(dev(topk), dev(indptr), dev(items), [5, 20]).cpu().numpy(), a)
+
+
 def test_coo_to_csr(lg, orc):
     g = load_golden('tiny')
     N = int(g['n_users']) + int(g['m_items'])
