@@ -13,7 +13,7 @@ All device work is done by liblgcn_b200.so (csrc/, C ABI in include/lgcn_b200.h)
 package without the built library raises at first use — there is no fallback implementation.
 """
 from . import _lib, world            # noqa: F401
-from . import ops, utils             # noqa: F401
+from . import ops, utils, sampling   # noqa: F401
 from . import dataloader, synth      # noqa: F401
 from .dataloader import BasicDataset, InteractionDataset, Loader     # noqa: F401
 from . import engine, model          # noqa: F401

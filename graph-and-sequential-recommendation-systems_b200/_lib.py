@@ -57,6 +57,7 @@ _SIGNATURES = {
                                      POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
     "lgcn_spmm_adam_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                           POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
+    "lgcn_debug_gather_rows": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_debug_spmm_variant": (ctypes.c_int, [ctypes.c_int]),
     "lgcn_adam_init": (ctypes.c_int, [_P, c_double, c_double, c_double, c_double, c_int32, _P]),
     "lgcn_adam_tick": (ctypes.c_int, [_P, _P]),
@@ -86,6 +87,8 @@ _SIGNATURES = {
     "lgcn_sample_bpr": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int64, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P]),
     "lgcn_sampler_seed": (None, [c_uint32]),
     "lgcn_sample_negative": (c_int64, [c_int32, c_int32, c_int64, _P, _P, c_int32, _P]),
+    "lgcn_sample_negative_by_user": (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P]),
+    "lgcn_randint": (c_int32, [c_int32]),
     "lgcn_parse_interactions": (c_int64, [ctypes.c_char_p, _P, _P, c_int64, _P, _P]),
 }
 

@@ -113,6 +113,39 @@ extern "C" int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int6
     return (int64_t)user_num * per_user;
 }
 
+// sample_negative_ByUser (code/sources/sampling.cpp:58-86): one row per LISTED user, same draw order
+extern "C" int64_t lgcn_sample_negative_by_user(const int32_t* users_host, int64_t n_listed, int32_t user_num, int32_t item_num,
+                                                const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
+                                                int32_t neg_num, int32_t* out_host) {
+    if (n_listed < 0 || user_num <= 0 || item_num <= 0 || neg_num < 1 || !allpos_indptr_host || !allpos_items_host || (n_listed && (!users_host || !out_host))) {
+        set_error("sample_negative_by_user: bad arguments"); return -1;
+    }
+    const int row = neg_num + 2;
+    for (int64_t k = 0; k < n_listed; ++k) {
+        const int32_t user = users_host[k];
+        if (user < 0 || user >= user_num) { set_error("sample_negative_by_user: user %d outside [0,%d)", user, user_num); return -4; }
+        const int32_t* pos = allpos_items_host + allpos_indptr_host[user];
+        const int64_t npos = allpos_indptr_host[user + 1] - allpos_indptr_host[user];
+        if (npos <= 0) { set_error("sample_negative_by_user: user %d has no positive item", user); return -2; }
+        if (npos >= item_num) { set_error("sample_negative_by_user: user %d interacted with every item", user); return -3; }
+        int32_t* o = out_host + k * row;
+        o[0] = user;
+        o[1] = pos[rand() % npos];
+        for (int idx = 2; idx < row; ++idx) {
+            int neg;
+            do { neg = rand() % item_num; } while (std::find(pos, pos + npos, neg) != pos + npos);
+            o[idx] = neg;
+        }
+    }
+    return n_listed;
+}
+
+// randint (code/sources/sampling.cpp:22-25, exported to Python at :100): next value of the same rand() stream
+extern "C" int32_t lgcn_randint(int32_t end) {
+    if (end <= 0) { set_error("randint: end must be positive"); return -1; }
+    return rand() % end;
+}
+
 // ---- ingest: the reference's interaction files --------------------------------------------------
 // "uid item item ..." per line, whitespace separated; blank lines and lines without items are skipped
 // (code/dataloader.py:82-115).  One pass over the file; pairs beyond `capacity` are counted, not stored.

@@ -405,9 +405,69 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
     return 0;
 }
 
+// ---- L2 -> SM gather ceiling probe (bench.py `roofline_l2`) -------------------------------------------------
+// The plainest kernel with K1's access pattern and none of its overheads: every LANES-lane group walks a contiguous run of
+// row ids (coalesced index loads) and gathers the d-float rows they name, 16 bytes per lane, UNROLL rows in flight, summing
+// them; one row per group is written at the end so nothing is optimised away.  No values, no shuffles beyond the index
+// hand-out, no epilogue, perfectly balanced runs.  What it reaches on an L2-resident table is the bandwidth K1's gathers
+// are bounded by on this box.
+template <int D, int LANES, int UNROLL>
+__global__ void __launch_bounds__(128, 8)
+gather_probe_kernel(const float4* __restrict__ X, const int* __restrict__ idx, long long n_idx, int run, float4* __restrict__ out) {
+    constexpr int VEC = D / 4, VPL = VEC / LANES, GROUPS = 128 / LANES;
+    const int lane = threadIdx.x % LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+    const long long g = (long long)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    const long long begin = g * run;
+    if (begin >= n_idx) return;
+    const long long end = begin + run < n_idx ? begin + run : n_idx;
+    float4 acc[VPL];
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+    for (long long base = begin; base < end; base += LANES) {
+        const long long j = base + lane < end ? base + lane : end - 1;
+        const int c = ld_stream_i32(idx + j);
+        const int cnt = (int)(end - base < LANES ? end - base : LANES);
+#pragma unroll 1
+        for (int t = 0; t < cnt; t += UNROLL) {
+            float4 x[UNROLL][VPL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int cc = __shfl_sync(gmask, c, (t + u) % LANES, LANES);
+                const float4* src = X + (size_t)cc * VEC + lane;
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) x[u][p] = gather_f4(src + p * LANES);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) f4_add(acc[p], x[u][p]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) out[(size_t)g * VEC + lane + p * LANES] = acc[p];
+}
+
 }  // namespace lgcn
 
 using namespace lgcn;
+
+extern "C" int lgcn_debug_gather_rows(const float* X, const int32_t* idx, int64_t n_idx, int32_t d, int32_t run,
+                                      int32_t variant, float* out, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(X && idx && out && n_idx > 0 && run > 0, "debug_gather_rows: bad arguments");
+    LGCN_CHECK_ARG(d == 64, "debug_gather_rows: d=%d unsupported (64)", d);
+    const long long groups = (n_idx + run - 1) / run;
+    const float4* X4 = reinterpret_cast<const float4*>(X); float4* o4 = reinterpret_cast<float4*>(out);
+    cudaStream_t st = as_stream(stream);
+    switch (variant) {
+        case 1:  gather_probe_kernel<64, 16, 8><<<(unsigned)((groups + 7) / 8), 128, 0, st>>>(X4, idx, n_idx, run, o4); break;
+        case 2:  gather_probe_kernel<64, 8, 8><<<(unsigned)((groups + 15) / 16), 128, 0, st>>>(X4, idx, n_idx, run, o4); break;
+        case 3:  gather_probe_kernel<64, 16, 4><<<(unsigned)((groups + 7) / 8), 128, 0, st>>>(X4, idx, n_idx, run, o4); break;
+        default: gather_probe_kernel<64, 8, 4><<<(unsigned)((groups + 15) / 16), 128, 0, st>>>(X4, idx, n_idx, run, o4); break;
+    }
+    LGCN_CHECK_LAUNCH("gather_probe_kernel");
+    return 0;
+}
 
 extern "C" int lgcn_debug_spmm_variant(int variant) { const int old = g_variant; g_variant = variant; return old; }
 

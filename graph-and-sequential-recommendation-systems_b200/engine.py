@@ -443,8 +443,11 @@ class Engine:
         self._host_step = int(step)
         ops.adam_reinit(self.scalars, self.lr, step=self._host_step)
 
-    def _enqueue_step(self, users, pos, neg, ctl):
-        """Everything between 'batch is on the device' and 'loss_out is written'."""
+    def _enqueue_step(self, users, pos, neg, ctl, only_spmm=False):
+        """Everything between 'batch is on the device' and 'loss_out is written'.
+        only_spmm (measurement): just the step's 2L K1 launches (with their exchanges), on whatever the buffers hold."""
+        if only_spmm:
+            return self._enqueue_spmm_only()
         ops.adam_tick(self.scalars)
         masks = None
         if self.prune:
@@ -488,6 +491,35 @@ class Engine:
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
         else:
             ops.bpr_clear_rows(self.G, users, pos, neg, self.B_cap, ctl, self.nu)
+
+    def _enqueue_spmm_only(self):
+        self.forward((self.m0, None) if self.prune else None)
+        r0, r1 = self.r0, self.r1
+        Mo, Vo = (self.M, self.V) if self._mv_local else (self.M[r0:r1], self.V[r0:r1])
+        g = self.local if self.dist_mode == 'rowpart' else self.csr
+        peers_e0 = self._peer.get(self.E0.data_ptr()) if self.p2p else None
+        mc_e0 = self._mc.get(self.E0.data_ptr(), 0) if self.p2p else 0
+
+        def last(X, alpha, beta, zs, col_mask):
+            ops.spmm_adam(g, X, self.E0[r0:r1], Mo, Vo, self.scalars, alpha, beta, [z[r0:r1] for z in zs], col_mask=col_mask,
+                          peer_p=None if (peers_e0 is None or mc_e0) else [peers_e0[p][r0:r1] for p in range(self.world) if p != self.rank],
+                          mc_p=(mc_e0 + r0 * self.d * 4) if mc_e0 else 0)
+            if peers_e0 is not None or mc_e0:
+                self._rank_barrier()
+        if self.L > 0:
+            self._backward_chain(self.G, last)
+
+    def spmm_only_graph(self):
+        """A CUDA graph holding exactly the 2L K1 launches of a training step (same arguments, same row mask as the last
+        step) — bench.py times its replays to get K1's launch duration under the conditions of the captured step.
+        Replays run the Adam epilogue on whatever G holds: callers save and restore E0/M/V/scalars around them."""
+        self._sync_params_across_ranks()
+        self._enqueue_spmm_only()
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue_spmm_only()
+        return g
 
     def _warm_kernels(self, users, pos, neg, ctl):
         """Run the step once on throw-away state so every kernel is loaded before graph capture."""

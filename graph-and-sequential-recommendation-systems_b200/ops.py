@@ -297,6 +297,17 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_
                                       g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p, 0, mc_p), _stream()), "spmm_adam")
 
 
+def gather_probe(X, idx, run=32, variant=0, out=None):
+    """Measurement hook: sum the rows X[idx] in runs of `run` (lgcn_debug_gather_rows) -> float32 [ceil(n/run), d]."""
+    _need(X, torch.float32, "X", 2), _need(idx, torch.int32, "idx", 1)
+    n, d = idx.numel(), X.shape[1]
+    groups = (n + run - 1) // run
+    if out is None:
+        out = torch.empty((groups, d), dtype=torch.float32, device=X.device)
+    _lib.check(_lib.load().lgcn_debug_gather_rows(_p(X), _p(idx), n, d, int(run), int(variant), _p(out), _stream()), "debug_gather_rows")
+    return out
+
+
 def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
     s = torch.zeros(ctypes.sizeof(_lib.AdamScalars) // 4, dtype=torch.int32, device=device)
     _lib.check(_lib.load().lgcn_adam_init(_p(s), lr, beta1, beta2, eps, int(step), _stream()), "adam_init")

@@ -83,41 +83,71 @@ def write_txt(graph, path):
                     f.write(f"{uu} {' '.join(map(str, its.tolist()))}\n")
 
 
-def make_powerlaw_device(n_users, m_items, n_edges, seed=2020, device=None, chunk=1 << 26):
-    """BASELINE config 5 (scaled power-law graph) generated ON THE DEVICE: int64 (train_user, train_item) tensors.
-    u = floor(n_users * r^2), i = floor(m_items * r^2.5): hub user ~ n_edges/sqrt(n_users), hub item ~ n_edges/m_items^0.4.
-    Duplicate pairs are left in (K4 sums them like scipy's csr_matrix)."""
+def powerlaw_chunks(n_users, m_items, n_edges, seed=2020, device=None, chunk=1 << 26):
+    """BASELINE config 5 (scaled power-law graph) generated ON THE DEVICE, one chunk of edges at a time: yields
+    (train_user, train_item) int64 tensors.  u = floor(n_users * r^2), i = floor(m_items * r^2.5): hub user ~
+    n_edges/sqrt(n_users), hub item ~ n_edges/m_items^0.4.  Duplicate pairs are left in (K4 sums them like scipy's
+    csr_matrix).  Deterministic in (seed, chunk): every call — and every rank — walks the same edge stream, which is what
+    lets each rank of the row partition filter out its own rows without any rank ever holding the whole edge list."""
     import torch
     device = device or torch.device('cuda')
     gen = torch.Generator(device=device).manual_seed(seed)
-    tu = torch.empty(n_edges, dtype=torch.int64, device=device)
-    ti = torch.empty(n_edges, dtype=torch.int64, device=device)
     for lo in range(0, n_edges, chunk):
         hi = min(n_edges, lo + chunk)
         r1 = torch.rand(hi - lo, device=device, generator=gen, dtype=torch.float64)
         r2 = torch.rand(hi - lo, device=device, generator=gen, dtype=torch.float64)
-        tu[lo:hi] = (r1 * r1 * n_users).long().clamp_(0, n_users - 1)
-        ti[lo:hi] = (r2.pow(2.5) * m_items).long().clamp_(0, m_items - 1)
+        tu = (r1 * r1 * n_users).long().clamp_(0, n_users - 1)
+        ti = (r2.pow(2.5) * m_items).long().clamp_(0, m_items - 1)
+        del r1, r2
+        yield tu, ti
+
+
+def make_powerlaw_device(n_users, m_items, n_edges, seed=2020, device=None, chunk=1 << 26):
+    """The whole edge list of powerlaw_chunks as two int64 device tensors (single-GPU path)."""
+    import torch
+    device = device or torch.device('cuda')
+    tu = torch.empty(n_edges, dtype=torch.int64, device=device)
+    ti = torch.empty(n_edges, dtype=torch.int64, device=device)
+    lo = 0
+    for cu, ci in powerlaw_chunks(n_users, m_items, n_edges, seed, device, chunk):
+        tu[lo:lo + cu.numel()] = cu; ti[lo:lo + ci.numel()] = ci
+        lo += cu.numel()
     return tu, ti
 
 
 class DeviceGraphDataset:
     """Minimal dataset over device-resident edge arrays (no host copies): what LightGCN needs to build its graph.
-    Training uses the device sampler (world.config['device_sampler'])."""
+    Training uses the device sampler (world.config['device_sampler']).  With `chunks` (a callable returning an iterable of
+    edge chunks, e.g. functools.partial(powerlaw_chunks, ...)) instead of arrays, it is the graph source of the
+    memory-partitioned row partition: getRowBlockBuilder() — no rank materialises the edge list or the whole CSR."""
 
-    def __init__(self, n_users, m_items, train_user_dev, train_item_dev, seg_len=128):
+    def __init__(self, n_users, m_items, train_user_dev=None, train_item_dev=None, seg_len=128, chunks=None, n_edges=None):
         self.n_users, self.m_items = int(n_users), int(m_items)
-        self.trainDataSize = int(train_user_dev.numel())
+        self.trainDataSize = int(train_user_dev.numel()) if train_user_dev is not None else int(n_edges or 0)
         self._tu, self._ti, self._seg_len = train_user_dev, train_item_dev, seg_len
-        self._csr, self.Graph = None, None
+        self._chunks = chunks
+        self._csr, self.Graph, self._builder = None, None, None
         self.testDict = {}
 
     def getCSRGraph(self):
         if self._csr is None:
             from . import ops
+            if self._tu is None:
+                raise RuntimeError("this dataset streams its edges in chunks: use getRowBlockBuilder() (dist_mode='rowpart')")
             self._csr = ops.csr_build(self._tu, self._ti, self.n_users, self.m_items, seg_len=self._seg_len)
             self._tu = self._ti = None            # the edge list is no longer needed
         return self._csr
+
+    def getRowBlockBuilder(self):
+        if self._builder is None:
+            from . import ops
+            chunks = self._chunks
+            if chunks is None:
+                tu, ti = self._tu, self._ti
+                chunks = lambda: iter([(tu, ti)])         # noqa: E731
+            self._builder = ops.RowBlockBuilder(self.n_users, self.m_items, chunks, seg_len=self._seg_len)
+            self.trainDataSize = self._builder.n_edges
+        return self._builder
 
     def getSparseGraph(self):
         if self.Graph is None:

@@ -180,6 +180,13 @@ int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* va
  * plain kernel; 0 = shipped configuration.  Returns the previous value.  Results are identical. */
 int lgcn_debug_spmm_variant(int variant);
 
+/* measurement hook (bench.py `roofline_l2`, scripts/l2_gather_ceiling.py): the plainest kernel with K1's access pattern —
+ * groups of lanes walk `run` consecutive entries of idx int32[n_idx] and sum the d-float rows of X they name (16-byte
+ * gathers, several rows in flight); out float32[ceil(n_idx/run)*d].  variant 0..3 = {8,16} lanes x {4,8} rows in flight.
+ * What it reaches on an L2-resident X is the L2->SM gather bandwidth K1 is bounded by on this box. */
+int lgcn_debug_gather_rows(const float* X, const int32_t* idx, int64_t n_idx, int32_t d, int32_t run,
+                           int32_t variant, float* out, lgcn_stream_t stream);
+
 int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                        int32_t n_rows, int32_t d, const float* X, float* Y /* may be NULL */,
                        float alpha, float beta, const float* const* z_host, int32_t nz,
@@ -310,6 +317,13 @@ void lgcn_sampler_seed(uint32_t seed);
 int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_num,
                              const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
                              int32_t neg_num, int32_t* out_host);
+
+/* sample_negative_ByUser (code/sources/sampling.cpp:58-86): one row {user, pos, neg...} per entry of users_host int32[n_listed],
+ * and randint (sampling.cpp:22-25,100): both continue the same rand() stream as lgcn_sample_negative. */
+int64_t lgcn_sample_negative_by_user(const int32_t* users_host, int64_t n_listed, int32_t user_num, int32_t item_num,
+                                     const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
+                                     int32_t neg_num, int32_t* out_host);
+int32_t lgcn_randint(int32_t end);
 
 /* ---------------------------------------------------------------------------------------------
  * Ingest of the reference's interaction files

@@ -206,7 +206,12 @@ def sampler_golden():
     train_num = sum(len(v) for v in train.values())
     sampling.seed(2020)
     S = sampling.sample_negative(nu, ni, train_num, all_pos, 1)
+    # the rest of the module's ABI, continuing the same rand() stream: randint, then sample_negative_ByUser (2 negatives)
+    randints = np.array([sampling.randint(1000) for _ in range(16)], dtype=np.int32)
+    by_users = np.array([5, 0, 299, 5, 17, 123, 42, 42], dtype=np.int32)
+    S_by_user = sampling.sample_negative_ByUser(by_users.tolist(), ni, all_pos, 2)
     np.savez_compressed(os.path.join(GOLDEN, 'sampler.npz'), S=S, train_num=train_num, n_users=nu, m_items=ni,
+                        randints=randints, by_users=by_users, S_by_user=S_by_user,
                         indptr=np.concatenate([[0], np.cumsum([len(a) for a in all_pos])]).astype(np.int64),
                         items=np.concatenate(all_pos).astype(np.int32))
     print(f"[golden] sampler: {S.shape} first rows {S[:3].tolist()}")

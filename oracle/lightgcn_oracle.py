@@ -205,3 +205,40 @@ def metrics_at_k(topk_items, ground_truth, ks):
             idcg = disc[:min(k, len(gt))].sum()
             res['ndcg'][j] += (r[:k] * disc).sum() / (idcg if idcg != 0 else 1.0)
     return {m: v / max(n, 1) for m, v in res.items()}
+
+
+# ------------------------------------------------------------------------------ sampler (oracle/c/sampler_ref.c)
+def sample_negative_ref(seed, user_num, item_num, train_num, indptr, items, neg_num=1):
+    """The reference's C++ sampler (code/sources/sampling.cpp:27-56,88-91) restated in C: srand(seed), then per user
+    train_num // user_num triples.  indptr int64[user_num+1], items int32 -> int32[rows, 2+neg_num]."""
+    lib = clib()
+    lib.oracle_sample_negative.restype = ctypes.c_int64
+    lib.oracle_sample_negative.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64); items = np.ascontiguousarray(items, dtype=np.int32)
+    out = np.empty((user_num * (train_num // user_num), 2 + neg_num), dtype=np.int32)
+    if seed is not None:
+        lib.oracle_sampler_seed(ctypes.c_uint(int(seed) & 0xffffffff))
+    rows = lib.oracle_sample_negative(user_num, item_num, train_num, indptr.ctypes.data, items.ctypes.data, neg_num, out.ctypes.data)
+    if rows < 0:
+        raise RuntimeError("oracle sampler: a user has no positive item")
+    return out
+
+
+def sample_negative_by_user_ref(users, item_num, indptr, items, neg_num=1):
+    """code/sources/sampling.cpp:58-86, continuing the current rand() stream."""
+    lib = clib()
+    lib.oracle_sample_negative_by_user.restype = ctypes.c_int64
+    lib.oracle_sample_negative_by_user.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    users = np.ascontiguousarray(users, dtype=np.int32)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64); items = np.ascontiguousarray(items, dtype=np.int32)
+    out = np.empty((users.size, 2 + neg_num), dtype=np.int32)
+    if lib.oracle_sample_negative_by_user(users.ctypes.data, users.size, item_num, indptr.ctypes.data, items.ctypes.data, neg_num, out.ctypes.data) < 0:
+        raise RuntimeError("oracle sampler: a user has no positive item")
+    return out
+
+
+def randint_ref(end):
+    """code/sources/sampling.cpp:22-25."""
+    lib = clib()
+    lib.oracle_randint.restype = ctypes.c_int
+    return int(lib.oracle_randint(ctypes.c_int(int(end))))

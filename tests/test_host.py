@@ -86,6 +86,32 @@ def test_sampler_matches_reference_cpp_bit_exact():
     assert np.array_equal(out, g['S'])
 
 
+def test_sampling_module_abi_matches_reference_cpp():
+    """The whole ABI of the reference's pybind11 `sampling` module (code/sources/sampling.cpp:95-106): seed,
+    sample_negative, randint, sample_negative_ByUser — one rand() stream, recorded from the reference's compiled file."""
+    import lgcn_b200 as lg
+    g = load_golden('sampler')
+    nu, ni, tn = int(g['n_users']), int(g['m_items']), int(g['train_num'])
+    all_pos = np.split(g['items'], g['indptr'][1:-1])
+    lg.sampling.seed(2020)
+    assert np.array_equal(lg.sampling.sample_negative(nu, ni, tn, all_pos, 1), g['S'])
+    assert [lg.sampling.randint(1000) for _ in range(16)] == g['randints'].tolist()
+    S2 = lg.sampling.sample_negative_ByUser(g['by_users'].tolist(), ni, all_pos, 2)
+    assert S2.dtype == np.int32 and np.array_equal(S2, g['S_by_user'])
+    with pytest.raises(RuntimeError):
+        lg.sampling.sample_negative_ByUser([nu + 3], ni, all_pos, 1)
+
+
+def test_oracle_c_sampler_matches_reference_cpp():
+    """oracle/c/sampler_ref.c (what bench.py --impl reference draws its triples with) against the same recording."""
+    from oracle import lightgcn_oracle as orc
+    g = load_golden('sampler')
+    nu, ni, tn = int(g['n_users']), int(g['m_items']), int(g['train_num'])
+    assert np.array_equal(orc.sample_negative_ref(2020, nu, ni, tn, g['indptr'], g['items'], 1), g['S'])
+    assert [orc.randint_ref(1000) for _ in range(16)] == g['randints'].tolist()
+    assert np.array_equal(orc.sample_negative_by_user_ref(g['by_users'], ni, g['indptr'], g['items'], 2), g['S_by_user'])
+
+
 def test_sampler_through_dataset_api():
     import lgcn_b200 as lg
     ds = lg.synth.make_dataset('tiny')
