@@ -24,6 +24,17 @@
 //     counter, self-resetting) adds the partials in part order — a fixed summation order — and runs
 //     the epilogue.  No float atomics, one launch, results independent of scheduling.
 //
+//   * COLUMN-SLAB BLOCKING (graphs whose gathered table does not fit the 126 MB L2 — BASELINE config 5: N*d*4 = 3 GB).
+//     Unblocked, every non-zero is a 256-byte gather from HBM: nnz*256 B = 256 GB per layer against 14 GB algorithmic
+//     (18x amplification, measured 36 ms = HBM speed on the gathers).  Blocked: the columns are cut into slabs of
+//     <= ~64 MB of X; the layer is one launch per slab over the (row, slab) segments (the row's non-zeros are sorted by
+//     column, so a slab is a contiguous piece of the row, found by binary search at plan time); a segment starts from the
+//     row's running sum (plan.acc, 256 B read) unless it is the row's first, and writes it back unless it is the row's
+//     last, which runs the epilogue.  X is then read from HBM once per layer and the gathers hit L2; what is paid
+//     instead is the running-sum traffic, 512 B per (row, slab) pair.  The per-row summation order is unchanged
+//     (bit-identical to the unblocked kernel except for rows long enough to be segmented inside a slab).  Streams
+//     (indices, values, descriptors, running sums) carry an L2 evict-first policy so that they do not displace the slab.
+//
 // HBM roofline: B_spmm = 8*nnz + 4*(N+1) + 8*N*d bytes per layer.
 #include "common.cuh"
 
@@ -45,11 +56,30 @@ struct SpmmArgs {
     // (and of P in the Adam epilogue) over NVLink, so no separate all-gather pass re-reads and re-sends it
     int n_peers; float4* peerY[LGCN_MAX_PEERS]; float4* peerP[LGCN_MAX_PEERS];
     int multicast;      // peerY[0] / peerP[0] are NVSwitch multimem addresses: ONE store reaches every replica
+    // column-slab blocking: items carry flags (bit0 = not the row's first segment: start from acc[row]; bit1 = not its last:
+    // store the running sum to acc[row] instead of running the epilogue); acc == NULL -> every item is a whole row
+    float4* acc;
 };
+
+// L2 eviction policy for data that is touched once per launch (so that it does not displace the gathered slab)
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ld_f4_policy(const float4* p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_f4_policy(float4* p, const float4& v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 
 __device__ __forceinline__ bool mask_bit(const unsigned* m, int i) { return (__ldg(m + (i >> 5)) >> (i & 31)) & 1u; }
 
 static int g_variant = 0;      // tuning variant of the d=64 kernels (lgcn_debug_spmm_variant, profiling hook)
+static int g_blocked_variant = 0;   // items per group of the column-blocked kernel: 0 -> 4 (shipped), 1 -> 1, 2 -> 8, 3 -> 2 (variant 100 + x)
 
 __device__ __forceinline__ float4 gather_f4(const float4* p) {
     float4 v;
@@ -57,24 +87,39 @@ __device__ __forceinline__ float4 gather_f4(const float4* p) {
     return v;
 }
 
-template <int D, int LANES, int UNROLL>
+__device__ __forceinline__ unsigned long long policy_evict_normal() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ int ld_stream_i32_policy(const int* p, unsigned long long pol) {
+    int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ float ld_stream_f32_policy(const float* p, unsigned long long pol) {
+    float v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v;
+}
+
+// HINT (blocked plans): the (col,val) stream carries an L2 evict-first policy so that it does not displace the slab of X
+template <int D, int LANES, int UNROLL, bool HINT>
 __device__ __forceinline__ void accumulate_item(const SpmmArgs& a, int start, int end, int lane,
                                                 unsigned gmask, float4 (&acc)[D / 4 / LANES]) {
     constexpr int VEC = D / 4, VPL = VEC / LANES;
     static_assert(LANES % UNROLL == 0, "UNROLL must divide the group width");
     if (start >= end) return;
+    unsigned long long pol = 0;
+    if constexpr (HINT) pol = policy_evict_first();
+    auto ld_c = [&](const int* p) { if constexpr (HINT) return ld_stream_i32_policy(p, pol); else return ld_stream_i32(p); };
+    auto ld_v = [&](const float* p) { if constexpr (HINT) return ld_stream_f32_policy(p, pol); else return ld_stream_f32(p); };
     int cnt = min(LANES, end - start);
     int j = start + min(lane, cnt - 1);                     // lanes past the end: last valid entry, weight 0
-    int c_nxt = ld_stream_i32(a.indices + j);
-    float v_nxt = lane < cnt ? ld_stream_f32(a.vals + j) : 0.f;
+    int c_nxt = ld_c(a.indices + j);
+    float v_nxt = lane < cnt ? ld_v(a.vals + j) : 0.f;
     for (int base = start; base < end; base += LANES) {
         const int c = c_nxt; const float v = v_nxt;
         const int cur = cnt;
         if (base + LANES < end) {
             cnt = min(LANES, end - base - LANES);
             j = base + LANES + min(lane, cnt - 1);
-            c_nxt = ld_stream_i32(a.indices + j);
-            v_nxt = lane < cnt ? ld_stream_f32(a.vals + j) : 0.f;
+            c_nxt = ld_c(a.indices + j);
+            v_nxt = lane < cnt ? ld_v(a.vals + j) : 0.f;
         }
 #pragma unroll 1
         for (int t = 0; t < cur; t += UNROLL) {
@@ -173,36 +218,24 @@ __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, c
     }
 }
 
-template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB, bool MASKED = false>
-__global__ void __launch_bounds__(THREADS, MINB)
-spmm_kernel(const __grid_constant__ SpmmArgs a) {
+// Everything after an item's products are summed.  Whole-row item: epilogue.  Blocked plans (BLOCKED): a whole segment that is
+// not its row's last stores the running sum to a.acc instead.  Part of a segmented (hub) row/segment: the partial goes to
+// a.partials and the part that arrives last adds them in part order (after the running sum, if any) and finishes the row.
+template <int D, int LANES, bool ADAM, bool BLOCKED>
+__device__ __forceinline__ void finish_item(const SpmmArgs& a, int row, int lane, unsigned gmask, int seg_ref, float4 (&acc)[D / 4 / LANES]) {
     constexpr int VEC = D / 4, VPL = VEC / LANES;
-    constexpr int GROUPS = THREADS / LANES;
-    static_assert(VEC % LANES == 0 && LANES <= 32 && VPL >= 1, "bad group width");
-    const int lane = threadIdx.x % LANES;
-    const unsigned gmask = (LANES == 32) ? 0xffffffffu
-                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
-    const long long gidx = (long long)blockIdx.x * GROUPS + threadIdx.x / LANES;
-    if (gidx >= a.n_items) return;
-    int row, start, end, seg_ref;
-    if (a.items != nullptr) {
-        const int4 it = __ldg(a.items + gidx);
-        row = it.x; start = it.y; end = it.z; seg_ref = it.w;
-    } else {
-        row = (int)gidx; start = __ldg(a.indptr + row); end = __ldg(a.indptr + row + 1); seg_ref = -1;
-    }
-    if (a.row_mask != nullptr && !mask_bit(a.row_mask, row)) return;     // dead row: nobody reads it this step
-    float4 acc[VPL];
-#pragma unroll
-    for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
-    if constexpr (MASKED) accumulate_item_masked<D, LANES, UNROLL>(a, start, end, lane, gmask, (threadIdx.x & 31) / LANES * LANES, acc);
-    else accumulate_item<D, LANES, UNROLL>(a, start, end, lane, gmask, acc);
     if (seg_ref < 0) {
-        epilogue<D, LANES, ADAM>(a, row, lane, acc);
+        if (BLOCKED && ((-1 - seg_ref) & 2)) {
+            const unsigned long long pol = policy_evict_first();
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) st_f4_policy(a.acc + (size_t)row * VEC + lane + p * LANES, acc[p], pol);
+        } else {
+            epilogue<D, LANES, ADAM>(a, row, lane, acc);
+        }
         return;
     }
     const int4 si = __ldg(a.seginfo + seg_ref);
-    const int part = si.x, n_parts = si.y, slot_base = si.z, long_id = si.w;
+    const int part = si.x, n_parts = si.y, slot_base = si.z, long_id = si.w & 0x0fffffff, sflags = BLOCKED ? (int)((unsigned)si.w >> 28) : 0;
     float4* mine = a.partials + (size_t)(slot_base + part) * VEC + lane;
 #pragma unroll
     for (int p = 0; p < VPL; ++p) mine[p * LANES] = acc[p];
@@ -213,8 +246,13 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
     prev = __shfl_sync(gmask, prev, 0, LANES);
     if (prev != n_parts - 1) return;
     __threadfence();
+    if (sflags & 1) {                                                     // the row's running sum comes first, then the parts in order
 #pragma unroll
-    for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+        for (int p = 0; p < VPL; ++p) acc[p] = ld_cg_f4(a.acc + (size_t)row * VEC + lane + p * LANES);
+    } else {
+#pragma unroll
+        for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+    }
     // fixed summation order (part 0, 1, 2, ...), but the loads of several parts are in flight together: with one part per
     // iteration every partial cost an L2 round trip, which made the tail of a hub row proportional to its part count
     constexpr int RB = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);    // 8 float4 of partials per lane in flight
@@ -239,8 +277,118 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
 #pragma unroll
         for (int p = 0; p < VPL; ++p) f4_add(acc[p], ld_cg_f4(src + p * LANES));
     }
-    epilogue<D, LANES, ADAM>(a, row, lane, acc);
+    if (sflags & 2) {
+#pragma unroll
+        for (int p = 0; p < VPL; ++p) a.acc[(size_t)row * VEC + lane + p * LANES] = acc[p];
+    } else {
+        epilogue<D, LANES, ADAM>(a, row, lane, acc);
+    }
     if (lane == 0) a.counters[long_id] = 0;                  // ready for the next launch
+}
+
+template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB, bool MASKED = false>
+__global__ void __launch_bounds__(THREADS, MINB)
+spmm_kernel(const __grid_constant__ SpmmArgs a) {
+    constexpr int VEC = D / 4, VPL = VEC / LANES;
+    constexpr int GROUPS = THREADS / LANES;
+    static_assert(VEC % LANES == 0 && LANES <= 32 && VPL >= 1, "bad group width");
+    const int lane = threadIdx.x % LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu
+                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+    const long long gidx = (long long)blockIdx.x * GROUPS + threadIdx.x / LANES;
+    if (gidx >= a.n_items) return;
+    int row, start, end, seg_ref;
+    if (a.items != nullptr) {
+        const int4 it = __ldg(a.items + gidx);
+        row = it.x; start = it.y; end = it.z; seg_ref = it.w;
+    } else {
+        row = (int)gidx; start = __ldg(a.indptr + row); end = __ldg(a.indptr + row + 1); seg_ref = -1;
+    }
+    if (a.row_mask != nullptr && !mask_bit(a.row_mask, row)) return;     // dead row: nobody reads it this step
+    float4 acc[VPL];
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+    if constexpr (MASKED) accumulate_item_masked<D, LANES, UNROLL>(a, start, end, lane, gmask, (threadIdx.x & 31) / LANES * LANES, acc);
+    else accumulate_item<D, LANES, UNROLL, false>(a, start, end, lane, gmask, acc);
+    finish_item<D, LANES, ADAM, false>(a, row, lane, gmask, seg_ref, acc);
+}
+
+// ---- column-slab blocked launches --------------------------------------------------------------------------------
+// The items of a slab launch are SHORT (a row's entries inside one 64 MB slab of columns: ~3-40) and each one is a dependent
+// chain  descriptor -> (columns, values, running sum) -> gathers -> store.  With one item per group (spmm_kernel) a slab launch
+// is latency-bound: measured 4.3 TB/s of DRAM traffic on BASELINE config 5, no faster than the unblocked kernel although it
+// moves 40 % fewer bytes (profiles/r2_blocked_v1_ncu_dram.csv).  Here a group walks IPG consecutive items (same length: the
+// list is sorted by length) as a software pipeline: while item k is gathered, the descriptor of item k+2 and the first
+// (col,val) chunk of item k+1 are already in flight.
+template <int D, int LANES, int UNROLL, bool ADAM, int IPG>
+__global__ void __launch_bounds__(128, 8)
+spmm_blocked_kernel(const __grid_constant__ SpmmArgs a) {
+    constexpr int VEC = D / 4, VPL = VEC / LANES, GROUPS = 128 / LANES;
+    static_assert(VEC % LANES == 0 && LANES <= 32 && VPL >= 1 && LANES % UNROLL == 0, "bad group width");
+    const int lane = threadIdx.x % LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+    const long long first = ((long long)blockIdx.x * GROUPS + threadIdx.x / LANES) * IPG;
+    if (first >= a.n_items) return;
+    const int n_mine = (int)min((long long)IPG, (long long)a.n_items - first);
+    const unsigned long long pol = policy_evict_first();
+    const int4* items = a.items + first;
+    int4 it = __ldg(items);
+    int4 it_n = n_mine > 1 ? __ldg(items + 1) : it;
+    // first (col,val) chunk of item 0
+    int cnt = min(LANES, it.z - it.y);
+    int c = 0; float v = 0.f;
+    if (cnt > 0) { const int j = it.y + min(lane, cnt - 1); c = ld_stream_i32_policy(a.indices + j, pol); v = lane < cnt ? ld_stream_f32_policy(a.vals + j, pol) : 0.f; }
+#pragma unroll 1
+    for (int k = 0; k < n_mine; ++k) {
+        // stage A(k+2): descriptor;  stage B(k+1): first chunk of the next item
+        const int4 it_nn = (k + 2 < n_mine) ? __ldg(items + k + 2) : it_n;
+        int cnt_n = 0, c_n = 0; float v_n = 0.f;
+        if (k + 1 < n_mine) {
+            cnt_n = min(LANES, it_n.z - it_n.y);
+            if (cnt_n > 0) { const int j = it_n.y + min(lane, cnt_n - 1); c_n = ld_stream_i32_policy(a.indices + j, pol); v_n = lane < cnt_n ? ld_stream_f32_policy(a.vals + j, pol) : 0.f; }
+        }
+        // stage C(k)
+        const int row = it.x, start = it.y, end = it.z, seg_ref = it.w;
+        if (a.row_mask == nullptr || mask_bit(a.row_mask, row)) {
+            float4 acc[VPL];
+            if (seg_ref < 0 && ((-1 - seg_ref) & 1)) {
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) acc[p] = ld_f4_policy(a.acc + (size_t)row * VEC + lane + p * LANES, pol);
+            } else {
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
+            }
+            int cc = c; float vv = v; int cur = cnt;
+            for (int base = start; base < end; base += LANES) {
+                int c2 = 0; float v2 = 0.f; int cnt2 = 0;
+                if (base + LANES < end) {                      // items longer than one chunk: in-item prefetch, as in spmm_kernel
+                    cnt2 = min(LANES, end - base - LANES);
+                    const int j = base + LANES + min(lane, cnt2 - 1);
+                    c2 = ld_stream_i32_policy(a.indices + j, pol);
+                    v2 = lane < cnt2 ? ld_stream_f32_policy(a.vals + j, pol) : 0.f;
+                }
+#pragma unroll 1
+                for (int t = 0; t < cur; t += UNROLL) {
+                    float4 x[UNROLL][VPL]; float w[UNROLL];
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u) {
+                        const int col = __shfl_sync(gmask, cc, t + u, LANES);
+                        w[u] = __shfl_sync(gmask, vv, t + u, LANES);
+                        const float4* src = a.X + (size_t)col * VEC + lane;
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) x[u][p] = gather_f4(src + p * LANES);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) f4_fma(acc[p], w[u], x[u][p]);
+                }
+                cc = c2; vv = v2; cur = cnt2;
+            }
+            finish_item<D, LANES, ADAM, true>(a, row, lane, gmask, seg_ref, acc);
+        }
+        it = it_n; it_n = it_nn; c = c_n; v = v_n; cnt = cnt_n;
+    }
 }
 
 // ---- plan kernels -------------------------------------------------------------------------
@@ -258,11 +406,34 @@ __device__ __forceinline__ void split_row(int deg, int seg_len, int& n_parts, in
     n_parts = (deg + len - 1) / len;
 }
 
-// counts: {n_long, n_segs, longest item}
-__global__ void plan_count_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* counts) {
+// Which piece of every row a plan covers: the whole row (indices == nullptr), or — column-slab blocking — the entries whose
+// column lies in [col_lo, col_hi) (contiguous, because a row's entries are sorted by column).
+struct Slab { const int* indices; int col_lo, col_hi, is_first; };
+
+__device__ __forceinline__ int lower_bound_col(const int* __restrict__ idx, int lo, int hi, int key) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(idx + mid) < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// false: row r has no item in this plan.  flags: bit0 = the segment is not the row's first, bit1 = not its last.
+__device__ __forceinline__ bool slab_segment(const int* __restrict__ indptr, int r, const Slab& sl, int& s, int& e, int& flags) {
+    const int rb = indptr[r], re = indptr[r + 1];
+    if (sl.indices == nullptr) { s = rb; e = re; flags = 0; return true; }
+    s = lower_bound_col(sl.indices, rb, re, sl.col_lo);
+    e = lower_bound_col(sl.indices, s, re, sl.col_hi);
+    flags = (s > rb ? 1 : 0) | (e < re ? 2 : 0);
+    if (e > s) return true;
+    return rb == re && sl.is_first;          // an empty row still needs its epilogue: once, in the first slab
+}
+
+// counts: {n_long, n_segs, longest item, rows with an item}
+__global__ void plan_count_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, Slab sl, int* counts) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    const int deg = indptr[r + 1] - indptr[r];
+    int s, e, flags;
+    if (!slab_segment(indptr, r, sl, s, e, flags)) return;
+    atomicAdd(counts + 3, 1);
+    const int deg = e - s;
     if (deg > seg_len) {
         int n_parts, len; split_row(deg, seg_len, n_parts, len);
         atomicAdd(counts + 0, 1);
@@ -273,10 +444,12 @@ __global__ void plan_count_kernel(const int* __restrict__ indptr, int n_rows, in
     }
 }
 
-__global__ void plan_hist_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, int* bins) {   // bins[0..max_len]
+__global__ void plan_hist_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, Slab sl, int* bins) {   // bins[0..max_len]
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    const int deg = indptr[r + 1] - indptr[r];
+    int s, e, flags;
+    if (!slab_segment(indptr, r, sl, s, e, flags)) return;
+    const int deg = e - s;
     if (deg <= seg_len) { atomicAdd(bins + deg, 1); return; }
     int n_parts, len; split_row(deg, seg_len, n_parts, len);
     for (int p = 0; p < n_parts; ++p) {
@@ -292,14 +465,16 @@ __global__ void plan_offsets_kernel(const int* __restrict__ bins, int max_len, i
     for (int l = max_len; l >= 0; --l) { offsets[l] = run; run += bins[l]; }
 }
 
-__global__ void plan_scatter_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, const int* __restrict__ offsets,
+__global__ void plan_scatter_kernel(const int* __restrict__ indptr, int n_rows, int seg_len, Slab sl, const int* __restrict__ offsets,
                                     int* cursors, int* long_cursor, int4* items, int4* seginfo) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    const int s = indptr[r], deg = indptr[r + 1] - s;
+    int s, e, flags;
+    if (!slab_segment(indptr, r, sl, s, e, flags)) return;
+    const int deg = e - s;
     if (deg <= seg_len) {
         const int pos = offsets[deg] + atomicAdd(cursors + deg, 1);
-        items[pos] = make_int4(r, s, s + deg, -1);
+        items[pos] = make_int4(r, s, s + deg, -1 - flags);
         return;
     }
     int n_parts, len; split_row(deg, seg_len, n_parts, len);
@@ -307,7 +482,7 @@ __global__ void plan_scatter_kernel(const int* __restrict__ indptr, int n_rows, 
     const int slot_base = atomicAdd(long_cursor + 1, n_parts);
     for (int p = 0; p < n_parts; ++p) {
         const int b = s + p * len, l = min(len, deg - p * len);
-        seginfo[slot_base + p] = make_int4(p, n_parts, slot_base, long_id);
+        seginfo[slot_base + p] = make_int4(p, n_parts, slot_base, long_id | (flags << 28));
         const int pos = offsets[l] + atomicAdd(cursors + l, 1);
         items[pos] = make_int4(r, b, b + l, slot_base + p);
     }
@@ -330,8 +505,29 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
     return 0;
 }
 
+template <int D, int LANES, int UNROLL, bool ADAM>
+static int launch_blocked(const SpmmArgs& a, cudaStream_t st) {
+    if (a.n_items == 0) return 0;
+    if (a.col_mask != nullptr) return fail("spmm: col_mask is not supported with a column-blocked plan");
+    auto grid = [&](int ipg) { return (unsigned)((((long long)a.n_items + ipg - 1) / ipg + (128 / LANES) - 1) / (128 / LANES)); };
+    if (g_blocked_variant == 1) spmm_blocked_kernel<D, LANES, UNROLL, ADAM, 1><<<grid(1), 128, 0, st>>>(a);
+    else if (g_blocked_variant == 2) spmm_blocked_kernel<D, LANES, UNROLL, ADAM, 8><<<grid(8), 128, 0, st>>>(a);
+    else if (g_blocked_variant == 3) spmm_blocked_kernel<D, LANES, UNROLL, ADAM, 2><<<grid(2), 128, 0, st>>>(a);
+    else spmm_blocked_kernel<D, LANES, UNROLL, ADAM, 4><<<grid(4), 128, 0, st>>>(a);
+    LGCN_CHECK_LAUNCH("spmm_blocked_kernel");
+    return 0;
+}
+
 template <bool ADAM>
 static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
+    if (a.acc != nullptr) switch (d) {            // column-slab blocked plan: the pipelined short-item kernel
+        case 16:  return launch_blocked<16, 4, 2, ADAM>(a, st);
+        case 32:  return launch_blocked<32, 4, 2, ADAM>(a, st);
+        case 64:  return launch_blocked<64, 8, 2, ADAM>(a, st);
+        case 128: return launch_blocked<128, 16, 2, ADAM>(a, st);
+        case 256: return launch_blocked<256, 32, 2, ADAM>(a, st);
+        default:  return fail("spmm: d=%d unsupported (16,32,64,128,256)", d);
+    }
     switch (d) {
         case 16:  return launch_cfg<16, 4, 4, ADAM, 128, 8>(a, st);
         case 32:  return launch_cfg<32, 4, 4, ADAM, 128, 8>(a, st);
@@ -385,9 +581,11 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
         a.items = reinterpret_cast<const int4*>(plan->items); a.n_items = plan->n_items;
         a.seginfo = reinterpret_cast<const int4*>(plan->seginfo);
         a.counters = plan->counters; a.partials = reinterpret_cast<float4*>(plan->partials);
+        LGCN_CHECK_ARG(((uintptr_t)plan->acc % 16) == 0, "spmm: plan.acc must be 16-byte aligned");
+        a.acc = reinterpret_cast<float4*>(plan->acc);
     } else {
         LGCN_CHECK_ARG(indptr || n_rows == 0, "spmm: indptr is null and no plan was given");
-        a.items = nullptr; a.n_items = n_rows; a.seginfo = nullptr; a.counters = nullptr; a.partials = nullptr;
+        a.items = nullptr; a.n_items = n_rows; a.seginfo = nullptr; a.counters = nullptr; a.partials = nullptr; a.acc = nullptr;
     }
     a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr;
     a.row_mask = row_mask; a.col_mask = col_mask;
@@ -469,16 +667,29 @@ extern "C" int lgcn_debug_gather_rows(const float* X, const int32_t* idx, int64_
     return 0;
 }
 
-extern "C" int lgcn_debug_spmm_variant(int variant) { const int old = g_variant; g_variant = variant; return old; }
+extern "C" int lgcn_debug_spmm_variant(int variant) {
+    if (variant >= 100) { const int old = 100 + g_blocked_variant; g_blocked_variant = variant - 100; return old; }
+    const int old = g_variant; g_variant = variant; return old;
+}
 
-extern "C" int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
-                                    int32_t* counts_out, lgcn_stream_t stream) {
+static int plan_count_impl(const int32_t* indptr, int32_t n_rows, int32_t seg_len, const Slab& sl, int32_t* counts_out, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(indptr && counts_out && seg_len > 0 && n_rows >= 0, "spmm_plan_count: bad arguments");
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(counts_out, 0, 4 * sizeof(int32_t), st);
-    if (n_rows > 0) plan_count_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(indptr, n_rows, seg_len, counts_out);
+    if (n_rows > 0) plan_count_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(indptr, n_rows, seg_len, sl, counts_out);
     LGCN_CHECK_LAUNCH("plan_count_kernel");
     return 0;
+}
+
+extern "C" int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
+                                    int32_t* counts_out, lgcn_stream_t stream) {
+    return plan_count_impl(indptr, n_rows, seg_len, Slab{nullptr, 0, 0, 1}, counts_out, stream);
+}
+
+extern "C" int lgcn_spmm_plan_count_slab(const int32_t* indptr, const int32_t* indices, int32_t n_rows, int32_t seg_len,
+                                         int32_t col_lo, int32_t col_hi, int32_t is_first_slab, int32_t* counts_out, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(indices && col_lo <= col_hi, "spmm_plan_count_slab: bad arguments");
+    return plan_count_impl(indptr, n_rows, seg_len, Slab{indices, col_lo, col_hi, is_first_slab ? 1 : 0}, counts_out, stream);
 }
 
 extern "C" size_t lgcn_spmm_plan_workspace_bytes(int32_t max_len) {
@@ -486,9 +697,8 @@ extern "C" size_t lgcn_spmm_plan_workspace_bytes(int32_t max_len) {
     return sizeof(int32_t) * (4 + 3 * ((size_t)max_len + 1));
 }
 
-extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len, int32_t max_len,
-                                   int32_t* items_out, int32_t* seginfo_out,
-                                   void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+static int plan_fill_impl(const int32_t* indptr, int32_t n_rows, int32_t seg_len, int32_t max_len, const Slab& sl,
+                          int32_t* items_out, int32_t* seginfo_out, void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(indptr && items_out && seg_len > 0 && n_rows >= 0 && max_len >= 0, "spmm_plan_fill: bad arguments");
     LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_spmm_plan_workspace_bytes(max_len), "spmm_plan_fill: workspace too small");
     LGCN_CHECK_ARG(((uintptr_t)items_out % 16) == 0 && ((uintptr_t)seginfo_out % 16) == 0, "spmm_plan_fill: outputs must be 16-byte aligned");
@@ -498,14 +708,29 @@ extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_
     cudaMemsetAsync(workspace, 0, lgcn_spmm_plan_workspace_bytes(max_len), st);
     if (n_rows == 0) return 0;
     const unsigned nb = (n_rows + 255) / 256;
-    plan_hist_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, bins);
+    plan_hist_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, sl, bins);
     LGCN_CHECK_LAUNCH("plan_hist_kernel");
     plan_offsets_kernel<<<1, 32, 0, st>>>(bins, max_len, offsets);
     LGCN_CHECK_LAUNCH("plan_offsets_kernel");
-    plan_scatter_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, offsets, cursors, long_cursor,
+    plan_scatter_kernel<<<nb, 256, 0, st>>>(indptr, n_rows, seg_len, sl, offsets, cursors, long_cursor,
                                             reinterpret_cast<int4*>(items_out), reinterpret_cast<int4*>(seginfo_out));
     LGCN_CHECK_LAUNCH("plan_scatter_kernel");
     return 0;
+}
+
+extern "C" int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len, int32_t max_len,
+                                   int32_t* items_out, int32_t* seginfo_out,
+                                   void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    return plan_fill_impl(indptr, n_rows, seg_len, max_len, Slab{nullptr, 0, 0, 1}, items_out, seginfo_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int lgcn_spmm_plan_fill_slab(const int32_t* indptr, const int32_t* indices, int32_t n_rows, int32_t seg_len, int32_t max_len,
+                                        int32_t col_lo, int32_t col_hi, int32_t is_first_slab,
+                                        int32_t* items_out, int32_t* seginfo_out,
+                                        void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(indices && col_lo <= col_hi, "spmm_plan_fill_slab: bad arguments");
+    return plan_fill_impl(indptr, n_rows, seg_len, max_len, Slab{indices, col_lo, col_hi, is_first_slab ? 1 : 0}, items_out, seginfo_out,
+                          workspace, workspace_bytes, stream);
 }
 
 extern "C" int lgcn_spmm_f32(const int32_t* indptr, const int32_t* indices, const float* vals,

@@ -12,6 +12,14 @@ import torch
 from . import _lib
 
 DEFAULT_SEG_LEN = 128
+# Column-slab blocking of K1 (csrc/spmm.cu) for gathered tables that do not fit L2: slabs of at most SLAB_BYTES stay resident
+# in the 126 MB L2 next to the streams of one launch.  OFF by default (LGCN_BLOCKING=1 turns it on for tables larger than
+# BLOCK_THRESHOLD_BYTES; CSRGraph.block_plans(d, slab_bytes=...) forces it): measured on BASELINE config 5 it cuts the DRAM
+# traffic of a layer from 245 GB to 155 GB but the layer takes the same 35-36 ms — every gathered byte still has to cross
+# L2 -> SM, and gathers + fills + running sums together saturate the L2 slices (profiles/README.md, round 2).
+SLAB_BYTES = int(os.environ.get('LGCN_SLAB_MB', '64')) << 20
+BLOCK_THRESHOLD_BYTES = int(os.environ.get('LGCN_BLOCK_THRESHOLD_MB', '112')) << 20
+BLOCKING_DEFAULT = os.environ.get('LGCN_BLOCKING', '0') == '1'
 
 
 def _stream():
@@ -74,6 +82,59 @@ class CSRGraph:
         self._partials = None
         self._plan = None
         self.use_plan = True
+        self.use_blocking = True      # honoured only for plans that exist: automatic planning needs BLOCKING_DEFAULT
+        self._blocks = None           # (d_max, [SpmmPlan per non-empty slab], keep-alive tensors)
+
+    def block_plans(self, d, slab_bytes=None):
+        """Column-slab plans for gathers from an (n_cols, d) fp32 table that does not fit L2, else None.
+        One layer = one launch per returned plan, in order (ascending columns)."""
+        if not (self.use_plan and self.use_blocking) or self.n_rows == 0:
+            return None
+        if self._blocks is not None and self._blocks[0] >= d and slab_bytes is None:
+            return self._blocks[1]                    # planned before (automatically, or forced with an explicit slab size)
+        if slab_bytes is None and (not BLOCKING_DEFAULT or self.n_cols * d * 4 <= BLOCK_THRESHOLD_BYTES):
+            return None
+        lib = _lib.load()
+        slab_bytes = int(slab_bytes or SLAB_BYTES)
+        n_slabs = max(1, -(-self.n_cols * d * 4 // slab_bytes))
+        slab_cols = -(-self.n_cols // n_slabs)
+        dev = self.device
+        acc = torch.empty(self.n_rows * d, dtype=torch.float32, device=dev)
+        counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        plans, keep, max_long, max_segs = [], [acc], 1, 1
+        specs = []
+        for sidx in range(n_slabs):
+            lo, hi = sidx * slab_cols, min(self.n_cols, (sidx + 1) * slab_cols)
+            _lib.check(lib.lgcn_spmm_plan_count_slab(_p(self.indptr), _p(self.indices), self.n_rows, self.seg_len, lo, hi, int(sidx == 0),
+                                                     _p(counts), _stream()), "spmm_plan_count_slab")
+            n_long, n_segs, max_len, n_with = (int(v) for v in counts.cpu().tolist())          # setup-time sync, once per slab
+            n_items = n_with - n_long + n_segs
+            if n_items == 0:
+                continue
+            items = torch.empty(n_items * 4, dtype=torch.int32, device=dev)
+            seginfo = torch.zeros(max(n_segs, 1) * 4, dtype=torch.int32, device=dev)
+            ws_bytes = lib.lgcn_spmm_plan_workspace_bytes(max_len)
+            ws = torch.zeros((ws_bytes + 3) // 4, dtype=torch.int32, device=dev)
+            _lib.check(lib.lgcn_spmm_plan_fill_slab(_p(self.indptr), _p(self.indices), self.n_rows, self.seg_len, max_len, lo, hi, int(sidx == 0),
+                                                    _p(items), _p(seginfo), _p(ws), ws.numel() * 4, _stream()), "spmm_plan_fill_slab")
+            keep += [items, seginfo]
+            max_long, max_segs = max(max_long, n_long), max(max_segs, n_segs)
+            specs.append((n_long, n_segs, n_items, items, seginfo))
+        counters = torch.zeros(max_long, dtype=torch.int32, device=dev)
+        partials = torch.empty(max_segs * d, dtype=torch.float32, device=dev)
+        keep += [counters, partials]
+        for n_long, n_segs, n_items, items, seginfo in specs:
+            pl = _lib.SpmmPlan()
+            pl.seg_len, pl.n_long, pl.n_segs, pl.n_items, pl.d_max = self.seg_len, n_long, n_segs, n_items, d
+            pl.items, pl.seginfo = items.data_ptr(), seginfo.data_ptr()
+            pl.counters, pl.partials, pl.acc = counters.data_ptr(), partials.data_ptr(), acc.data_ptr()
+            plans.append(pl)
+        self._blocks = (d, plans, keep)
+        self.n_slabs, self.n_block_items = n_slabs, sum(sp[2] for sp in specs)
+        return plans
+
+    def clear_blocking(self):
+        self._blocks = None
 
     def plan(self, d):
         if not self.use_plan:
@@ -280,6 +341,13 @@ def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None, pe
     arr, nz = _z_array(zs)
     for z in (zs or []):
         _need(z, torch.float32, "z", 2)
+    blocks = g.block_plans(d) if col_mask is None else None
+    if blocks:        # the gathered table does not fit L2: one launch per column slab, running sums carried in plan.acc
+        peers = _peers_struct(peer_y, None, mc_y)
+        for pl in blocks:
+            _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
+                                         float(alpha), float(beta), arr, nz, byref(pl), _p(row_mask), None, peers, _stream()), "spmm")
+        return Y
     _lib.check(lib.lgcn_spmm_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                  float(alpha), float(beta), arr, nz, g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(peer_y, None, mc_y), _stream()), "spmm")
     return Y
@@ -292,6 +360,14 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_
     for t, n in ((X, "X"), (P, "P"), (M, "M"), (V, "V")):
         _need(t, torch.float32, n, 2)
     arr, nz = _z_array(zs)
+    blocks = g.block_plans(d) if col_mask is None else None
+    if blocks:
+        peers = _peers_struct(None, peer_p, 0, mc_p)
+        for pl in blocks:
+            _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
+                                              float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
+                                              byref(pl), _p(row_mask), None, peers, _stream()), "spmm_adam")
+        return
     _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                       float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
                                       g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p, 0, mc_p), _stream()), "spmm_adam")

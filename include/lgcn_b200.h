@@ -124,6 +124,8 @@ typedef struct {
     const int32_t* seginfo;   /* int32[4*n_segs]: part,n_parts,slot_base,long_id                    */
     int32_t* counters;        /* int32[n_long], zero-initialised, self-resetting                   */
     float* partials;          /* float32[n_segs*d_max]                                             */
+    float* acc;               /* column-slab blocking (lgcn_spmm_plan_*_slab): float32[n_rows*d_max] running sums carried from one
+                                 slab's launch to the next; NULL for a whole-row plan                                      */
 } lgcn_spmm_plan_t;
 
 /* Fused SpMM + all-gather for the row partition: pointers to the PEER GPUs' copies of Y (and of P for
@@ -149,9 +151,21 @@ typedef struct {
 int lgcn_rank_barrier(uint32_t* flags_local, void* const* peer_flags_host, int32_t rank, int32_t world,
                       uint32_t* epoch_dev, int32_t* err_dev, int32_t timeout_ms, lgcn_stream_t stream);
 
-/* counts_out int32[4] = {n_long, n_segs, longest item, -} (device).  A row is cut into at most 2048 segments. */
+/* counts_out int32[4] = {n_long, n_segs, longest item, rows with an item} (device).  A row is cut into at most 2048 segments. */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
                          int32_t* counts_out, lgcn_stream_t stream);
+/* COLUMN-SLAB BLOCKING for graphs whose gathered table exceeds L2 (BASELINE config 5).  The *_slab variants plan only the
+ * entries of each row whose column lies in [col_lo, col_hi) — contiguous, since rows are sorted by column.  One layer is
+ * then one lgcn_spmm_f32 launch per slab IN ASCENDING COLUMN ORDER, all with the same plan.acc: a segment that is not its
+ * row's first starts from acc[row], one that is not its row's last stores its running sum there, the last runs the epilogue
+ * (empty rows get theirs from the slab planned with is_first_slab != 0).  X is read from HBM once per layer instead of once
+ * per non-zero; the summation order of a row is unchanged.  n_items = counts[3] - counts[0] + counts[1]. */
+int lgcn_spmm_plan_count_slab(const int32_t* indptr, const int32_t* indices, int32_t n_rows, int32_t seg_len,
+                              int32_t col_lo, int32_t col_hi, int32_t is_first_slab, int32_t* counts_out, lgcn_stream_t stream);
+int lgcn_spmm_plan_fill_slab(const int32_t* indptr, const int32_t* indices, int32_t n_rows, int32_t seg_len, int32_t max_len,
+                             int32_t col_lo, int32_t col_hi, int32_t is_first_slab,
+                             int32_t* items_out, int32_t* seginfo_out,
+                             void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
 size_t lgcn_spmm_plan_workspace_bytes(int32_t max_len);
 /* fills items_out int32[4*n_items] and seginfo_out int32[4*n_segs]; max_len = counts_out[2] */
 int lgcn_spmm_plan_fill(const int32_t* indptr, int32_t n_rows, int32_t seg_len, int32_t max_len,

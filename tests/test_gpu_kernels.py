@@ -132,6 +132,69 @@ def test_row_block_build_equals_rows_of_the_full_build(lg, orc, parts, chunked):
     assert tot == full.nnz
 
 
+@pytest.mark.parametrize("seg_len,slab_rows", [(4096, 97), (4096, 700), (16, 211), (128, 5000)])
+def test_spmm_column_slab_blocking_equals_unblocked(lg, orc, seg_len, slab_rows):
+    """K1 with column-slab blocking (graphs whose gathered table exceeds L2): one launch per slab, running sums carried
+    between launches.  A row's summation order is unchanged, so with no row segmented inside a slab (seg_len 4096) the
+    result is BIT-identical to the unblocked kernel; with segmentation it agrees to rounding.  Covers empty rows, slabs
+    without any entry, hub rows, the mean epilogue with own-row addends, and the Adam epilogue."""
+    rng = np.random.default_rng(seg_len + slab_rows)
+    nu, ni, d = 900, 1300, 64
+    tu, ti = random_edges(rng, nu, ni - 300, 20000, dup=50)            # 300 items never seen: empty rows and an empty slab
+    tu = np.concatenate([tu, np.zeros(1500, np.int64)]); ti = np.concatenate([ti, rng.integers(0, ni - 300, 1500)])   # a hub user
+    N = nu + ni
+    g0 = build(lg, tu, ti, nu, ni, seg_len=seg_len)
+    g1 = build(lg, tu, ti, nu, ni, seg_len=seg_len)
+    plans = g1.block_plans(d, slab_bytes=slab_rows * d * 4)
+    assert plans is not None and len(plans) >= 1 and len(plans) <= -(-N // slab_rows)
+    X = torch.randn(N, d, device='cuda'); Z1 = torch.randn(N, d, device='cuda'); Z2 = torch.randn(N, d, device='cuda')
+    Y0, Y1 = torch.full((N, d), 7.0, device='cuda'), torch.full((N, d), -3.0, device='cuda')
+    lg.ops.spmm(g0, X, Y0, 0.25, 0.5, [Z1, Z2]); lg.ops.spmm(g1, X, Y1, 0.25, 0.5, [Z1, Z2])
+    if seg_len == 4096:
+        assert torch.equal(Y0, Y1)
+    else:
+        assert rel_err(Y1.cpu().numpy(), Y0.cpu().numpy()) < 2e-6
+    ref = 0.25 * orc.spmm(*(a.cpu().numpy() for a in (g0.indptr, g0.indices, g0.vals)), X.cpu().numpy().astype(np.float64)) + 0.5 * (Z1 + Z2).cpu().numpy()
+    assert rel_err(Y1.cpu().numpy(), ref) < TOL
+    # row mask: masked-out rows are left untouched by every slab launch
+    mask = torch.from_numpy(rng.integers(0, 2**31, (N + 31) // 32).astype(np.int32)).cuda()
+    Ym0, Ym1 = torch.full((N, d), 7.0, device='cuda'), torch.full((N, d), 7.0, device='cuda')
+    lg.ops.spmm(g0, X, Ym0, row_mask=mask); lg.ops.spmm(g1, X, Ym1, row_mask=mask)
+    assert torch.equal(Ym0, Ym1) if seg_len == 4096 else rel_err(Ym1.cpu().numpy(), Ym0.cpu().numpy()) < 2e-6
+    # Adam epilogue
+    sc = lg.ops.adam_scalars(X.device, 1e-3); lg.ops.adam_tick(sc)
+    P0 = torch.randn(N, d, device='cuda'); M0 = torch.zeros_like(P0); V0 = torch.zeros_like(P0)
+    P1, M1, V1 = P0.clone(), M0.clone(), V0.clone()
+    lg.ops.spmm_adam(g0, X, P0, M0, V0, sc, 1.0, 0.25, [Z1]); lg.ops.spmm_adam(g1, X, P1, M1, V1, sc, 1.0, 0.25, [Z1])
+    if seg_len == 4096:
+        assert torch.equal(P0, P1) and torch.equal(M0, M1) and torch.equal(V0, V1)
+    else:
+        assert rel_err(M1.cpu().numpy(), M0.cpu().numpy()) < 2e-6 and rel_err(P1.cpu().numpy(), P0.cpu().numpy()) < 1e-4
+
+
+def test_training_step_with_blocked_graph_matches_unblocked(lg):
+    """The whole fused step (forward, K2, backward, Adam) with K1 column-blocked == unblocked, bit for bit (tiny graph, no
+    row long enough to be segmented inside a slab), through the reference-facing API in deterministic mode."""
+    g = load_golden('tiny')
+    nu = int(g['n_users'])
+    res = []
+    for blocked in (False, True):
+        cfg = dict(lg.world.config)
+        cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), bpr_batch_size=len(g['users']), decay=float(g['decay']),
+                   lr=float(g['lr']), deterministic=True, spmm_seg_len=4096)
+        ds = lg.InteractionDataset(nu, int(g['m_items']), g['train_user'], g['train_item'], g['test_user'], g['test_item'], config=cfg)
+        m = lg.LightGCN(cfg, ds)
+        with torch.no_grad():
+            m.embedding_user.weight.copy_(torch.from_numpy(g['E0'][:nu])); m.embedding_item.weight.copy_(torch.from_numpy(g['E0'][nu:]))
+        if blocked:
+            assert ds.getCSRGraph().block_plans(int(g['d']), slab_bytes=150 * int(g['d']) * 4) is not None
+        bpr = lg.utils.BPRLoss(m, cfg)
+        losses = [bpr.stageOne(*(torch.from_numpy(np.roll(g[k], s * 17)).long() for k in ('users', 'pos', 'neg'))) for s in range(3)]
+        res.append((losses, torch.cat([m.embedding_user.weight, m.embedding_item.weight]).detach().cpu().numpy()))
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])
+    assert rel_err(res[1][1], g['params_after'][2]) < 1e-4
+
+
 def test_rank_metrics_is_bitwise_repeatable_and_split_invariant(lg):
     """lgcn_rank_metrics adds the per-row values in a fixed order: the same bits on every call — the property the multi-GPU
     Test relies on (ranked lists gathered from the ranks, then this kernel on every rank)."""
