@@ -71,6 +71,7 @@ _SIGNATURES = {
     "lgcn_bpr_clear_rows": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "lgcn_batch_advance": (ctypes.c_int, [_P, c_int32, _P]),
     "lgcn_batch_masks": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "lgcn_batch_masks_rows": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_score_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "lgcn_score_topk": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32,
                                        _P, _P, _P, c_size_t, _P]),

@@ -251,6 +251,21 @@ batch_masks_kernel(const long long* users, const long long* pos, const long long
     for (int j = s + lane; j < t; j += 32) { const int c = indices[j]; atomicOr(m1 + (c >> 5), 1u << (c & 31)); }
 }
 
+// the same bitmap restricted to a row block [row_begin, row_end) and indexed by LOCAL row (row partition: a rank prunes
+// the last forward layer to the batch rows it owns)
+__global__ void __launch_bounds__(256)
+batch_masks_rows_kernel(const long long* users, const long long* pos, const long long* neg, int B_cap, const int* ctl,
+                        int n_users, int row_begin, int row_end, unsigned* m0) {
+    const int off = ctl[0];
+    const int B = min(ctl[1], B_cap);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * B) return;
+    const int row = (int)(e < B ? users[off + e] : (e < 2 * B ? pos[off + e - B] + n_users : neg[off + e - 2 * B] + n_users));
+    if (row < row_begin || row >= row_end) return;
+    const int r = row - row_begin;
+    atomicOr(m0 + (r >> 5), 1u << (r & 31));
+}
+
 static size_t bpr_blocks(int B_cap, int d) {
     const int vec = d / 4, lanes = vec < 32 ? vec : 32, groups = kBprThreads / lanes;
     return (size_t)(B_cap + groups - 1) / groups;
@@ -357,5 +372,20 @@ extern "C" int lgcn_batch_masks(const int64_t* users, const int64_t* pos, const 
     batch_masks_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(users), reinterpret_cast<const long long*>(pos),
                                                reinterpret_cast<const long long*>(neg), B_cap, batch_ctl_dev, n_users, indptr, indices, m0, m1);
     LGCN_CHECK_LAUNCH("batch_masks_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_batch_masks_rows(const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t B_cap,
+                                     const int32_t* batch_ctl_dev, int32_t n_users, int32_t row_begin, int32_t row_end,
+                                     uint32_t* m0_local, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(users && pos && neg && batch_ctl_dev && m0_local && B_cap > 0 && row_begin >= 0 && row_end >= row_begin, "batch_masks_rows: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const size_t words = ((size_t)(row_end - row_begin) + 31) / 32;
+    if (words == 0) return 0;
+    cudaMemsetAsync(m0_local, 0, words * 4, st);
+    const unsigned blocks = (unsigned)((3LL * B_cap + 255) / 256);
+    batch_masks_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(users), reinterpret_cast<const long long*>(pos),
+                                                    reinterpret_cast<const long long*>(neg), B_cap, batch_ctl_dev, n_users, row_begin, row_end, m0_local);
+    LGCN_CHECK_LAUNCH("batch_masks_rows_kernel");
     return 0;
 }

@@ -193,7 +193,8 @@ class Engine:
         self._host_step = 0
         self.param_epoch = 0
         # dead-row pruning of the training step (see _enqueue_step): bitmaps over the N nodes
-        self.prune = bool(prune) and dist_mode in (None, 'dp_idx')
+        # (row partition: the bitmap covers the rank's own rows, indexed by local row; (re)allocated in _take_block)
+        self.prune = bool(prune) and dist_mode in (None, 'dp_idx', 'rowpart')
         words = (N + 31) // 32
         self.m0 = torch.zeros(words, dtype=torch.int32, device=device)
         # row partition
@@ -244,6 +245,7 @@ class Engine:
         self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.local = None
         self.local = self.builder.build(self.r0, self.r1) if self.builder is not None else self.csr.rows(self.r0, self.r1)
+        self.m0 = torch.zeros((self.r1 - self.r0 + 31) // 32 + 1, dtype=torch.int32, device=self.device)
 
     def adam_state_full(self):
         """Full (N,d) Adam moments on every rank (collective in the memory-partitioned row partition: checkpoints)."""
@@ -285,7 +287,7 @@ class Engine:
         dist.all_gather(allt, mine, group=self.group)
         self.out.zero_()
         times = [float(x.item()) for x in allt]
-        if max(times) < 1.15 * min(times):          # already balanced to within the timing noise
+        if max(times) < 1.04 * min(times):          # already balanced to within the timing noise
             return list(self.bounds)
         return rebalance_by_time(indptr_cpu, self.bounds, times, row_cost)
 
@@ -356,14 +358,14 @@ class Engine:
             peers = self._peer.get(Y.data_ptr()) if self.p2p else None
             mc = self._mc.get(Y.data_ptr(), 0) if self.p2p else 0
             if mc:
-                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None, mc_y=mc + r0 * self.d * 4)
+                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None, row_mask=row_mask, mc_y=mc + r0 * self.d * 4)
                 self._rank_barrier()
             elif peers is not None:
-                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None,
+                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None, row_mask=row_mask,
                          peer_y=[peers[p][r0:r1] for p in range(self.world) if p != self.rank])
                 self._rank_barrier()
             else:
-                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None)
+                ops.spmm(self.local, X, Y[r0:r1], alpha, beta, [z[r0:r1] for z in zs] if zs else None, row_mask=row_mask)
                 self._allgather_rows(Y)
         else:
             ops.spmm(self.csr, X, Y, alpha, beta, zs, row_mask=row_mask, col_mask=col_mask)
@@ -457,7 +459,10 @@ class Engine:
             # yelp2018 shape: the batch rows hold ~60 % of the non-zeros because positives are popularity-biased,
             # so this saves ~15 us of the 44 us layer; pruning X_{L-1} to the 1-hop set m1 (90 % of the rows) and
             # masking the first backward product by m0 did not pay and are not used — profiles/README.md.)
-            ops.batch_masks(users, pos, neg, self.B_cap, ctl, self.nu, self.csr, self.m0, None)
+            if self.dist_mode == 'rowpart':      # each rank prunes to the batch rows it owns (local bitmap)
+                ops.batch_masks_rows(users, pos, neg, self.B_cap, ctl, self.nu, self.r0, self.r1, self.m0)
+            else:
+                ops.batch_masks(users, pos, neg, self.B_cap, ctl, self.nu, self.csr, self.m0, None)
             masks = (self.m0, None)
         self.forward(masks)
         if self.dist_mode == 'dp':

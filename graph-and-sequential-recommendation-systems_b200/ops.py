@@ -438,6 +438,12 @@ def batch_masks(users, pos, neg, B_cap, ctl, n_users, g, m0, m1):
                                             _p(g.indices), _p(m0), _p(m1), _stream()), "batch_masks")
 
 
+def batch_masks_rows(users, pos, neg, B_cap, ctl, n_users, row_begin, row_end, m0_local):
+    """Bitmap of the batch rows inside [row_begin, row_end), indexed by local row."""
+    _lib.check(_lib.load().lgcn_batch_masks_rows(_p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users, int(row_begin), int(row_end),
+                                                 _p(m0_local), _stream()), "batch_masks_rows")
+
+
 def batch_advance(ctl, B_cap):
     _lib.check(_lib.load().lgcn_batch_advance(_p(ctl), B_cap, _stream()), "batch_advance")
 

@@ -259,6 +259,12 @@ int lgcn_batch_masks(const int64_t* users, const int64_t* pos, const int64_t* ne
                      const int32_t* indptr, const int32_t* indices, uint32_t* m0, uint32_t* m1,
                      lgcn_stream_t stream);
 
+/* the same m0 restricted to the row block [row_begin,row_end) and indexed by LOCAL row: uint32[(row_end-row_begin+31)/32]
+ * (row partition: every rank prunes the last forward layer to the batch rows it owns) */
+int lgcn_batch_masks_rows(const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t B_cap,
+                          const int32_t* batch_ctl_dev, int32_t n_users, int32_t row_begin, int32_t row_end,
+                          uint32_t* m0_local, lgcn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K3  user x item scores fused with the train-item mask and per-row top-k
  * replaces  getUsersRating matmul (code/model.py:114-123), the -(1<<10) mask
