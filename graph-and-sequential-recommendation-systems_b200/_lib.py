@@ -72,6 +72,11 @@ _SIGNATURES = {
     "lgcn_batch_advance": (ctypes.c_int, [_P, c_int32, _P]),
     "lgcn_batch_masks": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "lgcn_batch_masks_rows": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P, _P]),
+    "lgcn_popgate_param_count": (c_int32, [c_int32, c_int32, c_int32]),
+    "lgcn_popgate_fuse": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32, c_float, _P, _P, _P]),
+    "lgcn_popgate_bpr_workspace_bytes": (c_size_t, [c_int32]),
+    "lgcn_popgate_bpr_fwd_bwd": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32,
+                                                c_float, c_float, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "lgcn_score_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "lgcn_score_topk": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32,
                                        _P, _P, _P, c_size_t, _P]),

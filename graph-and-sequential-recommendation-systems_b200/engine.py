@@ -235,8 +235,20 @@ class Engine:
             self._barrier = ops.RankBarrier(self._flags, map_peer_buffers(self._flags, group), self.rank, self.world)
             dist.barrier(group)
         # batch staging: [ctl(4 x int32) | users | pos | neg] in one block so that a host batch is one H2D
+        self.pg = None              # popularity-gate variant (enable_popgate): MLP parameter block + its Adam state
         self._alloc_batch(self.B_cap)
         self._epoch = None          # (S tensor [3,cap], ctl) for epoch-resident mode
+        self._graphs = {}
+
+    def enable_popgate(self, item_pop, params, pop_hidden, gate_hidden, temperature, entropy_coeff):
+        """Train the popularity-gate variant (code/model.py:139-183) through the fused step: K2 is replaced by the pop-gate
+        BPR kernel (csrc/popgate.cu), the MLP parameter block gets its own dense Adam launch.  Single GPU only."""
+        if self.dist_mode is not None:
+            raise NotImplementedError("the fused pop-gate step is single-GPU (the MLP gradients come from float atomics, so "
+                                      "replicas would drift); use bpr_loss().backward() under dist_mode")
+        self.pg = dict(pop=item_pop, params=params, H1=int(pop_hidden), H2=int(gate_hidden), temp=float(temperature), coeff=float(entropy_coeff),
+                       grad=torch.zeros_like(params), M=torch.zeros_like(params), V=torch.zeros_like(params),
+                       ws=ops.popgate_workspace(self.B_cap, self.device))
         self._graphs = {}
 
     def _take_block(self):
@@ -471,6 +483,10 @@ class Engine:
                             self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
             dist.all_reduce(self.G, group=self.group)
             dist.all_reduce(self.loss_out[:3], group=self.group)
+        elif self.pg is not None:
+            pg = self.pg
+            ops.popgate_bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, pg['pop'], pg['params'], pg['H1'], pg['H2'],
+                                    pg['temp'], pg['coeff'], self.decay, self.loss_out, self.G, pg['grad'], pg['ws'])
         else:
             ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
                             self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
@@ -492,6 +508,9 @@ class Engine:
                 if peers_e0 is not None or mc_e0:        # the updated parameter rows are already in every replica
                     self._rank_barrier()
             self._backward_chain(self.G, last)
+        if self.pg is not None:     # the 8 MLP tensors are one flat block: one dense Adam launch, same step scalars
+            ops.adam(self.pg['params'], self.pg['M'], self.pg['V'], self.pg['grad'], self.scalars)
+            self.pg['grad'].zero_()
         if self.dist_mode == 'dp':
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
         else:
@@ -529,6 +548,8 @@ class Engine:
     def _warm_kernels(self, users, pos, neg, ctl):
         """Run the step once on throw-away state so every kernel is loaded before graph capture."""
         state = (self.E0, self.M, self.V, self.scalars, self.loss_out, ctl)
+        if self.pg is not None:
+            state = state + (self.pg['params'], self.pg['M'], self.pg['V'])
         saved = [t.clone() for t in state]
         ctl.zero_()                                   # B = 0: the batch kernels touch nothing
         self._enqueue_step(users, pos, neg, ctl)

@@ -185,6 +185,10 @@ class LightGCN(nn.Module):
             self.item_pop_scalar = ((pop - pop.mean()) / (pop.std() + 1e-8)).to(self.device)
             self.pop_mlp = nn.Sequential(nn.Linear(1, self.pop_hidden), nn.ReLU(), nn.Linear(self.pop_hidden, self.latent_dim)).to(self.device)
             self.gate_mlp = nn.Sequential(nn.Linear(2 * self.latent_dim, self.gate_hidden), nn.ReLU(), nn.Linear(self.gate_hidden, 1)).to(self.device)
+            self._pg_flat = None
+            if (self.latent_dim in (32, 64, 128) and self.pop_hidden <= 64 and self.gate_hidden <= 128
+                    and config.get('dist_mode') is None and config.get('popgate_kernel', True)):
+                self._pack_popgate()
 
         # item-item smoothing (code/model.py:99-109): explicit-value CSR and its transpose, both served by K1
         self._i2i = self._i2i_t = None
@@ -201,8 +205,43 @@ class LightGCN(nn.Module):
 
     @property
     def plain(self):
-        """True when neither optional variant is active, i.e. the fused training step applies."""
-        return not self.use_pop_gate and not (self._i2i is not None and self.i2i_alpha > 0.0)
+        """True when the fused training step applies: the plain model, or the popularity gate with its kernels enabled
+        (csrc/popgate.cu).  Item-item smoothing trains through bpr_loss().backward()."""
+        if self._i2i is not None and self.i2i_alpha > 0.0:
+            return False
+        return (not self.use_pop_gate) or getattr(self, '_pg_flat', None) is not None
+
+    def popgate_tensors(self):
+        """The 8 MLP tensors in the order of the kernel's parameter block (include/lgcn_b200.h)."""
+        return [self.pop_mlp[0].weight, self.pop_mlp[0].bias, self.pop_mlp[2].weight, self.pop_mlp[2].bias,
+                self.gate_mlp[0].weight, self.gate_mlp[0].bias, self.gate_mlp[2].weight, self.gate_mlp[2].bias]
+
+    def _pack_popgate(self):
+        """Make the 8 MLP tensors views of ONE flat device block (what the kernels read and the fused Adam updates); names,
+        shapes and values stay the reference's (state_dict keys pop_mlp.*, gate_mlp.*)."""
+        n = ops.popgate_param_count(self.latent_dim, self.pop_hidden, self.gate_hidden)
+        flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=self.device)      # padded: the dense Adam kernel works in float4
+        off = 0
+        with torch.no_grad():
+            for t in self.popgate_tensors():
+                k = t.numel()
+                flat[off:off + k].copy_(t.data.reshape(-1))
+                t.data = flat[off:off + k].view(t.shape)
+                off += k
+        assert off == n
+        self._pg_flat = flat
+        self._engine.enable_popgate(self.item_pop_scalar.contiguous(), flat, self.pop_hidden, self.gate_hidden,
+                                    self.pop_gate_temp, self.gate_entropy_coeff)
+
+    def _popgate_packed(self):
+        if self._pg_flat is None:
+            return False
+        off = 0
+        for t in self.popgate_tensors():
+            if t.data_ptr() != self._pg_flat.data_ptr() + 4 * off:
+                return False
+            off += t.numel()
+        return True
 
     def _fuse_item_embeddings(self, items_emb):
         """gate = sigmoid(gate_mlp([items, pop_vec]) / T); fused = gate*items + (1-gate)*pop_vec  (code/model.py:139-157)."""
@@ -215,7 +254,19 @@ class LightGCN(nn.Module):
         return gate * items_emb + (1.0 - gate) * pop_vec
 
     def _items_for_scoring(self, all_items):
-        return self._fuse_item_embeddings(all_items).contiguous() if self.use_pop_gate else all_items
+        if not self.use_pop_gate:
+            return all_items
+        eng = self._engine
+        if (getattr(self, '_pg_flat', None) is not None and not torch.is_grad_enabled()
+                and all_items.data_ptr() == eng.out.data_ptr() + self.n_users * self.latent_dim * 4):
+            if not self._popgate_packed():
+                self._pack_popgate()
+            # the fusion kernel on the resident propagated table (no M x 2d concat, no M x H intermediates)
+            fused, gate = ops.popgate_fuse(eng.out, self.n_users, self.m_items, self.item_pop_scalar, self._pg_flat,
+                                           self.pop_hidden, self.gate_hidden, self.pop_gate_temp, want_gate=True)
+            self._last_item_gate = gate.unsqueeze(1)
+            return fused
+        return self._fuse_item_embeddings(all_items).contiguous()
 
     # ------------------------------------------------------------------ parameter storage
     def _pack_params(self):
@@ -251,6 +302,8 @@ class LightGCN(nn.Module):
             if self.embedding_user.weight.device.type != 'cuda':
                 raise RuntimeError("lgcn_b200.LightGCN parameters must stay on the CUDA device")
             self._pack_params()
+        if getattr(self, '_pg_flat', None) is not None and not self._popgate_packed():
+            self._pack_popgate()
         return self
 
     def invalidate_cache(self):
@@ -328,7 +381,7 @@ class LightGCN(nn.Module):
         """(bpr, reg) as in code/model.py:162-183; both support .backward() through loss + decay*reg."""
         uw, iw = self.embedding_user.weight, self.embedding_item.weight
         users, pos, neg = (t.to(torch.int64).contiguous() for t in (users, pos, neg))
-        if not self.plain:
+        if self.use_pop_gate or (self._i2i is not None and self.i2i_alpha > 0.0):
             # variants: the reference's arithmetic on top of the kernel-backed propagation (code/model.py:162-183)
             u, pos_e, neg_e, _, _ = self.getEmbedding(users.to(self.device), pos.to(self.device), neg.to(self.device))
             bpr = -torch.mean(F.logsigmoid((u * pos_e).sum(dim=1) - (u * neg_e).sum(dim=1)))
@@ -357,9 +410,11 @@ class LightGCN(nn.Module):
         """stageOne without autograd: forward, BPR, backward and Adam in one captured sequence.
         Returns the engine (loss in engine.loss_out on the device)."""
         if not self.plain:
-            raise RuntimeError("the fused step covers the plain LightGCN path; pop-gate / item-item variants train through bpr_loss().backward()")
+            raise RuntimeError("the fused step covers the plain and pop-gate models; item-item smoothing trains through bpr_loss().backward()")
         if not self._params_packed():
             self._pack_params()
+        if self.use_pop_gate and not self._popgate_packed():
+            self._pack_popgate()
         eng = self._engine
         if lr is not None:
             eng.set_lr(lr)

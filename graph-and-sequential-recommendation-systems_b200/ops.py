@@ -427,6 +427,36 @@ def bpr_fwd_bwd(out, users, pos, neg, B_cap, ctl, n_users, m_items, inv_norm, de
                                     workspace.numel() * 4, _stream()), "bpr_fwd_bwd")
 
 
+def popgate_param_count(d, pop_hidden, gate_hidden):
+    return int(_lib.load().lgcn_popgate_param_count(int(d), int(pop_hidden), int(gate_hidden)))
+
+
+def popgate_fuse(out, n_users, m_items, item_pop, params, pop_hidden, gate_hidden, temperature=1.0, want_gate=False):
+    """fused item table [m_items, d] (+ gates [m_items]) from the propagated table `out` [N, d]  (code/model.py:139-157)."""
+    _need(out, torch.float32, "out", 2), _need(item_pop, torch.float32, "item_pop", 1), _need(params, torch.float32, "params", 1)
+    d = out.shape[1]
+    fused = torch.empty((m_items, d), dtype=torch.float32, device=out.device)
+    gate = torch.empty(m_items, dtype=torch.float32, device=out.device) if want_gate else None
+    _lib.check(_lib.load().lgcn_popgate_fuse(_p(out), int(n_users), int(m_items), d, _p(item_pop), _p(params), int(pop_hidden), int(gate_hidden),
+                                             float(temperature), _p(fused), _p(gate), _stream()), "popgate_fuse")
+    return (fused, gate) if want_gate else fused
+
+
+def popgate_workspace(B_cap, device):
+    nbytes = _lib.load().lgcn_popgate_bpr_workspace_bytes(B_cap)
+    return torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)
+
+
+def popgate_bpr_fwd_bwd(out, users, pos, neg, B_cap, ctl, n_users, m_items, item_pop, params, pop_hidden, gate_hidden, temperature,
+                        entropy_coeff, decay, loss_out, G, params_grad, workspace):
+    """K2 of the pop-gate variant: loss_out = {bpr - coeff*entropy, reg, total, running}; G += d total/d out; params_grad += d total/d MLPs."""
+    _need(out, torch.float32, "out", 2)
+    _lib.check(_lib.load().lgcn_popgate_bpr_fwd_bwd(_p(out), _p(users), _p(pos), _p(neg), B_cap, _p(ctl), int(n_users), int(m_items), out.shape[1],
+                                                    _p(item_pop), _p(params), int(pop_hidden), int(gate_hidden), float(temperature),
+                                                    float(entropy_coeff), float(decay), _p(loss_out), _p(G), _p(params_grad),
+                                                    _p(workspace), workspace.numel() * 4, _stream()), "popgate_bpr_fwd_bwd")
+
+
 def bpr_clear_rows(G, users, pos, neg, B_cap, ctl, n_users):
     _lib.check(_lib.load().lgcn_bpr_clear_rows(_p(G), _p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users,
                                                G.shape[1], _stream()), "bpr_clear_rows")

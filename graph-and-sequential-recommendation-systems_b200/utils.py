@@ -37,6 +37,14 @@ class _AdamStateView(optim.Adam):
             if M is not None:
                 st['exp_avg'] = M[sl]
                 st['exp_avg_sq'] = V[sl]
+        if eng.pg is not None:          # pop-gate MLPs: the 8 tensors are consecutive slices of the engine's flat blocks
+            off = 0
+            for t in m.popgate_tensors():
+                st = self.state[t]
+                st['step'] = torch.tensor(float(eng._host_step))
+                st['exp_avg'] = eng.pg['M'][off:off + t.numel()].view(t.shape)
+                st['exp_avg_sq'] = eng.pg['V'][off:off + t.numel()].view(t.shape)
+                off += t.numel()
 
     def state_dict(self):
         eng = self._model._engine
@@ -60,6 +68,13 @@ class _AdamStateView(optim.Adam):
         if len(parts) == 2:
             dev = eng.M.device
             eng.load_adam_state(torch.cat([parts[0][0].to(dev), parts[1][0].to(dev)]), torch.cat([parts[0][1].to(dev), parts[1][1].to(dev)]))
+        if eng.pg is not None:
+            off = 0
+            for t in m.popgate_tensors():
+                st = self.state.get(t, {})
+                if 'exp_avg' in st:
+                    eng.pg['M'][off:off + t.numel()].copy_(st['exp_avg'].reshape(-1)); eng.pg['V'][off:off + t.numel()].copy_(st['exp_avg_sq'].reshape(-1))
+                off += t.numel()
         eng.set_lr(self.param_groups[0]['lr'])
         eng.set_adam_step(step)
         self._bind()

@@ -266,6 +266,31 @@ int lgcn_batch_masks_rows(const int64_t* users, const int64_t* pos, const int64_
                           uint32_t* m0_local, lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Popularity gate
+ * replaces  _fuse_item_embeddings  code/model.py:139-157 ; bpr_loss with use_pop_gate  code/model.py:162-183 and its backward
+ *
+ * params float32[lgcn_popgate_param_count(d, H1, H2)] = W1[H1] b1[H1] W2[d][H1] b2[d] G1[H2][2d] c1[H2] G2[H2] c2[1]
+ *   (weights/biases of pop_mlp.0, pop_mlp.2, gate_mlp.0, gate_mlp.2 in nn.Linear layout); item_pop float32[m_items] is the
+ *   standardised log1p(item degree) of code/model.py:74-77.  d in {32,64,128}, H1 <= 64, H2 <= 128.
+ * lgcn_popgate_fuse: fused_out[m_items,d] = g*x + (1-g)*v for every item row x = out[n_users+i]; gate_out[m_items] optional.
+ * lgcn_popgate_bpr_fwd_bwd: loss_out = {bpr - entropy_coeff*mean gate entropy over the 2B pos/neg gates, reg on (u, fused pos,
+ *   fused neg), total = loss + decay*reg, running sum}; G[N,d] += d total/d out; params_grad += d total/d params
+ *   (G == params_grad == NULL: forward only).  Float atomics: not bit-reproducible from run to run.
+ *   workspace: zero-filled once (self-resetting arrival counter).
+ * -------------------------------------------------------------------------------------------*/
+int32_t lgcn_popgate_param_count(int32_t d, int32_t pop_hidden, int32_t gate_hidden);
+int lgcn_popgate_fuse(const float* out, int32_t n_users, int32_t m_items, int32_t d, const float* item_pop,
+                      const float* params, int32_t pop_hidden, int32_t gate_hidden, float temperature,
+                      float* fused_out, float* gate_out, lgcn_stream_t stream);
+size_t lgcn_popgate_bpr_workspace_bytes(int32_t B_cap);
+int lgcn_popgate_bpr_fwd_bwd(const float* out, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                             int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items, int32_t d,
+                             const float* item_pop, const float* params, int32_t pop_hidden, int32_t gate_hidden,
+                             float temperature, float entropy_coeff, float decay,
+                             float* loss_out, float* G, float* params_grad,
+                             void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K3  user x item scores fused with the train-item mask and per-row top-k
  * replaces  getUsersRating matmul (code/model.py:114-123), the -(1<<10) mask
  *           (code/Procedure.py:177-181) and torch.topk (code/Procedure.py:183)

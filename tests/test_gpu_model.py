@@ -272,8 +272,8 @@ def test_gowalla_step0_known_answer_end_to_end(lg, gowalla, tmp_path):
 # ------------------------------------------------------------------------------------ variants
 def _variant_model(lg, g, tmp_path, kind):
     over = {}
-    if kind == 'popgate':
-        over = dict(use_pop_gate=True)
+    if kind.startswith('popgate'):
+        over = dict(use_pop_gate=True, popgate_kernel=(kind == 'popgate'))
     else:
         import scipy.sparse as sp
         ni = int(g['m_items'])
@@ -281,19 +281,21 @@ def _variant_model(lg, g, tmp_path, kind):
         path = str(tmp_path / 'i2i.npz'); sp.save_npz(path, m)
         over = dict(use_item_item=True, i2i_path=path, i2i_alpha=float(g['i2i_alpha']))
     cfg, ds, m = make_model(lg, g, **over)
-    if kind == 'popgate':
+    if kind.startswith('popgate'):
         sd = {k[3:].replace('__', '.'): torch.from_numpy(v) for k, v in g.items() if k.startswith('sd_')}
         missing = m.load_state_dict(sd, strict=False)
         assert set(missing.missing_keys) == {'embedding_user.weight', 'embedding_item.weight'} and not missing.unexpected_keys
     return cfg, ds, m
 
 
-@pytest.mark.parametrize("kind", ["popgate", "i2i"])
+@pytest.mark.parametrize("kind", ["popgate", "popgate_autograd", "i2i"])
 def test_model_variants_match_reference(lg, tmp_path, kind):
-    """use_pop_gate / use_item_item: loss, gradients, three optimiser steps and scores against the real reference."""
-    g = load_golden(kind)
+    """use_pop_gate / use_item_item: loss, gradients, three optimiser steps and scores against the real reference.
+    'popgate' trains through the FUSED step (csrc/popgate.cu: fusion + BPR + closed-form backward + fused Adam on the MLP
+    block), 'popgate_autograd' / 'i2i' through bpr_loss().backward() + torch Adam on top of the kernel-backed propagation."""
+    g = load_golden('popgate' if kind.startswith('popgate') else kind)
     cfg, ds, m = _variant_model(lg, g, tmp_path, kind)
-    assert not m.plain
+    assert m.plain == (kind == 'popgate')
     nu = int(g['n_users'])
     with torch.no_grad():
         out = torch.cat(m.computer()).cpu().numpy()
@@ -305,13 +307,30 @@ def test_model_variants_match_reference(lg, tmp_path, kind):
     (loss + reg * float(g['decay'])).backward()
     grad = torch.cat([m.embedding_user.weight.grad, m.embedding_item.weight.grad]).cpu().numpy()
     assert rel_err(grad, g['grad']) < 5e-5
-    if kind == 'popgate':
+    if kind.startswith('popgate'):
         for name, prm in m.named_parameters():
             if not name.startswith('embedding'):
                 assert rel_err(prm.grad.cpu().numpy(), g['grad_' + name.replace('.', '__')]) < 1e-4, name
+    if kind == 'popgate':
+        # the kernel's closed-form backward against the same reference gradients (embeddings AND the 8 MLP tensors)
+        eng = m._engine
+        eng.forward(); eng.G.zero_(); eng.pg['grad'].zero_()
+        eng._stage_batch(u, p, n)
+        lg.ops.popgate_bpr_fwd_bwd(eng.out, eng.bu, eng.bp, eng.bn, eng.B_cap, eng.ctl, eng.nu, eng.ni, eng.pg['pop'], eng.pg['params'],
+                                   eng.pg['H1'], eng.pg['H2'], eng.pg['temp'], eng.pg['coeff'], float(g['decay']), eng.loss_out, eng.G, eng.pg['grad'], eng.pg['ws'])
+        lo = eng.loss_out.cpu().numpy()
+        assert abs(lo[0] - float(g['loss'])) < 2e-5 * abs(float(g['loss'])) and abs(lo[1] - float(g['reg'])) < 2e-5 * abs(float(g['reg']))
+        gE = eng.backward_to(eng.G.clone(), eng.grad_buffer()).cpu().numpy()
+        assert rel_err(gE, g['grad']) < 5e-5
+        off = 0
+        for name, t in zip(['pop_mlp.0.weight', 'pop_mlp.0.bias', 'pop_mlp.2.weight', 'pop_mlp.2.bias',
+                            'gate_mlp.0.weight', 'gate_mlp.0.bias', 'gate_mlp.2.weight', 'gate_mlp.2.bias'], m.popgate_tensors()):
+            got = eng.pg['grad'][off:off + t.numel()].view(t.shape).cpu().numpy(); off += t.numel()
+            assert rel_err(got, g['grad_' + name.replace('.', '__')]) < 1e-4, name
+        eng.G.zero_(); eng.pg['grad'].zero_()
     m.zero_grad()
     bpr = lg.utils.BPRLoss(m, cfg)
-    assert not bpr.fused
+    assert bpr.fused == (kind == 'popgate')
     B = len(g['users'])
     for s in range(3):
         l = bpr.stageOne(*(t.cuda() for t in triples(g, (s * 17) % B)))
