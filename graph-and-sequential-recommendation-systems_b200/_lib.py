@@ -92,7 +92,7 @@ _SIGNATURES = {
     "lgcn_score_dense": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_rank_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "lgcn_rank_metrics": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P, c_int32, _P, _P, c_size_t, _P]),
-    "lgcn_sample_bpr": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int64, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P]),
+    "lgcn_sample_bpr": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int64, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P, _P]),
     "lgcn_sampler_seed": (None, [c_uint32]),
     "lgcn_sample_negative": (c_int64, [c_int32, c_int32, c_int64, _P, _P, c_int32, _P]),
     "lgcn_sample_negative_by_user": (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P]),

@@ -39,7 +39,7 @@ __device__ __forceinline__ unsigned long long feistel_perm(unsigned long long p,
 __global__ void __launch_bounds__(256)
 sample_bpr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, int n_users, int m_items,
                   long long per_user, long long n, int half_bits, unsigned long long key,
-                  long long* __restrict__ users, long long* __restrict__ pos, long long* __restrict__ neg) {
+                  long long* __restrict__ users, long long* __restrict__ pos, long long* __restrict__ neg, int* __restrict__ status) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const long long s = (long long)feistel_perm((unsigned long long)p, (unsigned long long)n, half_bits, key);
@@ -47,7 +47,9 @@ sample_bpr_kernel(const int* __restrict__ indptr, const int* __restrict__ indice
     const int lo = __ldg(indptr + u), hi = __ldg(indptr + u + 1), deg = hi - lo;
     unsigned long long st = splitmix64(key ^ ((unsigned long long)s * 0xD1342543DE82EF95ull));
     long long pi = 0, ni = 0;
+    bool found = false;
     if (deg > 0) pi = (long long)__ldg(indices + lo + (int)(st % (unsigned long long)deg)) - n_users;
+    else if (status) atomicOr(status, 1);               // a user without train items: the triple is fabricated — the caller must fail
     if (deg < m_items) {
         for (int attempt = 0; attempt < 1 << 20; ++attempt) {
             st = splitmix64(st);
@@ -55,9 +57,10 @@ sample_bpr_kernel(const int* __restrict__ indptr, const int* __restrict__ indice
             const int keyc = cand + n_users;
             int l = lo, h = hi;
             while (l < h) { const int mid = (l + h) >> 1; if (__ldg(indices + mid) < keyc) l = mid + 1; else h = mid; }
-            if (!(l < hi && __ldg(indices + l) == keyc)) { ni = cand; break; }
+            if (!(l < hi && __ldg(indices + l) == keyc)) { ni = cand; found = true; break; }
         }
     }
+    if (!found && status) atomicOr(status, 2);           // the user interacted with every item (or 2^20 rejections in a row)
     users[p] = u; pos[p] = pi; neg[p] = ni;
 }
 
@@ -67,7 +70,7 @@ using namespace lgcn;
 
 extern "C" int lgcn_sample_bpr(const int32_t* indptr, const int32_t* indices, int32_t n_users, int32_t m_items,
                                int64_t train_num, uint64_t seed, uint64_t epoch,
-                               int64_t* users_out, int64_t* pos_out, int64_t* neg_out, lgcn_stream_t stream) {
+                               int64_t* users_out, int64_t* pos_out, int64_t* neg_out, int32_t* status_out, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(indptr && indices && users_out && pos_out && neg_out, "sample_bpr: null argument");
     LGCN_CHECK_ARG(n_users > 0 && m_items > 0 && train_num >= 0, "sample_bpr: bad sizes");
     const long long per_user = train_num / n_users;
@@ -77,7 +80,7 @@ extern "C" int lgcn_sample_bpr(const int32_t* indptr, const int32_t* indices, in
     const unsigned long long key = seed * 0x9E3779B97F4A7C15ull + epoch * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull;
     sample_bpr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
         indptr, indices, n_users, m_items, per_user, n, bits / 2, key,
-        reinterpret_cast<long long*>(users_out), reinterpret_cast<long long*>(pos_out), reinterpret_cast<long long*>(neg_out));
+        reinterpret_cast<long long*>(users_out), reinterpret_cast<long long*>(pos_out), reinterpret_cast<long long*>(neg_out), status_out);
     LGCN_CHECK_LAUNCH("sample_bpr_kernel");
     return 0;
 }

@@ -599,12 +599,19 @@ def rank_metrics(topk_idx, test_indptr, test_indices, ks):
     return sums.view(len(ks), 3)
 
 
-def sample_bpr(g, n_users, m_items, train_num, seed, epoch, out=None):
+def sample_bpr(g, n_users, m_items, train_num, seed, epoch, out=None, check=True):
     """Device-side sampler + shuffle: int64 tensor [3, n] (users, pos, neg), n = (train_num // n_users) * n_users."""
     n = (int(train_num) // int(n_users)) * int(n_users)
     if out is None or out.shape[1] < n:
         out = torch.empty((3, max(n, 1)), dtype=torch.int64, device=g.device)
     S = out[:, :n]
+    status = torch.zeros(1, dtype=torch.int32, device=g.device)
     _lib.check(_lib.load().lgcn_sample_bpr(_p(g.indptr), _p(g.indices), n_users, m_items, int(train_num), int(seed) & (2**64 - 1),
-                                           int(epoch), _p(out[0]), _p(out[1]), _p(out[2]), _stream()), "sample_bpr")
+                                           int(epoch), _p(out[0]), _p(out[1]), _p(out[2]), _p(status), _stream()), "sample_bpr")
+    if check:
+        st = int(status.item())             # one sync per epoch
+        if st & 1:
+            raise RuntimeError("sample_bpr: a user has no train item (the reference's sampler cannot serve such a dataset either)")
+        if st & 2:
+            raise RuntimeError("sample_bpr: a user has no admissible negative item")
     return S

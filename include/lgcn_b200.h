@@ -387,10 +387,13 @@ int64_t lgcn_parse_interactions(const char* path, int64_t* users_out_host, int64
  * indptr/indices: the adjacency CSR (user rows hold n_users + item).  Every user gets train_num/n_users triples
  * (uniform positive of its row, rejection-sampled negative outside it); output is already permuted, int64,
  * users_out/pos_out/neg_out[n] with n = (train_num/n_users)*n_users.  Counter-based RNG keyed by (seed, epoch).
+ * status_out (device int32[1], zero it first; may be NULL): bit 0 = some user has no train item, bit 1 = some user has no
+ * admissible negative — the triples of such users are fabricated and the epoch must not be trained on (the host sampler
+ * returns an error for the same input, the reference's C++ divides by zero, code/sources/sampling.cpp:43).
  * -------------------------------------------------------------------------------------------*/
 int lgcn_sample_bpr(const int32_t* indptr, const int32_t* indices, int32_t n_users, int32_t m_items,
                     int64_t train_num, uint64_t seed, uint64_t epoch,
-                    int64_t* users_out, int64_t* pos_out, int64_t* neg_out, lgcn_stream_t stream);
+                    int64_t* users_out, int64_t* pos_out, int64_t* neg_out, int32_t* status_out, lgcn_stream_t stream);
 
 #ifdef __cplusplus
 }

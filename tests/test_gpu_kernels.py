@@ -551,6 +551,30 @@ def test_score_topk_tensor_core_is_bit_identical_to_exact(lg, scale):
     assert torch.equal(ti_, ei) and torch.equal(tv, ev)
 
 
+@pytest.mark.parametrize("shape", ["random", "trained-like"])
+def test_score_topk_tensor_core_directly_against_the_c_oracle(lg, orc, shape):
+    """The tcgen05 path against oracle/c/score_topk_ref.c DIRECTLY (not through the exact kernel): 200 sampled users over
+    a 40,981-item table (gowalla's size), masks from a real-shaped train CSR, indices AND scores bit for bit."""
+    rng = np.random.default_rng(5 if shape == "random" else 6)
+    gr = lg.synth.make_graph('gowalla', seed=2020)
+    nu, ni, d, k = gr['n_users'], gr['m_items'], 64, 20
+    g = build(lg, gr['train_user'], gr['train_item'], nu, ni)
+    if shape == "random":
+        U = rng.normal(0, 0.1, (nu, d)).astype(np.float32); V = rng.normal(0, 0.1, (ni, d)).astype(np.float32)
+    else:       # popular items (small ids) have large norms and score high for everybody; a few exact ties
+        common = rng.normal(0, 1, d).astype(np.float32)
+        pop = (1.0 / (1.0 + np.arange(ni) / 300.0)).astype(np.float32)[:, None]
+        V = (0.05 * rng.normal(0, 1, (ni, d)) + pop * common).astype(np.float32)
+        U = (0.1 * rng.normal(0, 1, (nu, d)) + 0.3 * common).astype(np.float32)
+        V[11] = V[4]; V[2000] = V[1999]
+    users = np.sort(rng.choice(nu, 200, replace=False)).astype(np.int64)
+    indptr, indices = g.indptr.cpu().numpy(), g.indices.cpu().numpy()
+    exp_idx, exp_val = orc.score_topk_exact(U, V, users, k, indptr, indices, nu)
+    ti_, tv, redone = lg.ops.score_topk_tc(dev(U), dev(V), dev(users), k, g.indptr, g.indices, nu)
+    assert np.array_equal(ti_.cpu().numpy(), exp_idx) and np.array_equal(tv.cpu().numpy(), exp_val)
+    assert redone <= 10, redone                                  # and it is the tensor-core path that answered, not the fallback
+
+
 def test_score_topk_tensor_core_popular_items_with_adjacent_ids(lg):
     """What a trained model looks like: every user's best items are the popular ones, popular items have small ADJACENT
     ids and large norms, and a user's train items are among its best.  In id order that put most candidates into a few
@@ -690,6 +714,17 @@ def test_device_sampler_properties(lg):
     # negatives are uniform over the complement
     nn_ = big[2]
     assert abs(nn_.mean() - (ni - 1) / 2) < 0.05 * ni
+
+
+def test_device_sampler_refuses_users_without_train_items(lg):
+    """A user with no train interaction would get a fabricated positive (item 0): the device sampler reports it and the
+    wrapper raises, like the host sampler does for the same input."""
+    tu = np.array([0, 0, 2, 2, 2], np.int64); ti = np.array([1, 3, 0, 2, 4], np.int64)       # user 1 has nothing
+    g = build(lg, tu, ti, 3, 6)
+    with pytest.raises(RuntimeError, match="no train item"):
+        lg.ops.sample_bpr(g, 3, 6, 6, seed=1, epoch=0)
+    S = lg.ops.sample_bpr(g, 3, 6, 6, seed=1, epoch=0, check=False)
+    assert S.shape == (3, 6)
 
 
 def test_rank_metrics_vs_oracle(lg, orc):
