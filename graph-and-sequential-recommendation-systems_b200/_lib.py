@@ -90,6 +90,9 @@ _SIGNATURES = {
     "lgcn_score_topk_tc_position_space": (c_int32, [c_int32]),
     "lgcn_score_topk_tc_item_positions": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P]),
     "lgcn_score_dense": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
+    "lgcn_score_dense_tc_supported": (ctypes.c_int, [c_int32]),
+    "lgcn_score_dense_tc_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "lgcn_score_dense_tc": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_size_t, _P]),
     "lgcn_rank_metrics_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "lgcn_rank_metrics": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     "lgcn_sample_bpr": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int64, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P, _P]),

@@ -636,6 +636,169 @@ rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const l
     }
 }
 
+// =====================================================================================================================
+// Dense scores on tensor cores: getUsersRating (reference code/model.py:114-123, torch.matmul(u_emb, i_emb.t())).
+// The caller gets the Bt x M matrix, so nothing can be filtered and the accuracy has to be fp32's: 3xTF32.  Every operand is
+// split exactly into hi (the 10 mantissa bits tcgen05.mma.kind::tf32 reads) and lo = x - hi; the product is
+// lo_a*hi_b + hi_a*lo_b + hi_a*hi_b, small terms first, all accumulated in the fp32 TMEM accumulator (the dropped lo*lo
+// term is below 2^-20 of |a||b|).  CTA = 128 user rows x a split of the 128-item tiles (natural item order); warp 0 = TMA
+// producer (2-stage ring, a stage = hi and lo of one item tile), warp 1 = MMA issuer (24 MMAs M128 N128 K8 per tile,
+// double-buffered accumulators), warps 2-9 = epilogue: TMEM -> registers -> shared-memory transpose -> coalesced row
+// segments of the output.  The work is bound by writing Bt x M x 4 bytes; the exact CUDA-core kernel it replaces for this
+// call was compute-bound at 6.5-11 TFLOP/s (slower than cuBLAS SGEMM).
+constexpr int DT_STAGES = 2;
+constexpr int DT_EPI_WARPS = 8;                              // lane quarter (warp % 4) x 2 column halves
+constexpr int DT_THREADS = 64 + 32 * DT_EPI_WARPS;
+constexpr int DT_A_BYTES = 2 * 2 * TC_A_ATOM_BYTES;          // hi, lo x 2 K atoms x 16 KB = 64 KB
+constexpr int DT_B_STAGE_BYTES = 2 * TC_B_STAGE_BYTES;       // hi + lo of one tile = 64 KB
+constexpr int DT_STG_FLOATS = DT_EPI_WARPS * 32 * 33;        // per epilogue warp: 32 rows x 32 columns (+1 pad)
+constexpr int DT_SMEM_BYTES = 1024 + DT_A_BYTES + DT_STAGES * DT_B_STAGE_BYTES + DT_STG_FLOATS * 4 + 256;
+
+struct DtArgs { int Bt; int m_items; int tiles_per_split; float* out; };
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+score_dense_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                      const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ DtArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                    // [hi|lo][K atom][128 rows][128 B]
+    uint8_t* sB = sA + DT_A_BYTES;                         // [stage][hi|lo][K atom][128 items][128 B]
+    float* stg = reinterpret_cast<float*>(sB + DT_STAGES * DT_B_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + DT_STG_FLOATS);
+    constexpr int B_FULL = 1, B_EMPTY = 1 + DT_STAGES, T_FULL = 1 + 2 * DT_STAGES, T_EMPTY = 3 + 2 * DT_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T_EMPTY + 2);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ub = blockIdx.x * TC_M;
+    const int n_item_tiles = (a.m_items + TC_N - 1) / TC_N;
+    const int t_begin = blockIdx.y * a.tiles_per_split;
+    const int n_tiles = min(n_item_tiles, t_begin + a.tiles_per_split) - t_begin;
+
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(0), 1);
+        for (int s = 0; s < DT_STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
+        for (int c = 0; c < 2; ++c) { mbar_init(BAR(T_FULL + c), 1); mbar_init(BAR(T_EMPTY + c), 32 * DT_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(BAR(0), DT_A_BYTES);
+            for (int ka = 0; ka < 2; ++ka) {
+                tma_load_2d(smem_u32(sA + ka * TC_A_ATOM_BYTES), &map_ah, BAR(0), ka * TC_ATOM_K, ub);
+                tma_load_2d(smem_u32(sA + (2 + ka) * TC_A_ATOM_BYTES), &map_al, BAR(0), ka * TC_ATOM_K, ub);
+            }
+            for (int it = 0; it < n_tiles; ++it) {
+                const int s = it % DT_STAGES, r = it / DT_STAGES;
+                mbar_wait(BAR(B_EMPTY + s), (r & 1) ^ 1);
+                mbar_expect_tx(BAR(B_FULL + s), DT_B_STAGE_BYTES);
+                const int ib = (t_begin + it) * TC_N;
+                uint8_t* dst = sB + s * DT_B_STAGE_BYTES;
+                for (int ka = 0; ka < 2; ++ka) {
+                    tma_load_2d(smem_u32(dst + ka * TC_B_ATOM_BYTES), &map_bh, BAR(B_FULL + s), ka * TC_ATOM_K, ib);
+                    tma_load_2d(smem_u32(dst + (2 + ka) * TC_B_ATOM_BYTES), &map_bl, BAR(B_FULL + s), ka * TC_ATOM_K, ib);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = (lane == 0);
+        mbar_wait(BAR(0), 0);
+        const uint64_t da0 = umma_desc_k_sw128(smem_u32(sA));
+        for (int it = 0; it < n_tiles; ++it) {
+            const int s = it % DT_STAGES, r = it / DT_STAGES, acc = it & 1, ra = it >> 1;
+            mbar_wait(BAR(B_FULL + s), r & 1);
+            mbar_wait(BAR(T_EMPTY + acc), (ra & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t db0 = umma_desc_k_sw128(smem_u32(sB + s * DT_B_STAGE_BYTES));
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {               // lo*hi, hi*lo, then hi*hi
+                const int a_part = (term == 0) ? 1 : 0, b_part = (term == 1) ? 1 : 0;
+#pragma unroll
+                for (int j = 0; j < TC_D / 8; ++j) {
+                    const uint64_t da = da0 + (uint64_t)(((a_part * 2 + (j >> 2)) * TC_A_ATOM_BYTES + (j & 3) * 32) >> 4);
+                    const uint64_t db = db0 + (uint64_t)(((b_part * 2 + (j >> 2)) * TC_B_ATOM_BYTES + (j & 3) * 32) >> 4);
+                    if (leader) tc_mma_tf32(tmem_base + acc * TC_N, da, db, TC_IDESC, (term > 0 || j > 0) ? 1u : 0u);
+                }
+            }
+            if (leader) { tc_commit(BAR(B_EMPTY + s)); tc_commit(BAR(T_FULL + acc)); }
+            __syncwarp();
+        }
+    } else {
+        const int e = warp - 2, q = warp & 3, half = e >> 2;         // TMEM lane quarter q = warp % 4 (hardware rule)
+        float* my = stg + e * (32 * 33);
+        uint32_t r_[32];
+        for (int it = 0; it < n_tiles; ++it) {
+            const int acc = it & 1, rph = it >> 1;
+            const int ib = (t_begin + it) * TC_N + half * TC_HALF;
+            mbar_wait(BAR(T_FULL + acc), rph & 1);
+            tc_fence_after();
+            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_N + half * TC_HALF);
+#pragma unroll 1
+            for (int c32 = 0; c32 < 2; ++c32) {
+                tmem_ld32_issue(tb + 32 * c32, r_);
+                tmem_ld_wait(r_);
+                if (c32 == 1) { tc_fence_before(); mbar_arrive(BAR(T_EMPTY + acc)); }   // everything of this tile is in registers
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) my[lane * 33 + c] = __uint_as_float(r_[c]);     // thread = row: conflict-free (stride 33)
+                __syncwarp();
+                const int col = ib + 32 * c32 + lane;
+                if (col < a.m_items) {
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {                                          // lane = column: one 128-byte segment per row
+                        const int row = ub + q * 32 + rr;
+                        if (row < a.Bt) a.out[(size_t)row * a.m_items + col] = my[rr * 33 + lane];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+// x = hi + lo exactly, hi = x with the 13 low mantissa bits cleared (what kind::tf32 reads)
+__global__ void split_tf32_kernel(const float4* __restrict__ in, long long n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 x = in[i];
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+    hi[i] = h; lo[i] = l;
+}
+
+// gathered, zero-padded user rows, split in one pass
+__global__ void gather_split_rows_kernel(const float4* __restrict__ U, const long long* __restrict__ users, int Bt, int Bt_pad,
+                                         float4* __restrict__ hi, float4* __restrict__ lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Bt_pad * 16) return;
+    const int r = i >> 4, c = i & 15;
+    float4 x = f4_zero();
+    if (r < Bt) { const long long u = users ? users[r] : (long long)r; x = __ldg(U + (size_t)u * 16 + c); }
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+    hi[i] = h; lo[i] = l;
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -815,4 +978,66 @@ extern "C" int32_t lgcn_score_topk_tc_host_item(int32_t pos, int32_t m_items) {
     if (m_items < TC_MIN_ITEMS || pos < 0 || pos >= lgcn_score_topk_tc_position_space(m_items)) return -1;
     const int item = tc_item_of_pos(pos, tc_order(m_items));
     return item < m_items ? item : -1;
+}
+
+// ---- dense scores on tensor cores (getUsersRating) ----------------------------------------------------------------
+struct DtLayout { int bt_pad, item_tiles, n_splits, tiles_per_split; size_t off_al, off_bh, off_bl, total; };
+static DtLayout dt_layout(int Bt, int m_items) {
+    DtLayout L;
+    L.bt_pad = (Bt + TC_M - 1) / TC_M * TC_M;
+    L.item_tiles = (m_items + TC_N - 1) / TC_N;
+    const int row_blocks = L.bt_pad / TC_M, sms = sm_count() > 0 ? sm_count() : 148;
+    int splits = (2 * sms + row_blocks - 1) / row_blocks;          // ~2 CTAs per SM worth of work, >= 4 tiles per split
+    if (splits > (L.item_tiles + 3) / 4) splits = (L.item_tiles + 3) / 4;
+    if (splits < 1) splits = 1;
+    L.tiles_per_split = (L.item_tiles + splits - 1) / splits;
+    L.n_splits = (L.item_tiles + L.tiles_per_split - 1) / L.tiles_per_split;
+    size_t o = align_up((size_t)L.bt_pad * TC_D * 4, 1024);
+    L.off_al = o; o += align_up((size_t)L.bt_pad * TC_D * 4, 1024);
+    L.off_bh = o; o += align_up((size_t)L.item_tiles * TC_N * TC_D * 4, 1024);
+    L.off_bl = o; o += align_up((size_t)L.item_tiles * TC_N * TC_D * 4, 1024);
+    L.total = o;
+    return L;
+}
+
+extern "C" int lgcn_score_dense_tc_supported(int32_t d) { return d == TC_D ? 1 : 0; }
+
+extern "C" size_t lgcn_score_dense_tc_workspace_bytes(int32_t Bt, int32_t m_items) {
+    if (Bt <= 0 || m_items <= 0) return 0;
+    return dt_layout(Bt, m_items).total;
+}
+
+extern "C" int lgcn_score_dense_tc(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
+                                   int32_t m_items, int32_t d, float* scores, void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(users_emb && items_emb && scores && Bt > 0 && m_items > 0, "score_dense_tc: bad arguments");
+    LGCN_CHECK_ARG(d == TC_D, "score_dense_tc: only d=%d takes the tensor-core path (use lgcn_score_dense)", TC_D);
+    const DtLayout L = dt_layout(Bt, m_items);
+    LGCN_CHECK_ARG(workspace && ((uintptr_t)workspace % 1024) == 0 && workspace_bytes >= L.total, "score_dense_tc: workspace too small or not 1024-byte aligned");
+    LGCN_CHECK_ARG(((uintptr_t)items_emb % 16) == 0 && ((uintptr_t)users_emb % 16) == 0, "score_dense_tc: tables must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    char* w = static_cast<char*>(workspace);
+    float* Ah = reinterpret_cast<float*>(w); float* Al = reinterpret_cast<float*>(w + L.off_al);
+    float* Bh = reinterpret_cast<float*>(w + L.off_bh); float* Bl = reinterpret_cast<float*>(w + L.off_bl);
+    gather_split_rows_kernel<<<(L.bt_pad * 16 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(users_emb), reinterpret_cast<const long long*>(users),
+                                                                         Bt, L.bt_pad, reinterpret_cast<float4*>(Ah), reinterpret_cast<float4*>(Al));
+    LGCN_CHECK_LAUNCH("gather_split_rows_kernel");
+    const long long n4 = (long long)m_items * 16, pad4 = (long long)L.item_tiles * TC_N * 16;
+    split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(items_emb), n4, reinterpret_cast<float4*>(Bh), reinterpret_cast<float4*>(Bl));
+    LGCN_CHECK_LAUNCH("split_tf32_kernel");
+    if (pad4 > n4) {                                                   // rows of the last tile beyond m_items: zero (never stored, but finite)
+        cudaMemsetAsync(Bh + n4 * 4, 0, (size_t)(pad4 - n4) * 16, st);
+        cudaMemsetAsync(Bl + n4 * 4, 0, (size_t)(pad4 - n4) * 16, st);
+    }
+    CUtensorMap mah, mal, mbh, mbl;
+    if (int rc = make_map(&mah, Ah, (uint64_t)L.bt_pad, TC_M)) return rc;
+    if (int rc = make_map(&mal, Al, (uint64_t)L.bt_pad, TC_M)) return rc;
+    if (int rc = make_map(&mbh, Bh, (uint64_t)L.item_tiles * TC_N, TC_N)) return rc;
+    if (int rc = make_map(&mbl, Bl, (uint64_t)L.item_tiles * TC_N, TC_N)) return rc;
+    DtArgs a; a.Bt = Bt; a.m_items = m_items; a.tiles_per_split = L.tiles_per_split; a.out = scores;
+    cudaError_t e = cudaFuncSetAttribute(score_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+    if (e != cudaSuccess) return fail("score_dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    dim3 grid(L.bt_pad / TC_M, L.n_splits);
+    score_dense_tc_kernel<<<grid, DT_THREADS, DT_SMEM_BYTES, st>>>(mah, mal, mbh, mbl, a);
+    LGCN_CHECK_LAUNCH("score_dense_tc_kernel");
+    return 0;
 }

@@ -584,6 +584,24 @@ def score_dense(users_emb, items_emb, users):
     return out
 
 
+def score_dense_tc(users_emb, items_emb, users):
+    """getUsersRating on tensor cores (3xTF32, fp32-class accuracy); d = 64 — other widths go to score_dense."""
+    lib = _lib.load()
+    _need(users_emb, torch.float32, "users_emb", 2), _need(items_emb, torch.float32, "items_emb", 2)
+    Bt = users_emb.shape[0] if users is None else users.numel()
+    m_items, d = items_emb.shape
+    if not lib.lgcn_score_dense_tc_supported(d) or Bt == 0:
+        return score_dense(users_emb, items_emb, users)
+    if users is not None:
+        _need(users, torch.int64, "users", 1)
+    out = torch.empty((Bt, m_items), dtype=torch.float32, device=items_emb.device)
+    ws_bytes = lib.lgcn_score_dense_tc_workspace_bytes(Bt, m_items)
+    ws = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device=items_emb.device)
+    ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+    _lib.check(lib.lgcn_score_dense_tc(_p(users_emb), _p(items_emb), _p(users), Bt, m_items, d, _p(out), c_void_p(ws_ptr), ws_bytes, _stream()), "score_dense_tc")
+    return out
+
+
 def rank_metrics(topk_idx, test_indptr, test_indices, ks):
     """Sums over rows of precision/recall/ndcg at each k in ks -> float64 tensor [len(ks), 3]."""
     lib = _lib.load()

@@ -337,6 +337,14 @@ int lgcn_score_topk_tc(const float* users_emb, const float* items_emb, const int
 int lgcn_score_dense(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
                      int32_t m_items, int32_t d, float* scores, lgcn_stream_t stream);
 
+/* The same matrix on tensor cores (d = 64): 3xTF32 — every operand is split exactly into hi + lo and the product is
+ * lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator, so the scores carry fp32-class accuracy (|err| <~ 1e-6 |u||v|; not the
+ * bit-exact FMA chain of lgcn_score_dense).  workspace must be 1024-byte aligned. */
+int lgcn_score_dense_tc_supported(int32_t d);
+size_t lgcn_score_dense_tc_workspace_bytes(int32_t Bt, int32_t m_items);
+int lgcn_score_dense_tc(const float* users_emb, const float* items_emb, const int64_t* users, int32_t Bt,
+                        int32_t m_items, int32_t d, float* scores, void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * On-device ranking metrics (precision/recall/NDCG sums over users)
  * replaces  test_one_batch/getLabel/RecallPrecision_ATk/NDCGatK_r

@@ -656,6 +656,26 @@ def test_score_dense_bit_exact(lg, orc):
     assert np.array_equal(got.cpu().numpy(), orc.score_dense_exact(out[:nu], out[nu:], users))
 
 
+@pytest.mark.parametrize("Bt,ni", [(100, 40981), (333, 16384 + 77), (2048, 38048), (5, 130)])
+def test_score_dense_tensor_core_3xtf32_accuracy(lg, orc, Bt, ni):
+    """getUsersRating on tcgen05 (3xTF32: hi/lo operand split, fp32 TMEM accumulation) against the fp64 product:
+    |err| <= 2e-6 |u||v| (fp32 class; plain TF32 would be ~1e-3), every cell of the Bt x M matrix written, ragged sizes."""
+    rng = np.random.default_rng(Bt + ni)
+    nu, d = max(Bt, 400), 64
+    U = (rng.normal(0, 1, (nu, d)) * rng.uniform(0.01, 3.0, (nu, 1))).astype(np.float32)
+    V = (rng.normal(0, 1, (ni, d)) * rng.uniform(0.01, 3.0, (ni, 1))).astype(np.float32)
+    users = rng.permutation(nu)[:Bt].astype(np.int64)
+    got = lg.ops.score_dense_tc(dev(U), dev(V), dev(users)).cpu().numpy()
+    assert got.shape == (Bt, ni) and np.isfinite(got).all()
+    ref = U[users].astype(np.float64) @ V.astype(np.float64).T
+    bound = np.linalg.norm(U[users], axis=1)[:, None] * np.linalg.norm(V, axis=1)[None, :]
+    assert np.max(np.abs(got - ref) / bound) < 2e-6
+    exact = lg.ops.score_dense(dev(U), dev(V), dev(users)).cpu().numpy()          # the bit-exact FMA-chain kernel
+    assert np.max(np.abs(got - exact) / bound) < 2e-6
+    got2 = lg.ops.score_dense_tc(dev(U[:Bt]), dev(V), None).cpu().numpy()         # users = None: rows 0..Bt-1
+    assert np.max(np.abs(got2 - U[:Bt].astype(np.float64) @ V.astype(np.float64).T) / (np.linalg.norm(U[:Bt], axis=1)[:, None] * np.linalg.norm(V, axis=1)[None, :])) < 2e-6
+
+
 def test_score_topk_full_size_against_fp64(lg):
     """yelp2018 shape, all users: against fp64 scores the indices may differ only at near-ties."""
     gr = lg.synth.make_graph('yelp2018')
