@@ -236,6 +236,7 @@ class Engine:
             dist.barrier(group)
         # batch staging: [ctl(4 x int32) | users | pos | neg] in one block so that a host batch is one H2D
         self.pg = None              # popularity-gate variant (enable_popgate): MLP parameter block + its Adam state
+        self.i2i = None             # item-item smoothing variant (enable_i2i)
         self._alloc_batch(self.B_cap)
         self._epoch = None          # (S tensor [3,cap], ctl) for epoch-resident mode
         self._graphs = {}
@@ -249,6 +250,18 @@ class Engine:
         self.pg = dict(pop=item_pop, params=params, H1=int(pop_hidden), H2=int(gate_hidden), temp=float(temperature), coeff=float(entropy_coeff),
                        grad=torch.zeros_like(params), M=torch.zeros_like(params), V=torch.zeros_like(params),
                        ws=ops.popgate_workspace(self.B_cap, self.device))
+        self._graphs = {}
+
+    def enable_i2i(self, i2i, i2i_t, alpha):
+        """Train the item-item smoothing variant (code/model.py:228-229: items <- items + alpha * I2I @ items on the
+        propagated item table) through the fused step: one more K1 product with the explicit-value item CSR after the
+        propagation, and one with its transpose before the backward chain.  Single GPU; dead-row pruning is off (the
+        smoothing reads the propagated rows of every neighbour in the item graph)."""
+        if self.dist_mode is not None:
+            raise NotImplementedError("the fused item-item step is single-GPU; use bpr_loss().backward() under dist_mode")
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.i2i = dict(A=i2i, At=i2i_t, alpha=float(alpha), outS=torch.zeros((self.N, self.d), **f32), G2=torch.zeros((self.N, self.d), **f32))
+        self.prune = False
         self._graphs = {}
 
     def _take_block(self):
@@ -477,6 +490,12 @@ class Engine:
                 ops.batch_masks(users, pos, neg, self.B_cap, ctl, self.nu, self.csr, self.m0, None)
             masks = (self.m0, None)
         self.forward(masks)
+        out, G_chain = self.out, self.G
+        if self.i2i is not None:
+            ii, nu = self.i2i, self.nu
+            out = ii['outS']
+            out[:nu].copy_(self.out[:nu])
+            ops.spmm(ii['A'], self.out[nu:], out[nu:], ii['alpha'], 1.0, [self.out[nu:]])      # items + alpha * I2I @ items
         if self.dist_mode == 'dp':
             import torch.distributed as dist
             ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
@@ -485,15 +504,20 @@ class Engine:
             dist.all_reduce(self.loss_out[:3], group=self.group)
         elif self.pg is not None:
             pg = self.pg
-            ops.popgate_bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, pg['pop'], pg['params'], pg['H1'], pg['H2'],
+            ops.popgate_bpr_fwd_bwd(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, pg['pop'], pg['params'], pg['H1'], pg['H2'],
                                     pg['temp'], pg['coeff'], self.decay, self.loss_out, self.G, pg['grad'], pg['ws'])
         else:
-            ops.bpr_fwd_bwd(self.out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
+            ops.bpr_fwd_bwd(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
                             self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
+        if self.i2i is not None:    # back through the smoothing: dL/d(items) = G' + alpha * I2I^T @ G'
+            ii, nu = self.i2i, self.nu
+            G_chain = ii['G2']
+            G_chain[:nu].copy_(self.G[:nu])
+            ops.spmm(ii['At'], self.G[nu:], G_chain[nu:], ii['alpha'], 1.0, [self.G[nu:]])
         r0, r1 = self.r0, self.r1
         Mo, Vo = (self.M, self.V) if self._mv_local else (self.M[r0:r1], self.V[r0:r1])
         if self.L == 0:
-            ops.adam(self.E0[r0:r1], Mo, Vo, self.G[r0:r1], self.scalars)
+            ops.adam(self.E0[r0:r1], Mo, Vo, G_chain[r0:r1], self.scalars)
         else:
             g = self.local if self.dist_mode == 'rowpart' else self.csr
 
@@ -507,7 +531,7 @@ class Engine:
                               mc_p=(mc_e0 + r0 * self.d * 4) if mc_e0 else 0)
                 if peers_e0 is not None or mc_e0:        # the updated parameter rows are already in every replica
                     self._rank_barrier()
-            self._backward_chain(self.G, last)
+            self._backward_chain(G_chain, last)
         if self.pg is not None:     # the 8 MLP tensors are one flat block: one dense Adam launch, same step scalars
             ops.adam(self.pg['params'], self.pg['M'], self.pg['V'], self.pg['grad'], self.scalars)
             self.pg['grad'].zero_()

@@ -202,13 +202,17 @@ class LightGCN(nn.Module):
             except Exception as e:      # the reference only warns and carries on without the item graph
                 world.cprint(f"[I2I] WARNING: cannot load {config['i2i_path']}: {e}")
                 self._i2i = self._i2i_t = None
+        if (self._i2i is not None and self.i2i_alpha > 0.0 and not self.use_pop_gate and config.get('dist_mode') is None
+                and config.get('i2i_kernel_step', True)):
+            self._engine.enable_i2i(self._i2i, self._i2i_t, self.i2i_alpha)
 
     @property
     def plain(self):
-        """True when the fused training step applies: the plain model, or the popularity gate with its kernels enabled
-        (csrc/popgate.cu).  Item-item smoothing trains through bpr_loss().backward()."""
+        """True when the fused training step applies: the plain model, the popularity gate with its kernels enabled
+        (csrc/popgate.cu), or item-item smoothing (two more K1 products).  Both variants at once train through
+        bpr_loss().backward()."""
         if self._i2i is not None and self.i2i_alpha > 0.0:
-            return False
+            return self._engine.i2i is not None                      # item-item smoothing: two more K1 products in the step
         return (not self.use_pop_gate) or getattr(self, '_pg_flat', None) is not None
 
     def popgate_tensors(self):
@@ -413,7 +417,7 @@ class LightGCN(nn.Module):
         """stageOne without autograd: forward, BPR, backward and Adam in one captured sequence.
         Returns the engine (loss in engine.loss_out on the device)."""
         if not self.plain:
-            raise RuntimeError("the fused step covers the plain and pop-gate models; item-item smoothing trains through bpr_loss().backward()")
+            raise RuntimeError("the fused step covers the plain model and ONE variant (pop-gate or item-item); both at once train through bpr_loss().backward()")
         if not self._params_packed():
             self._pack_params()
         if self.use_pop_gate and not self._popgate_packed():

@@ -275,11 +275,12 @@ def _variant_model(lg, g, tmp_path, kind):
     if kind.startswith('popgate'):
         over = dict(use_pop_gate=True, popgate_kernel=(kind == 'popgate'))
     else:
+        over_extra = dict(i2i_kernel_step=(kind == 'i2i'))
         import scipy.sparse as sp
         ni = int(g['m_items'])
         m = sp.csr_matrix((g['i2i_data'], g['i2i_indices'], g['i2i_indptr']), shape=(ni, ni))
         path = str(tmp_path / 'i2i.npz'); sp.save_npz(path, m)
-        over = dict(use_item_item=True, i2i_path=path, i2i_alpha=float(g['i2i_alpha']))
+        over = dict(use_item_item=True, i2i_path=path, i2i_alpha=float(g['i2i_alpha']), **over_extra)
     cfg, ds, m = make_model(lg, g, **over)
     if kind.startswith('popgate'):
         sd = {k[3:].replace('__', '.'): torch.from_numpy(v) for k, v in g.items() if k.startswith('sd_')}
@@ -288,14 +289,14 @@ def _variant_model(lg, g, tmp_path, kind):
     return cfg, ds, m
 
 
-@pytest.mark.parametrize("kind", ["popgate", "popgate_autograd", "i2i"])
+@pytest.mark.parametrize("kind", ["popgate", "popgate_autograd", "i2i", "i2i_autograd"])
 def test_model_variants_match_reference(lg, tmp_path, kind):
     """use_pop_gate / use_item_item: loss, gradients, three optimiser steps and scores against the real reference.
     'popgate' trains through the FUSED step (csrc/popgate.cu: fusion + BPR + closed-form backward + fused Adam on the MLP
     block), 'popgate_autograd' / 'i2i' through bpr_loss().backward() + torch Adam on top of the kernel-backed propagation."""
-    g = load_golden('popgate' if kind.startswith('popgate') else kind)
+    g = load_golden('popgate' if kind.startswith('popgate') else 'i2i')
     cfg, ds, m = _variant_model(lg, g, tmp_path, kind)
-    assert m.plain == (kind == 'popgate')
+    assert m.plain == (kind in ('popgate', 'i2i'))
     nu = int(g['n_users'])
     with torch.no_grad():
         out = torch.cat(m.computer()).cpu().numpy()
@@ -330,7 +331,7 @@ def test_model_variants_match_reference(lg, tmp_path, kind):
         eng.G.zero_(); eng.pg['grad'].zero_()
     m.zero_grad()
     bpr = lg.utils.BPRLoss(m, cfg)
-    assert bpr.fused == (kind == 'popgate')
+    assert bpr.fused == (kind in ('popgate', 'i2i'))
     B = len(g['users'])
     for s in range(3):
         l = bpr.stageOne(*(t.cuda() for t in triples(g, (s * 17) % B)))
