@@ -13,10 +13,12 @@
 //   pass 1   score_tc_kernel<1>: CTA = 256 users (two 128-row MMA tiles sharing every B tile) x a split of the
 //            item tiles.  warp 0 = TMA producer (4-stage ring of 128-item tiles), warp 1 = MMA issuer
 //            (16 x tcgen05.mma.kind::tf32 M128 N128 K8 per tile, double-buffered TMEM accumulators), warps 2-17 =
-//            epilogue, in pass 1 two groups of 8 warps taking alternate tiles: a thread owns one row and reads the
-//            FIRST 64 items of the tile (tcgen05.ld 32x32b.x32) — a 50 % sample, which halves the TMEM traffic — and
-//            reduces them to ONE number, the largest approximate score among the sampled items that are NOT train
-//            items of the row (a cursor walks the sorted position-space mask row) -> sample maxima Mx[row][tile].
+//            epilogue.  Pass 1 only needs a SAMPLE to place the threshold, so it runs the GEMM on every other tile
+//            (global tile index even — with the interleaved item layout any fixed set of tiles is a fair sample of
+//            the ids; round 1 ran all tiles and read half of each: same 50 % sample, twice the MMA work): a thread
+//            owns one row and one 64-item half of every sampled tile (tcgen05.ld 32x32b.x32) and reduces it to ONE
+//            number, the largest approximate score among those items that are NOT train items of the row (a cursor
+//            walks the sorted position-space mask row) -> sample maxima Mx[row][tile + half].
 //   select   tc_select_kernel: warp per row, radix select: the KSEL-th largest sample maximum is the row threshold
 //            tau.  KSEL unmasked sampled items score >= tau, hence about 2*KSEL +- sqrt(2*KSEL) items overall (any
 //            tau is SAFE — the certificate below does not depend on how it was chosen; a poor tau only costs time).
@@ -275,11 +277,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int t_begin = blockIdx.y * a.tiles_per_split;
     const int t_end = min(n_item_tiles, t_begin + a.tiles_per_split);
     const int n_tiles = t_end - t_begin;
+    // tiles this launch processes: all of them (pass 2), or those with an even GLOBAL index (pass 1: the sample)
+    const int it_first = (PASS == 1) ? (t_begin & 1) : 0, it_step = (PASS == 1) ? 2 : 1;
+    const int n_proc = (n_tiles > it_first) ? (n_tiles - it_first + it_step - 1) / it_step : 0;
 
     if (threadIdx.x == 0) {
         mbar_init(BAR(0), 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
-        for (int c = 0; c < 2; ++c) { mbar_init(BAR(T_FULL + c), 1); mbar_init(BAR(T_EMPTY + c), PASS == 1 ? 16 * TC_EPI_WARPS : 32 * TC_EPI_WARPS); }   // pass 1: one group per buffer
+        for (int c = 0; c < 2; ++c) { mbar_init(BAR(T_FULL + c), 1); mbar_init(BAR(T_EMPTY + c), 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -298,8 +303,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int rt = 0; rt < TC_RT; ++rt)
                 for (int ka = 0; ka < 2; ++ka)
                     tma_load_2d(smem_u32(sA + (rt * 2 + ka) * TC_A_ATOM_BYTES), &map_a, BAR(0), ka * TC_ATOM_K, ub + rt * TC_M);
-            for (int it = 0; it < n_tiles; ++it) {
-                const int s = it % TC_STAGES, r = it / TC_STAGES;
+            for (int j = 0; j < n_proc; ++j) {
+                const int it = it_first + j * it_step;
+                const int s = j % TC_STAGES, r = j / TC_STAGES;
                 mbar_wait(BAR(B_EMPTY + s), (r & 1) ^ 1);
                 mbar_expect_tx(BAR(B_FULL + s), TC_B_STAGE_BYTES);
                 const int ib = (t_begin + it) * TC_N;
@@ -316,7 +322,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const bool leader = (lane == 0);
         mbar_wait(BAR(0), 0);
         const uint64_t da0 = umma_desc_k_sw128(smem_u32(sA));
-        for (int it = 0; it < n_tiles; ++it) {
+        for (int it = 0; it < n_proc; ++it) {                      // it = index among the processed tiles
             const int s = it % TC_STAGES, r = it / TC_STAGES, acc = it & 1, ra = it >> 1;
             mbar_wait(BAR(B_FULL + s), r & 1);                     // B tile landed
             mbar_wait(BAR(T_EMPTY + acc), (ra & 1) ^ 1);           // accumulator pair drained by the epilogue
@@ -343,14 +349,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ================= epilogue: a thread owns one row; pass 2: one 64-item half of every tile, pass 1: the first half of every
         // other tile (group g = e / 8 takes the tiles with it % 2 == g, i.e. always the same accumulator buffer) =================
         const int e = warp - 2, q = warp & 3, rt = (e >> 2) & 1, grp = e >> 3;    // TMEM lane quarter q = warp % 4 is a hardware rule
-        const int half = (PASS == 1) ? 0 : grp;
+        const int half = grp;
         const int row = ub + rt * TC_M + q * 32 + lane;
         const bool live = row < a.Bt;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rt * TC_N + half * TC_HALF);
         uint32_t ra_[32], rb_[32];
 
         if (PASS == 3) {                                           // debug: MMA-only pacing (accumulators released unread)
-            for (int it = 0; it < n_tiles; ++it) {
+            for (int it = 0; it < n_proc; ++it) {
                 const int acc = it & 1, rph = it >> 1;
                 mbar_wait(BAR(T_FULL + acc), rph & 1);
                 tc_fence_after();
@@ -358,25 +364,27 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_arrive(BAR(T_EMPTY + acc));
             }
         } else         if (PASS == 1) {
-            // ---- maxima over 64 items, staged TC_STG tiles at a time so that the global stores are row segments ----
+            // ---- maxima over the warp's 64-item half of every SAMPLED tile, staged TC_STG at a time so that the global
+            // stores are row segments; entry (global tile + half) of the row: consecutive staged entries are 2 apart ----
             float* my = stg + e * (32 * TC_STG);                   // slot(row l, p) = l*TC_STG + ((p + l) % TC_STG)
             int nbuf = 0;
             float* out_rows = a.tile_max + (size_t)(ub + rt * TC_M + q * 32) * a.tile_stride;
             auto flush = [&](int t0) {
                 __syncwarp();
                 for (int rr = (lane >> 4); rr < 32; rr += 2) {                       // two rows per step, 16 lanes each
-                    const int p = lane & (TC_STG - 1);                              // staged tiles are 2 apart (the other group has the rest)
+                    const int p = lane & (TC_STG - 1);
                     if (p < nbuf) out_rows[(size_t)rr * a.tile_stride + t0 + 2 * p] = my[rr * TC_STG + ((p + rr) & (TC_STG - 1))];
                 }
                 __syncwarp();
             };
             TcMaskCursor mc; mc.init(a, live, row, t_begin * TC_N);
-            int first_staged = t_begin + grp;
-            for (int it = grp; it < n_tiles; it += 2) {
-                const int acc = grp, rph = it >> 1;
+            int first_staged = t_begin + it_first + half;
+            for (int j = 0; j < n_proc; ++j) {
+                const int it = it_first + 2 * j;
+                const int acc = j & 1, rph = j >> 1;
                 const int ib = (t_begin + it) * TC_N;
                 unsigned long long mb0, mb1;
-                mc.tile_bits(ib, mb0, mb1);                        // before the wait: overlaps the MMA of this tile
+                mc.tile_bits(ib, mb0, mb1);                        // before the wait: overlaps the MMA of this tile (entries of the skipped tile are dropped)
                 const unsigned long long mb = half ? mb1 : mb0;
                 mbar_wait(BAR(T_FULL + acc), rph & 1);
                 tc_fence_after();
@@ -385,14 +393,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait(ra_); tmem_ld_fence(rb_);
                 tc_fence_before();
                 mbar_arrive(BAR(T_EMPTY + acc));                   // accumulator free: this warp's part is in registers
-                // train items of the row take no part
+                // train items of the row take no part; block 127 is missing in this tile: slot 127 (half 1) if the residue is even,
+                // slot 63 (half 0) if it is odd
                 const int res1 = tc_residue_of_tile(t_begin + it, a.order);
-                const unsigned hole1 = ((res1 & 1) && res1 >= a.hole_from_residue) ? 0x80000000u : 0u;      // slot 63 of an odd residue
+                const unsigned hole1 = (res1 >= a.hole_from_residue && ((res1 & 1) ^ half)) ? 0x80000000u : 0u;
                 const unsigned bad0 = (unsigned)mb, bad1 = (unsigned)(mb >> 32) | hole1;
                 if (bad0) tc_kill_columns(ra_, bad0);
                 if (bad1) tc_kill_columns(rb_, bad1);
                 my[lane * TC_STG + ((nbuf + lane) & (TC_STG - 1))] = fmaxf(tc_max32(ra_), tc_max32(rb_));
-                if (++nbuf == TC_STG) { flush(first_staged); nbuf = 0; first_staged = t_begin + it + 2; }
+                if (++nbuf == TC_STG) { flush(first_staged); nbuf = 0; first_staged = t_begin + it + 2 + half; }
             }
             if (nbuf) flush(first_staged);
         } else {
@@ -854,7 +863,7 @@ static TcLayout tc_layout(int Bt, int m_items) {
     L.n_splits = tc_pick_splits(Bt, m_items);
     L.tiles_per_split = (L.item_tiles + L.n_splits - 1) / L.n_splits;
     L.n_splits = (L.item_tiles + L.tiles_per_split - 1) / L.tiles_per_split;
-    L.tile_stride = L.item_tiles;
+    L.tile_stride = (L.item_tiles + 3) & ~1;          // sample maxima: entry (even tile + half), at most item_tiles + 1 of them
     size_t o = align_up((size_t)L.bt_pad * TC_D * 4, 1024);
     L.off_vp = o;   o += align_up((size_t)L.item_tiles * TC_N * TC_D * 4, 1024);
     L.off_mx = o;   o += align_up((size_t)L.bt_pad * L.tile_stride * 4, 256);
@@ -933,7 +942,8 @@ extern "C" int lgcn_score_topk_tc(const float* users_emb, const float* items_emb
     dim3 grid(L.bt_pad / TC_ROWS, L.n_splits);
     score_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
     LGCN_CHECK_LAUNCH("score_tc_kernel<1>");
-    tc_select_kernel<<<(Bt + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(Bt, L.item_tiles, tile_max, L.tile_stride, TC_KSEL, tau);
+    // one maximum per 64-item half of every even tile: 2 * ceil(T / 2) entries per row
+    tc_select_kernel<<<(Bt + SEL_WARPS - 1) / SEL_WARPS, SEL_WARPS * 32, 0, st>>>(Bt, 2 * ((L.item_tiles + 1) / 2), tile_max, L.tile_stride, TC_KSEL, tau);
     LGCN_CHECK_LAUNCH("tc_select_kernel");
     score_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, a);
     LGCN_CHECK_LAUNCH("score_tc_kernel<2>");

@@ -362,7 +362,7 @@ def test_native_parser_fuzz_against_python_split(tmp_path):
 @pytest.mark.parametrize("kind", ["random", "popular_adjacent_ids"])
 def test_tensor_core_threshold_rule_on_the_host(kind):
     """The selection rule of the tensor-core ranking, replayed with numpy over the library's own item layout: tau = the
-    28th largest maximum over the sampled half (slots 0-63) of every tile.  Claims checked: at least 28 and on the order
+    28th largest maximum over the 64-item halves of every EVEN tile (the 50 % sample pass 1 scores).  Claims checked: at least 28 and on the order
     of 56 items reach tau, the k = 20 best items are comfortably above it, and no (split, half) event list of a row gets
     more than its 32 slots — for random embeddings AND for the trained-model picture (popular items = adjacent small
     ids, large norms, best for everybody), which in plain id order put > 100 hits into one list."""
@@ -386,7 +386,7 @@ def test_tensor_core_threshold_rule_on_the_host(kind):
         for u in range(nu):
             sp = np.full(T * 128, -np.inf, dtype=np.float32); sp[positions] = S[u]
             tiles = sp.reshape(T, 128)
-            tau = np.sort(tiles[:, :64].max(axis=1))[-28]
+            tau = np.sort(tiles[0::2].reshape(-1, 2, 64).max(axis=2).ravel())[-28]
             hit_pos = np.nonzero(sp >= tau)[0]
             lists = np.bincount((hit_pos // 128 // per) * 2 + (hit_pos % 128) // 64, minlength=2 * n_splits)
             if layout == "interleaved":
