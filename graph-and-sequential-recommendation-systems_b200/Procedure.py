@@ -169,9 +169,9 @@ def rank_all(dataset, Recmodel, k, user_tile=8192):
             hi = min(hi_r, lo + user_tile)
             idx, _ = Recmodel.rank_topk(users_dev[lo:hi], k)
             mine[lo - lo_r:hi - lo_r] = idx
-        allb = torch.empty((nranks, per, k), dtype=torch.int64, device=users_dev.device)
+        allb = torch.empty((nranks * per, k), dtype=torch.int64, device=users_dev.device)
         dist.all_gather_into_tensor(allb, mine, group=group)
-        return allb.view(nranks * per, k)[:n].contiguous()
+        return allb[:n].contiguous()
     out = []
     for lo in range(0, n, user_tile):
         idx, _ = Recmodel.rank_topk(users_dev[lo:lo + user_tile], k)

@@ -80,3 +80,92 @@ def test_rowpart_and_dp_host_logic_world2():
         assert p.exitcode == 0
     res = sorted(q.get(timeout=10) for _ in range(2))
     assert res == [(0, True, True, True), (1, True, True, True)]
+
+
+def test_rebalance_by_time_equalises_predicted_time():
+    """engine.rebalance_by_time: blocks whose measured time per unit of cost differs (item rows gather from the larger
+    table) are re-cut so that every block is predicted to take the same time."""
+    import lgcn_b200 as lg
+    rng = np.random.default_rng(0)
+    deg = rng.integers(1, 60, 4000)
+    indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(deg)]).astype(np.int64))
+    speed = np.where(np.arange(4000) < 3000, 1.0, 3.0)                    # last quarter of the rows is 3x slower per non-zero
+    true_prefix = np.concatenate([[0], np.cumsum(deg * speed)])
+    bounds = lg.engine.balanced_row_bounds(indptr, 4)
+    for _ in range(4):
+        times = [true_prefix[b1] - true_prefix[b0] for b0, b1 in zip(bounds, bounds[1:])]
+        bounds = lg.engine.rebalance_by_time(indptr, bounds, times)
+        assert bounds[0] == 0 and bounds[-1] == 4000 and all(a <= b for a, b in zip(bounds, bounds[1:]))
+    times = [true_prefix[b1] - true_prefix[b0] for b0, b1 in zip(bounds, bounds[1:])]
+    assert max(times) < 1.1 * min(times), times
+
+
+class _StubEngine:
+    def __init__(self, rank, world):
+        self.dist_mode, self.rank, self.world, self.group = 'rowpart', rank, world, None
+
+
+class _StubModel:
+    """Stands in for LightGCN in the host-side sharding logic of Procedure.rank_all: the 'ranking' of user u is a fixed
+    function of u, so the multi-rank assembly can be compared with the single-process result."""
+    def __init__(self, rank, world):
+        self._engine = _StubEngine(rank, world)
+        self.calls = 0
+
+    def computer(self):
+        self.calls += 1
+
+    def rank_topk(self, users, k):
+        idx = users.view(-1, 1) * 1000 + torch.arange(k, dtype=torch.int64).view(1, -1)
+        return idx, idx.to(torch.float32)
+
+
+class _StubDataset:
+    def __init__(self, n):
+        self._users = torch.arange(7, 7 + n, dtype=torch.int64)
+
+    def test_csr(self):
+        return self._users, None, None
+
+
+def _procedure_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import lgcn_b200 as lg
+        from lgcn_b200 import Procedure
+        ok = True
+        for n in (1, 5, 64, 101):                                   # fewer users than ranks, ragged shards, several tiles
+            ds = _StubDataset(n)
+            got = Procedure.rank_all(ds, _StubModel(rank, world), 4, user_tile=16)
+            want, _ = _StubModel(0, 1).rank_topk(ds._users, 4)
+            ok = ok and got.shape == (n, 4) and bool(torch.equal(got, want))
+        # every rank must feed the same triples: identical passes, different raises on every rank
+        same = torch.arange(30, dtype=torch.int64).view(3, 10)
+        Procedure._assert_same_on_every_rank(same, None, "triples")
+        diff = same.clone(); diff[1, 3] += rank
+        raised = False
+        try:
+            Procedure._assert_same_on_every_rank(diff, None, "triples")
+        except RuntimeError:
+            raised = True
+        q.put((rank, bool(ok), raised))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_procedure_sharding_host_logic_world2():
+    """Procedure.rank_all under dist_mode='rowpart' (users sharded in contiguous blocks, lists all-gathered, trimmed) equals
+    the single-process ranking, and the same-triples guard fires — over gloo, no GPU."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_procedure_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert res == [(0, True, True), (1, True, True)]
