@@ -49,6 +49,7 @@ _SIGNATURES = {
     "lgcn_csr_rows_emit": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
     "lgcn_csr_rows_finish": (ctypes.c_int, [c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "lgcn_rank_barrier": (ctypes.c_int, [_P, POINTER(c_void_p), c_int32, c_int32, _P, _P, c_int32, _P]),
+    "lgcn_copy_words": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P]),
     "lgcn_coo_to_csr": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
     "lgcn_spmm_plan_count": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P]),
     "lgcn_spmm_plan_count_slab": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),

@@ -51,9 +51,28 @@ __global__ void __launch_bounds__(32) rank_barrier_kernel(const __grid_constant_
     if (t == 0) *a.epoch = e;
 }
 
+// Copy between device memory and MAPPED PINNED HOST memory from a kernel (16-byte words).  Put at the two ends of the
+// captured training step, it replaces the cudaMemcpyAsync H2D of the batch and the D2H of the loss: no copy-engine hop
+// between the copies and the kernels, and stageOne becomes "write the pinned staging block, replay one graph, wait".
+__global__ void __launch_bounds__(256) copy16_kernel(int4* __restrict__ dst, const int4* __restrict__ src, long long n16, int to_host) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) dst[i] = src[i];
+    if (to_host) __threadfence_system();
+}
+
 }  // namespace lgcn
 
 using namespace lgcn;
+
+extern "C" int lgcn_copy_words(void* dst, const void* src, int64_t n_bytes, int32_t dst_is_host, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(dst && src && n_bytes >= 0 && n_bytes % 16 == 0, "copy_words: bad arguments (n_bytes must be a multiple of 16)");
+    LGCN_CHECK_ARG(((uintptr_t)dst % 16) == 0 && ((uintptr_t)src % 16) == 0, "copy_words: 16-byte alignment required");
+    if (n_bytes == 0) return 0;
+    const long long n16 = n_bytes / 16;
+    copy16_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, as_stream(stream)>>>(static_cast<int4*>(dst), static_cast<const int4*>(src), n16, dst_is_host ? 1 : 0);
+    LGCN_CHECK_LAUNCH("copy16_kernel");
+    return 0;
+}
 
 extern "C" int lgcn_rank_barrier(uint32_t* flags_local, void* const* peer_flags_host, int32_t rank, int32_t world,
                                  uint32_t* epoch_dev, int32_t* err_dev, int32_t timeout_ms, lgcn_stream_t stream) {

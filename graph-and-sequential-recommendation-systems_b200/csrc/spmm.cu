@@ -37,6 +37,7 @@
 //
 // HBM roofline: B_spmm = 8*nnz + 4*(N+1) + 8*N*d bytes per layer.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace lgcn {
 
@@ -76,9 +77,21 @@ __device__ __forceinline__ void st_f4_policy(float4* p, const float4& v, unsigne
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
+// Programmatic dependent launch (PDL): a K1 launched with the programmatic-serialization attribute may START while its
+// predecessor is still draining — its CTAs read their work item and prefetch the first (col,val) chunk (static data: the
+// plan and the CSR are never written inside a step), then wait here until the predecessor has completed and its writes are
+// visible.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool mask_bit(const unsigned* m, int i) { return (__ldg(m + (i >> 5)) >> (i & 31)) & 1u; }
 
 static int g_variant = 0;      // tuning variant of the d=64 kernels (lgcn_debug_spmm_variant, profiling hook)
+static int g_pdl = -1;              // programmatic dependent launch of K1 (LGCN_PDL=0 disables, lgcn_debug_spmm_variant(200/201) toggles)
+static bool pdl_enabled() {
+    if (g_pdl < 0) { const char* e = getenv("LGCN_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
+    return g_pdl == 1;
+}
 static int g_blocked_variant = 0;   // items per group of the column-blocked kernel: 0 -> 4 (shipped), 1 -> 1, 2 -> 8, 3 -> 2 (variant 100 + x)
 
 __device__ __forceinline__ float4 gather_f4(const float4* p) {
@@ -112,6 +125,7 @@ __device__ __forceinline__ void accumulate_item(const SpmmArgs& a, int start, in
     int j = start + min(lane, cnt - 1);                     // lanes past the end: last valid entry, weight 0
     int c_nxt = ld_c(a.indices + j);
     float v_nxt = lane < cnt ? ld_v(a.vals + j) : 0.f;
+    griddep_wait();                                         // X (and everything the epilogue touches) comes from the previous kernel
     for (int base = start; base < end; base += LANES) {
         const int c = c_nxt; const float v = v_nxt;
         const int cur = cnt;
@@ -304,12 +318,17 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
     } else {
         row = (int)gidx; start = __ldg(a.indptr + row); end = __ldg(a.indptr + row + 1); seg_ref = -1;
     }
-    if (a.row_mask != nullptr && !mask_bit(a.row_mask, row)) return;     // dead row: nobody reads it this step
+    if (a.row_mask != nullptr) {
+        griddep_wait();                                                   // the bitmap was written earlier in this step
+        if (!mask_bit(a.row_mask, row)) return;                           // dead row: nobody reads it this step
+    }
     float4 acc[VPL];
 #pragma unroll
     for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
-    if constexpr (MASKED) accumulate_item_masked<D, LANES, UNROLL>(a, start, end, lane, gmask, (threadIdx.x & 31) / LANES * LANES, acc);
+    if constexpr (MASKED) { griddep_wait(); accumulate_item_masked<D, LANES, UNROLL>(a, start, end, lane, gmask, (threadIdx.x & 31) / LANES * LANES, acc); }
     else accumulate_item<D, LANES, UNROLL, false>(a, start, end, lane, gmask, acc);
+    griddep_wait();                                                       // (empty items skip the wait inside accumulate_item)
+    griddep_launch_dependents();
     finish_item<D, LANES, ADAM, false>(a, row, lane, gmask, seg_ref, acc);
 }
 
@@ -500,6 +519,17 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
         LGCN_CHECK_LAUNCH("spmm_kernel<masked>");
         return 0;
     }
+    if (pdl_enabled()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, spmm_kernel<D, LANES, UNROLL, ADAM, THREADS, MINB>, a);
+        if (e != cudaSuccess) return fail("spmm_kernel (programmatic dependent launch): %s", cudaGetErrorString(e));
+        return 0;
+    }
     spmm_kernel<D, LANES, UNROLL, ADAM, THREADS, MINB><<<(unsigned)blocks, THREADS, 0, st>>>(a);
     LGCN_CHECK_LAUNCH("spmm_kernel");
     return 0;
@@ -668,6 +698,7 @@ extern "C" int lgcn_debug_gather_rows(const float* X, const int32_t* idx, int64_
 }
 
 extern "C" int lgcn_debug_spmm_variant(int variant) {
+    if (variant == 200 || variant == 201) { const int old = 200 + (pdl_enabled() ? 1 : 0); g_pdl = variant - 200; return old; }
     if (variant >= 100) { const int old = 100 + g_blocked_variant; g_blocked_variant = variant - 100; return old; }
     const int old = g_variant; g_variant = variant; return old;
 }

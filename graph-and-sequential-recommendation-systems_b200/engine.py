@@ -162,6 +162,7 @@ class Engine:
         self.device = device
         self.decay, self.lr = float(decay), float(lr)
         self.deterministic = bool(deterministic)
+        self.zero_copy = torch.device(device).type == 'cuda'
         self.B_cap = int(B_cap)
         self.dist_mode = dist_mode
         self.group = group
@@ -325,13 +326,23 @@ class Engine:
         self.bp = self._blk[2 + self.B_cap:2 + 2 * self.B_cap]
         self.bn = self._blk[2 + 2 * self.B_cap:2 + 3 * self.B_cap]
         # two pinned staging buffers: a buffer is rewritten only after the H2D that read it has finished
-        self._stage = [[torch.zeros(2 + 3 * self.B_cap, dtype=torch.int64).pin_memory(), None] for _ in range(2)]
+        self._stage = [[torch.zeros(2 + 3 * self.B_cap, dtype=torch.int64).pin_memory(), None, None] for _ in range(2)]
         self._stage_i = 0
         self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.bpr_ws = ops.bpr_workspace(self.B_cap, self.d, self.device)
         self._graphs = {}
+        # zero-copy staging: a host batch is read straight out of the pinned block by a kernel at the head of the captured
+        # step, and the loss is written into pinned memory by a kernel at its tail (no copy-engine hops, one graph launch)
+        self._zc_slot = None
+        self._loss_host_valid = False
+        if self.zero_copy:
+            ops.copy_words(self._loss_host, self.loss_out, 16, dst_is_host=True)      # loads the kernel before any capture
+            torch.cuda.current_stream().synchronize()
 
     def _stage_batch(self, users, pos, neg, B_global=0):
+        """Put the batch where the step reads it.  Device tensors: device-side copies into the staging block.  Host tensors:
+        fill one of the two pinned blocks; with zero_copy the captured step itself pulls it in (returns the slot), else one
+        H2D memcpy is enqueued here."""
         B = int(users.numel())
         if B > self.B_cap:
             torch.cuda.current_stream().synchronize()
@@ -339,8 +350,9 @@ class Engine:
         self._stage_i ^= 1
         slot = self._stage[self._stage_i]
         if slot[1] is not None:
-            slot[1].synchronize()
+            slot[1].synchronize()                   # the step that read this pinned block two calls ago has consumed it
         h = slot[0]
+        self._zc_slot = None
         if users.is_cuda:
             self.bu[:B].copy_(users.to(torch.int64), non_blocking=True)
             self.bp[:B].copy_(pos.to(torch.int64), non_blocking=True)
@@ -348,22 +360,43 @@ class Engine:
             hc = h[:2].view(torch.int32)
             hc[0], hc[1], hc[2], hc[3] = 0, B, B, B_global
             self._blk[:2].copy_(h[:2], non_blocking=True)
-        else:
-            hc = h[:2].view(torch.int32)
+            if slot[1] is None:
+                slot[1] = torch.cuda.Event()
+            slot[1].record()
+            return B
+        hc = h[:2].view(torch.int32)
+        if slot[2] != (B, B_global):                # the control words rarely change: skip four scalar tensor writes per step
             hc[0], hc[1], hc[2], hc[3] = 0, B, B, B_global
-            cap = self.B_cap
-            h[2:2 + B].copy_(users)
-            h[2 + cap:2 + cap + B].copy_(pos)
-            h[2 + 2 * cap:2 + 2 * cap + B].copy_(neg)
-            if B == cap:
-                self._blk.copy_(h, non_blocking=True)                       # one H2D for the whole batch
-            else:
-                self._blk[:2 + B].copy_(h[:2 + B], non_blocking=True)
-                self._blk[2 + cap:2 + cap + B].copy_(h[2 + cap:2 + cap + B], non_blocking=True)
-                self._blk[2 + 2 * cap:2 + 2 * cap + B].copy_(h[2 + 2 * cap:2 + 2 * cap + B], non_blocking=True)
+            slot[2] = (B, B_global)
+        cap = self.B_cap
+        h[2:2 + B].copy_(users)
+        h[2 + cap:2 + cap + B].copy_(pos)
+        h[2 + 2 * cap:2 + 2 * cap + B].copy_(neg)
+        if self.zero_copy:
+            self._zc_slot = self._stage_i           # _enqueue_step copies the block in with a kernel; the event is recorded after the step
+            return B
+        if B == cap:
+            self._blk.copy_(h, non_blocking=True)                       # one H2D for the whole batch
+        else:
+            self._blk[:2 + B].copy_(h[:2 + B], non_blocking=True)
+            self._blk[2 + cap:2 + cap + B].copy_(h[2 + cap:2 + cap + B], non_blocking=True)
+            self._blk[2 + 2 * cap:2 + 2 * cap + B].copy_(h[2 + 2 * cap:2 + 2 * cap + B], non_blocking=True)
         if slot[1] is None:
             slot[1] = torch.cuda.Event()
         slot[1].record()
+        return B
+
+    def stage_batch_now(self, users, pos, neg, B_global=0):
+        """_stage_batch for callers that launch kernels on the batch themselves (the autograd path): the batch is on the
+        device when this returns (stream-ordered)."""
+        B = self._stage_batch(users, pos, neg, B_global)
+        if self._zc_slot is not None:
+            slot = self._stage[self._zc_slot]
+            ops.copy_words(self._blk, slot[0])
+            if slot[1] is None:
+                slot[1] = torch.cuda.Event()
+            slot[1].record()
+            self._zc_slot = None
         return B
 
     # ------------------------------------------------------------------ collectives
@@ -475,6 +508,8 @@ class Engine:
         only_spmm (measurement): just the step's 2L K1 launches (with their exchanges), on whatever the buffers hold."""
         if only_spmm:
             return self._enqueue_spmm_only()
+        if self._zc_slot is not None:               # host batch: pull the pinned staging block in (kernel, part of the graph)
+            ops.copy_words(self._blk, self._stage[self._zc_slot][0])
         ops.adam_tick(self.scalars)
         masks = None
         if self.prune:
@@ -539,6 +574,8 @@ class Engine:
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
         else:
             ops.bpr_clear_rows(self.G, users, pos, neg, self.B_cap, ctl, self.nu)
+        if self._zc_slot is not None:               # ... and push the loss into pinned memory: loss_to_host() only has to wait
+            ops.copy_words(self._loss_host, self.loss_out, 16, dst_is_host=True)
 
     def _enqueue_spmm_only(self):
         self.forward((self.m0, None) if self.prune else None)
@@ -605,7 +642,15 @@ class Engine:
             B_global = 0
         self._stage_batch(users, pos, neg, B_global)
         self._sync_params_across_ranks()
-        self._run('direct', self.bu, self.bp, self.bn, self.ctl)
+        zc = self._zc_slot
+        self._run('direct' if zc is None else ('host', zc), self.bu, self.bp, self.bn, self.ctl)
+        if zc is not None:
+            slot = self._stage[zc]
+            if slot[1] is None:
+                slot[1] = torch.cuda.Event()
+            slot[1].record()                        # this pinned block may be refilled once the step has run
+        self._loss_host_valid = zc is not None
+        self._zc_slot = None
         self._host_step += 1
         self.param_epoch += 1
 
@@ -636,8 +681,10 @@ class Engine:
         return g[0], g[1], g[2]
 
     def loss_to_host(self):
-        """D2H of {bpr, reg, total, running sum}; synchronises the stream."""
-        self._loss_host.copy_(self.loss_out, non_blocking=True)
+        """{bpr, reg, total, running sum} on the host; synchronises the stream.  After a zero-copy step the values are already
+        in pinned memory (written by the step's last kernel); otherwise one 16-byte D2H."""
+        if not self._loss_host_valid:
+            self._loss_host.copy_(self.loss_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._loss_host
 
@@ -670,6 +717,8 @@ class Engine:
         S, ctl = self._epoch
         self._sync_params_across_ranks()
         ops.batch_advance(ctl, self.B_cap)
+        self._zc_slot = None
+        self._loss_host_valid = False
         self._run('epoch', S[0], S[1], S[2], ctl)
         self._host_step += 1
         self.param_epoch += 1

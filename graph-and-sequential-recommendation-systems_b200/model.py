@@ -74,7 +74,7 @@ class _BprLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, out, users, pos, neg, model):
         eng = model._engine
-        B = eng._stage_batch(users, pos, neg)
+        B = eng.stage_batch_now(users, pos, neg)
         out_c = out.contiguous()
         ops.bpr_fwd_bwd(out_c, eng.bu, eng.bp, eng.bn, eng.B_cap, eng.ctl, eng.nu, eng.ni, 1.0 / max(B, 1), 0.0,
                         0.0, 0.0, eng.loss_out, None, eng.bpr_ws)
@@ -89,7 +89,7 @@ class _BprLoss(torch.autograd.Function):
         model = ctx.model
         eng = model._engine
         out_c, u, p, n = ctx.saved_tensors
-        B = eng._stage_batch(u, p, n)
+        B = eng.stage_batch_now(u, p, n)
         G = eng.scratch()
         G.zero_()
         tmp = torch.empty(4, dtype=torch.float32, device=out_c.device)

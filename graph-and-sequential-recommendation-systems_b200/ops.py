@@ -384,6 +384,12 @@ def gather_probe(X, idx, run=32, variant=0, out=None):
     return out
 
 
+def copy_words(dst, src, n_bytes=None, dst_is_host=False):
+    """Kernel copy between device memory and mapped pinned host memory (lgcn_copy_words); capturable in a CUDA graph."""
+    n = int(n_bytes if n_bytes is not None else src.numel() * src.element_size())
+    _lib.check(_lib.load().lgcn_copy_words(c_void_p(dst.data_ptr()), c_void_p(src.data_ptr()), n, int(bool(dst_is_host)), _stream()), "copy_words")
+
+
 def adam_scalars(device, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
     s = torch.zeros(ctypes.sizeof(_lib.AdamScalars) // 4, dtype=torch.int32, device=device)
     _lib.check(_lib.load().lgcn_adam_init(_p(s), lr, beta1, beta2, eps, int(step), _stream()), "adam_init")

@@ -151,6 +151,13 @@ typedef struct {
 int lgcn_rank_barrier(uint32_t* flags_local, void* const* peer_flags_host, int32_t rank, int32_t world,
                       uint32_t* epoch_dev, int32_t* err_dev, int32_t timeout_ms, lgcn_stream_t stream);
 
+/* Kernel copy of n_bytes (multiple of 16, both pointers 16-byte aligned) where one side may be MAPPED PINNED HOST memory
+ * (with unified addressing every cudaHostAlloc'ed block is): at the two ends of the captured training step it replaces the
+ * H2D memcpy of the batch and the D2H memcpy of the loss (code/Procedure.py:52-54, code/utils.py:64 on the reference side),
+ * so one step through the public API is "fill the pinned staging block, replay one graph, wait".  dst_is_host != 0 adds a
+ * system-scope fence after the stores. */
+int lgcn_copy_words(void* dst, const void* src, int64_t n_bytes, int32_t dst_is_host, lgcn_stream_t stream);
+
 /* counts_out int32[4] = {n_long, n_segs, longest item, rows with an item} (device).  A row is cut into at most 2048 segments. */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,
                          int32_t* counts_out, lgcn_stream_t stream);

@@ -347,6 +347,29 @@ def test_model_variants_match_reference(lg, tmp_path, kind):
         assert np.allclose(res[name], g[name], rtol=0, atol=1e-4)
 
 
+def test_host_batches_zero_copy_equal_device_batches(lg, golden_tiny):
+    """stageOne with pinned-host / pageable-host batches (pulled in by a kernel at the head of the captured step, loss pushed
+    out by a kernel at its tail) == the same steps fed with device tensors, bit for bit — full, short and changing batch sizes."""
+    g = golden_tiny
+    B = len(g['users'])
+    runs = []
+    for where in ('device', 'host', 'pinned'):
+        cfg, _, m = make_model(lg, g, deterministic=True)
+        bpr = lg.utils.BPRLoss(m, cfg)
+        losses = []
+        for s, n in enumerate((B, B, 100, B, 37, 37, B)):
+            t = [torch.from_numpy(np.roll(g[k], s * 11)[:n].copy()).long() for k in ('users', 'pos', 'neg')]
+            if where == 'device':
+                t = [x.cuda() for x in t]
+            elif where == 'pinned':
+                t = [x.pin_memory() for x in t]
+            losses.append(bpr.stageOne(*t))
+        runs.append((losses, params(m)))
+    assert runs[0][0] == runs[1][0] == runs[2][0]
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][1], runs[2][1])
+    assert m._engine.zero_copy and any(isinstance(k, tuple) and k[0] == 'host' for k in m._engine._graphs)
+
+
 def _train_epochs(lg, ds, cfg, epochs, tmp_path):
     lg.utils.set_seed(2020)
     lg.utils.sampler_seed(2020)
