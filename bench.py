@@ -333,6 +333,7 @@ def k1_roofline(lg, eng, csr, tm, step_ms, peak, peak_src, workload):
     gs = eng.spmm_only_graph()
     ts = tm.median_us(gs.replay)
     del gs
+    eng.clear_batch_mask()
     for dst, src in zip((eng.E0, eng.M, eng.V, eng.scalars), saved):
         dst.copy_(src)
     torch.cuda.synchronize()
@@ -674,8 +675,10 @@ def run_ours(args):
     n_k1 = 2 * L_LAYERS
     # adam_tick + [batch_masks: pruning, not under the row partition] + K2 + clear_rows + [batch_advance: resident epoch]
     # + 2L x K1 + [2L x rank_barrier: fused exchange]
-    launches_per_step = n_k1 + 3 + (1 if eng.prune else 0) + (1 if not replicated else 0) + (n_k1 if eng._barrier is not None else 0)
-    launches_per_step_e2e = launches_per_step - (1 if not replicated else 0) + (2 if eng.zero_copy else 0)      # no batch_advance; stage-in + loss-out kernels
+    # step_begin (Adam tick + window advance | host-batch pull) + [batch_masks] + K2 + 2L x K1 + [2L x rank_barrier]
+    # + [clear_rows: only when the Adam-epilogue K1 cannot zero G itself, i.e. under the row partition]
+    launches_per_step = 1 + (1 if eng.prune else 0) + 1 + n_k1 + (n_k1 if eng._barrier is not None else 0) + (1 if mode == 'rowpart' else 0)
+    launches_per_step_e2e = launches_per_step
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True,
             "scaling": "weak" if replicated else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -689,8 +692,8 @@ def run_ours(args):
                       "model_and_graph_setup_s": t_setup},
             "e2e": {"value": samples_per_step * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 + 3 * B * 8, "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / K, "clock": "CUDA events around each stageOne call (H2D + step + loss D2H); the L2 flush between steps is outside the brackets",
-                    "transfers": ("host->device and device->host copies are done by kernels at the two ends of the captured step, reading / writing the "
-                                  "pinned host blocks directly (lgcn_copy_words): %d kernels per step" % launches_per_step_e2e) if eng.zero_copy else "cudaMemcpyAsync",
+                    "transfers": ("no memcpy calls: the head kernel of the captured step pulls the batch out of the pinned host block and K2 writes the loss "
+                                  "record into pinned host memory (%d kernels per step)" % launches_per_step_e2e) if eng.zero_copy else "cudaMemcpyAsync",
                     "wall_value": samples_per_step * K / wall_e2e, "wall_ms_per_step": 1e3 * wall_e2e / K,
                     "wall_note": "host clock over the same loop: includes the 512 MiB L2-flush read between steps (bench scaffolding)",
                     "wall_value_no_flush": samples_per_step * K / wall_nf, "wall_ms_per_step_no_flush": 1e3 * wall_nf / K,

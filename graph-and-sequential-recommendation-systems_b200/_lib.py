@@ -59,19 +59,20 @@ _SIGNATURES = {
     "lgcn_spmm_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
                                      POINTER(c_void_p), c_int32, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
     "lgcn_spmm_adam_f32": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_float,
-                                          POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), _P]),
+                                          POINTER(c_void_p), c_int32, _P, _P, _P, _P, POINTER(SpmmPlan), _P, _P, POINTER(SpmmPeers), c_int32, _P]),
     "lgcn_debug_gather_rows": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_debug_spmm_variant": (ctypes.c_int, [ctypes.c_int]),
     "lgcn_adam_init": (ctypes.c_int, [_P, c_double, c_double, c_double, c_double, c_int32, _P]),
     "lgcn_adam_tick": (ctypes.c_int, [_P, _P]),
+    "lgcn_step_begin": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int64, _P]),
     "lgcn_adam_f32": (ctypes.c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "lgcn_bpr_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "lgcn_bpr_fwd_bwd": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32,
                                         c_float, c_float, c_float, c_float, _P, _P, c_int32, c_int32,
-                                        c_int32, _P, c_size_t, _P]),
+                                        c_int32, _P, c_size_t, _P, _P, _P]),
     "lgcn_bpr_clear_rows": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "lgcn_batch_advance": (ctypes.c_int, [_P, c_int32, _P]),
-    "lgcn_batch_masks": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "lgcn_batch_masks": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),
     "lgcn_batch_masks_rows": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_popgate_param_count": (c_int32, [c_int32, c_int32, c_int32]),
     "lgcn_popgate_fuse": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, _P, _P, c_int32, c_int32, c_float, _P, _P, _P]),

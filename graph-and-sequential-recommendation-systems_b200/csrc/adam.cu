@@ -24,6 +24,23 @@ __global__ void adam_tick_kernel(lgcn_adam_scalars_t* s) {
     adam_refresh(s);
 }
 
+// The head of a captured training step in ONE launch: Adam step counter + bias corrections (thread 0), and either the
+// move of the resident epoch's batch window (thread 0) or the pull of a host batch out of mapped pinned memory (all threads).
+__global__ void __launch_bounds__(256)
+step_begin_kernel(lgcn_adam_scalars_t* s, int* advance_ctl, int B_cap, int4* __restrict__ stage_dst, const int4* __restrict__ stage_src, long long n16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        s->step = s->step + 1;
+        adam_refresh(s);
+        if (advance_ctl != nullptr) {
+            const int off = advance_ctl[0] + advance_ctl[1];
+            int B = advance_ctl[2] - off; if (B > B_cap) B = B_cap; if (B < 0) B = 0;
+            advance_ctl[0] = off; advance_ctl[1] = B;
+        }
+    }
+    if (i < n16) stage_dst[i] = stage_src[i];
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ P, float4* __restrict__ M, float4* __restrict__ V, const float4* __restrict__ G,
             long long n4, const lgcn_adam_scalars_t* __restrict__ sc) {
@@ -71,5 +88,19 @@ extern "C" int lgcn_adam_f32(float* P, float* M, float* V, const float* G, int64
     adam_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(P), reinterpret_cast<float4*>(M),
         reinterpret_cast<float4*>(V), reinterpret_cast<const float4*>(G), n4, scalars_dev);
     LGCN_CHECK_LAUNCH("adam_kernel");
+    return 0;
+}
+
+extern "C" int lgcn_step_begin(lgcn_adam_scalars_t* scalars_dev, int32_t* advance_ctl_dev, int32_t B_cap,
+                               void* stage_dst, const void* stage_src, int64_t stage_bytes, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(scalars_dev && B_cap > 0, "step_begin: null scalars or bad B_cap");
+    LGCN_CHECK_ARG(stage_bytes >= 0 && stage_bytes % 16 == 0 && (stage_bytes == 0 || (stage_dst && stage_src)), "step_begin: bad staging arguments");
+    LGCN_CHECK_ARG(((uintptr_t)stage_dst % 16) == 0 && ((uintptr_t)stage_src % 16) == 0, "step_begin: staging blocks must be 16-byte aligned");
+    LGCN_CHECK_ARG(!(advance_ctl_dev && stage_bytes), "step_begin: a step either advances the resident window or pulls a host batch");
+    const long long n16 = stage_bytes / 16;
+    const unsigned blocks = (unsigned)(n16 > 0 ? (n16 + 255) / 256 : 1);
+    step_begin_kernel<<<blocks, 256, 0, as_stream(stream)>>>(scalars_dev, advance_ctl_dev, B_cap, static_cast<int4*>(stage_dst),
+                                                             static_cast<const int4*>(stage_src), n16);
+    LGCN_CHECK_LAUNCH("step_begin_kernel");
     return 0;
 }

@@ -36,6 +36,9 @@ struct BprArgs {
     float* loss_out; float4* G; int own_begin, own_end;
     int* counter; float* partials; float* coef;   // workspace
     int write_coef; int scatter;
+    unsigned* clear_mask;       // optional: the batch-row bitmap of lgcn_batch_masks — its bits are cleared here (its last reader
+                                // ran before this kernel), so the next step's batch_masks needs no memset
+    float* loss_host;           // optional: mapped pinned host float[4] that receives a copy of loss_out
 };
 
 // 1/B of the means: explicit when > 0, else from the device-resident batch descriptor
@@ -88,6 +91,11 @@ bpr_kernel(const __grid_constant__ BprArgs a) {
         reg_t = 0.5f * (uu + pp + nn);
         const float ca = a.c_bpr * s * inv_norm, cr = a.c_reg * inv_norm;
         if (a.write_coef && lane == 0) a.coef[t] = ca;
+        if (a.clear_mask != nullptr && lane == 0) {
+            atomicAnd(a.clear_mask + (u >> 5), ~(1u << (u & 31)));
+            atomicAnd(a.clear_mask + (p >> 5), ~(1u << (p & 31)));
+            atomicAnd(a.clear_mask + (n >> 5), ~(1u << (n & 31)));
+        }
         if (a.scatter) {
             const bool own_u = (u >= a.own_begin && u < a.own_end);
             const bool own_p = (p >= a.own_begin && p < a.own_end);
@@ -131,7 +139,12 @@ bpr_kernel(const __grid_constant__ BprArgs a) {
             const float bpr = l * inv_norm, reg = r * inv_norm;
             const float total = bpr + a.decay * reg;
             a.loss_out[0] = bpr; a.loss_out[1] = reg; a.loss_out[2] = total;
-            a.loss_out[3] += total;                            // running sum (epoch average), reset by the host
+            const float run = a.loss_out[3] + total;           // running sum (epoch average), reset by the host
+            a.loss_out[3] = run;
+            if (a.loss_host != nullptr) {                      // the host reads the loss without a D2H copy
+                a.loss_host[0] = bpr; a.loss_host[1] = reg; a.loss_host[2] = total; a.loss_host[3] = run;
+                __threadfence_system();
+            }
             *a.counter = 0;
         }
     }
@@ -303,7 +316,7 @@ extern "C" int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const in
                                 int32_t d, float inv_norm, float decay, float c_bpr, float c_reg,
                                 float* loss_out, float* G, int32_t own_begin, int32_t own_end,
                                 int32_t deterministic, void* workspace, size_t workspace_bytes,
-                                lgcn_stream_t stream) {
+                                uint32_t* clear_mask, float* loss_host_mapped, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(out && users && pos && neg && batch_ctl_dev && loss_out, "bpr: null argument");
     LGCN_CHECK_ARG(B_cap > 0, "bpr: B_cap must be > 0");
     LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_bpr_workspace_bytes(B_cap, d), "bpr: workspace too small");
@@ -316,6 +329,7 @@ extern "C" int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const in
     a.B_cap = B_cap; a.ctl = batch_ctl_dev; a.n_users = n_users; a.m_items = m_items;
     a.inv_norm = inv_norm; a.decay = decay; a.c_bpr = c_bpr; a.c_reg = c_reg;
     a.loss_out = loss_out; a.G = reinterpret_cast<float4*>(G); a.own_begin = own_begin; a.own_end = own_end;
+    a.clear_mask = clear_mask; a.loss_host = loss_host_mapped;
     char* w = static_cast<char*>(workspace);
     a.counter = reinterpret_cast<int*>(w);
     a.partials = reinterpret_cast<float*>(w + 16);
@@ -361,12 +375,12 @@ extern "C" int lgcn_batch_advance(int32_t* batch_ctl_dev, int32_t B_cap, lgcn_st
 extern "C" int lgcn_batch_masks(const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t B_cap,
                                 const int32_t* batch_ctl_dev, int32_t n_users, int32_t n_nodes,
                                 const int32_t* indptr, const int32_t* indices, uint32_t* m0, uint32_t* m1,
-                                lgcn_stream_t stream) {
+                                int32_t clear_first, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(users && pos && neg && batch_ctl_dev && m0 && B_cap > 0 && n_nodes > 0, "batch_masks: bad arguments");
     LGCN_CHECK_ARG(m1 == nullptr || (indptr && indices), "batch_masks: m1 needs the CSR");
     cudaStream_t st = as_stream(stream);
     const size_t words = ((size_t)n_nodes + 31) / 32;
-    cudaMemsetAsync(m0, 0, words * 4, st);
+    if (clear_first) cudaMemsetAsync(m0, 0, words * 4, st);
     if (m1) cudaMemsetAsync(m1, 0, words * 4, st);
     const unsigned blocks = (unsigned)((3LL * B_cap * 32 + 255) / 256);
     batch_masks_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(users), reinterpret_cast<const long long*>(pos),

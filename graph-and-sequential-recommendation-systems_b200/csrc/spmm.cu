@@ -57,6 +57,8 @@ struct SpmmArgs {
     // (and of P in the Adam epilogue) over NVLink, so no separate all-gather pass re-reads and re-sends it
     int n_peers; float4* peerY[LGCN_MAX_PEERS]; float4* peerP[LGCN_MAX_PEERS];
     int multicast;      // peerY[0] / peerP[0] are NVSwitch multimem addresses: ONE store reaches every replica
+    int clear_z0;       // Adam epilogue: z[0] (= G, the batch gradient: zero except <= 3B rows) is zeroed where it was non-zero — this
+                        // launch is its last reader in the step, so no separate clear_rows kernel is needed
     // column-slab blocking: items carry flags (bit0 = not the row's first segment: start from acc[row]; bit1 = not its last:
     // store the running sum to acc[row] instead of running the epilogue); acc == NULL -> every item is a whole row
     float4* acc;
@@ -203,6 +205,10 @@ __device__ __forceinline__ void epilogue(const SpmmArgs& a, int row, int lane, c
         float4 g = make_float4(a.alpha * acc[p].x, a.alpha * acc[p].y, a.alpha * acc[p].z, a.alpha * acc[p].w);
         if (a.nz > 0) {
             float4 zs = ld_once_f4(a.z[0] + off);
+            if constexpr (ADAM) {
+                if (a.clear_z0 && (zs.x != 0.f || zs.y != 0.f || zs.z != 0.f || zs.w != 0.f))
+                    const_cast<float4*>(a.z[0])[off] = f4_zero();
+            }
 #pragma unroll 1
             for (int t = 1; t < a.nz; ++t) f4_add(zs, ld_once_f4(a.z[t] + off));
             f4_fma(g, a.beta, zs);
@@ -623,7 +629,7 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
         LGCN_CHECK_ARG(indptr || n_rows == 0, "spmm: indptr is null and no plan was given");
         a.items = nullptr; a.n_items = n_rows; a.seginfo = nullptr; a.counters = nullptr; a.partials = nullptr; a.acc = nullptr;
     }
-    a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr;
+    a.P = nullptr; a.M = nullptr; a.V = nullptr; a.sc = nullptr; a.clear_z0 = 0;
     a.row_mask = row_mask; a.col_mask = col_mask;
     a.n_peers = 0; a.multicast = 0;
     for (int q = 0; q < LGCN_MAX_PEERS; ++q) { a.peerY[q] = nullptr; a.peerP[q] = nullptr; }
@@ -787,10 +793,12 @@ extern "C" int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices,
                                   float alpha, float beta, const float* const* z_host, int32_t nz,
                                   float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
                                   const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
-                                  const lgcn_spmm_peers_t* peers_host, lgcn_stream_t stream) {
+                                  const lgcn_spmm_peers_t* peers_host, int32_t clear_first_addend, lgcn_stream_t stream) {
     SpmmArgs a;
     if (int rc = fill_args(a, indptr, indices, vals, n_rows, d, X, Y, alpha, beta, z_host, nz, plan_host, row_mask, col_mask, peers_host)) return rc;
     LGCN_CHECK_ARG(P && M && V && scalars_dev, "spmm_adam: null P/M/V/scalars");
+    LGCN_CHECK_ARG(!clear_first_addend || (nz >= 1 && row_mask == nullptr && X != z_host[0]), "spmm_adam: clear_first_addend needs an addend that is not the gathered table, and no row mask");
+    a.clear_z0 = clear_first_addend ? 1 : 0;
     LGCN_CHECK_ARG(((uintptr_t)P % 16) == 0 && ((uintptr_t)M % 16) == 0 && ((uintptr_t)V % 16) == 0, "spmm_adam: P/M/V must be 16-byte aligned");
     a.P = reinterpret_cast<float4*>(P); a.M = reinterpret_cast<float4*>(M); a.V = reinterpret_cast<float4*>(V);
     a.sc = scalars_dev;

@@ -163,6 +163,7 @@ class Engine:
         self.decay, self.lr = float(decay), float(lr)
         self.deterministic = bool(deterministic)
         self.zero_copy = torch.device(device).type == 'cuda'
+        self.fuse_small = True              # fold the step's small kernels (see _enqueue_step)
         self.B_cap = int(B_cap)
         self.dist_mode = dist_mode
         self.group = group
@@ -503,14 +504,29 @@ class Engine:
         self._host_step = int(step)
         ops.adam_reinit(self.scalars, self.lr, step=self._host_step)
 
-    def _enqueue_step(self, users, pos, neg, ctl, only_spmm=False):
-        """Everything between 'batch is on the device' and 'loss_out is written'.
-        only_spmm (measurement): just the step's 2L K1 launches (with their exchanges), on whatever the buffers hold."""
+    def _enqueue_step(self, users, pos, neg, ctl, only_spmm=False, advance=False):
+        """Everything between 'batch is in the staging block' and 'loss_out is written'.
+        advance: first move the resident epoch's batch window (ctl) by one batch.
+        only_spmm (measurement): just the step's 2L K1 launches (with their exchanges), on whatever the buffers hold.
+        Small kernels are folded (fuse_small): ONE head kernel (Adam tick + window advance | pull of the pinned host batch);
+        K2 clears the bits of the batch-row bitmap it is the last reader of (no memset next step) and writes the loss into
+        pinned host memory; the Adam-epilogue K1 zeroes the rows of G as it reads them (no clear_rows kernel)."""
         if only_spmm:
             return self._enqueue_spmm_only()
-        if self._zc_slot is not None:               # host batch: pull the pinned staging block in (kernel, part of the graph)
-            ops.copy_words(self._blk, self._stage[self._zc_slot][0])
-        ops.adam_tick(self.scalars)
+        zc, fuse = self._zc_slot, self.fuse_small
+        local_g = self.dist_mode in (None, 'dp_idx')                       # G, m0 are whole-graph and every row is visited by this rank
+        if fuse:
+            ops.step_begin(self.scalars, self.B_cap, advance_ctl=ctl if advance else None,
+                           stage_dst=self._blk if zc is not None else None, stage_src=self._stage[zc][0] if zc is not None else None)
+        else:
+            if zc is not None:                      # host batch: pull the pinned staging block in (kernel, part of the graph)
+                ops.copy_words(self._blk, self._stage[zc][0])
+            if advance:
+                ops.batch_advance(ctl, self.B_cap)
+            ops.adam_tick(self.scalars)
+        k2_clears_mask = fuse and self.prune and local_g and self.pg is None
+        k2_writes_host = fuse and zc is not None and self.pg is None and self.dist_mode != 'dp'
+        k1_clears_g = fuse and local_g and self.i2i is None and self.L > 0
         masks = None
         if self.prune:
             # Dead-row pruning: the loss reads `out` only on the <= 3B batch rows (bitmap m0), so the last forward
@@ -522,7 +538,8 @@ class Engine:
             if self.dist_mode == 'rowpart':      # each rank prunes to the batch rows it owns (local bitmap)
                 ops.batch_masks_rows(users, pos, neg, self.B_cap, ctl, self.nu, self.r0, self.r1, self.m0)
             else:
-                ops.batch_masks(users, pos, neg, self.B_cap, ctl, self.nu, self.csr, self.m0, None)
+                # (the bitmap starts all-zero and, when K2 clears the bits it set, is all-zero again after every step)
+                ops.batch_masks(users, pos, neg, self.B_cap, ctl, self.nu, self.csr, self.m0, None, clear_first=not k2_clears_mask)
             masks = (self.m0, None)
         self.forward(masks)
         out, G_chain = self.out, self.G
@@ -543,7 +560,8 @@ class Engine:
                                     pg['temp'], pg['coeff'], self.decay, self.loss_out, self.G, pg['grad'], pg['ws'])
         else:
             ops.bpr_fwd_bwd(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
-                            self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic)
+                            self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic,
+                            clear_mask=self.m0 if k2_clears_mask else None, loss_host=self._loss_host if k2_writes_host else None)
         if self.i2i is not None:    # back through the smoothing: dL/d(items) = G' + alpha * I2I^T @ G'
             ii, nu = self.i2i, self.nu
             G_chain = ii['G2']
@@ -563,7 +581,7 @@ class Engine:
                 ops.spmm_adam(g, X, self.E0[r0:r1], Mo, Vo, self.scalars, alpha, beta,
                               [z[r0:r1] for z in zs], col_mask=col_mask,
                               peer_p=None if (peers_e0 is None or mc_e0) else [peers_e0[p][r0:r1] for p in range(self.world) if p != self.rank],
-                              mc_p=(mc_e0 + r0 * self.d * 4) if mc_e0 else 0)
+                              mc_p=(mc_e0 + r0 * self.d * 4) if mc_e0 else 0, clear_z0=k1_clears_g)
                 if peers_e0 is not None or mc_e0:        # the updated parameter rows are already in every replica
                     self._rank_barrier()
             self._backward_chain(G_chain, last)
@@ -572,9 +590,9 @@ class Engine:
             self.pg['grad'].zero_()
         if self.dist_mode == 'dp':
             self.G.zero_()          # the all-reduced G is dense in the rows any rank touched
-        else:
+        elif not k1_clears_g:
             ops.bpr_clear_rows(self.G, users, pos, neg, self.B_cap, ctl, self.nu)
-        if self._zc_slot is not None:               # ... and push the loss into pinned memory: loss_to_host() only has to wait
+        if zc is not None and not k2_writes_host:   # ... and push the loss into pinned memory: loss_to_host() only has to wait
             ops.copy_words(self._loss_host, self.loss_out, 16, dst_is_host=True)
 
     def _enqueue_spmm_only(self):
@@ -599,6 +617,14 @@ class Engine:
         step) — bench.py times its replays to get K1's launch duration under the conditions of the captured step.
         Replays run the Adam epilogue on whatever G holds: callers save and restore E0/M/V/scalars around them."""
         self._sync_params_across_ranks()
+        if self.prune and self.dist_mode in (None, 'dp_idx'):
+            # K2 leaves the batch-row bitmap all-zero after every step: set the bits of the current batch window again
+            # (they stay set: these replays have no K2), so that the masked layer does the work it does in a real step
+            if self._epoch is not None:
+                S, ctl = self._epoch
+                ops.batch_masks(S[0], S[1], S[2], self.B_cap, ctl, self.nu, self.csr, self.m0, None, clear_first=True)
+            else:
+                ops.batch_masks(self.bu, self.bp, self.bn, self.B_cap, self.ctl, self.nu, self.csr, self.m0, None, clear_first=True)
         self._enqueue_spmm_only()
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
@@ -606,29 +632,33 @@ class Engine:
             self._enqueue_spmm_only()
         return g
 
-    def _warm_kernels(self, users, pos, neg, ctl):
+    def clear_batch_mask(self):
+        """Back to the all-zero bitmap the captured steps expect (after spmm_only_graph measurements)."""
+        self.m0.zero_()
+
+    def _warm_kernels(self, users, pos, neg, ctl, advance=False):
         """Run the step once on throw-away state so every kernel is loaded before graph capture."""
         state = (self.E0, self.M, self.V, self.scalars, self.loss_out, ctl)
         if self.pg is not None:
             state = state + (self.pg['params'], self.pg['M'], self.pg['V'])
         saved = [t.clone() for t in state]
         ctl.zero_()                                   # B = 0: the batch kernels touch nothing
-        self._enqueue_step(users, pos, neg, ctl)
+        self._enqueue_step(users, pos, neg, ctl, advance=advance)
         for dst, src in zip(state, saved):
             dst.copy_(src)
         self.G.zero_()
         torch.cuda.current_stream().synchronize()
 
-    def _run(self, key, users, pos, neg, ctl):
+    def _run(self, key, users, pos, neg, ctl, advance=False):
         if not self.use_graph:
-            self._enqueue_step(users, pos, neg, ctl)
+            self._enqueue_step(users, pos, neg, ctl, advance=advance)
             return
         g = self._graphs.get(key)
         if g is None:
-            self._warm_kernels(users, pos, neg, ctl)
+            self._warm_kernels(users, pos, neg, ctl, advance=advance)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._enqueue_step(users, pos, neg, ctl)
+                self._enqueue_step(users, pos, neg, ctl, advance=advance)
             self._graphs[key] = g
         g.replay()
 
@@ -716,9 +746,8 @@ class Engine:
     def epoch_step(self):
         S, ctl = self._epoch
         self._sync_params_across_ranks()
-        ops.batch_advance(ctl, self.B_cap)
         self._zc_slot = None
         self._loss_host_valid = False
-        self._run('epoch', S[0], S[1], S[2], ctl)
+        self._run('epoch', S[0], S[1], S[2], ctl, advance=True)
         self._host_step += 1
         self.param_epoch += 1

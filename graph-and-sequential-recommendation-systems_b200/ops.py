@@ -353,8 +353,9 @@ def spmm(g, X, Y, alpha=1.0, beta=0.0, zs=None, row_mask=None, col_mask=None, pe
     return Y
 
 
-def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None, peer_p=None, mc_p=0):
-    """K1 with the Adam epilogue: grad = alpha*(A@X) + beta*sum(zs); P,M,V updated in place."""
+def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_mask=None, col_mask=None, peer_p=None, mc_p=0, clear_z0=False):
+    """K1 with the Adam epilogue: grad = alpha*(A@X) + beta*sum(zs); P,M,V updated in place.
+    clear_z0: the non-zero rows of zs[0] (= G) are zeroed as they are read (its last reader in the step)."""
     lib = _lib.load()
     d = X.shape[1]
     for t, n in ((X, "X"), (P, "P"), (M, "M"), (V, "V")):
@@ -366,11 +367,11 @@ def spmm_adam(g, X, P, M, V, scalars, alpha=1.0, beta=0.0, zs=None, Y=None, row_
         for pl in blocks:
             _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                               float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
-                                              byref(pl), _p(row_mask), None, peers, _stream()), "spmm_adam")
+                                              byref(pl), _p(row_mask), None, peers, int(bool(clear_z0)), _stream()), "spmm_adam")
         return
     _lib.check(lib.lgcn_spmm_adam_f32(_p(g.indptr), _p(g.indices), _p(g.vals), g.n_rows, d, _p(X), _p(Y),
                                       float(alpha), float(beta), arr, nz, _p(P), _p(M), _p(V), _p(scalars),
-                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p, 0, mc_p), _stream()), "spmm_adam")
+                                      g._plan_ref(d), _p(row_mask), _p(col_mask), _peers_struct(None, peer_p, 0, mc_p), int(bool(clear_z0)), _stream()), "spmm_adam")
 
 
 def gather_probe(X, idx, run=32, variant=0, out=None):
@@ -400,6 +401,12 @@ def adam_reinit(scalars, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0):
     _lib.check(_lib.load().lgcn_adam_init(_p(scalars), lr, beta1, beta2, eps, int(step), _stream()), "adam_init")
 
 
+def step_begin(scalars, B_cap, advance_ctl=None, stage_dst=None, stage_src=None):
+    """Head of a captured step: Adam tick + (advance of the resident batch window | pull of a pinned host batch)."""
+    n = 0 if stage_src is None else stage_src.numel() * stage_src.element_size()
+    _lib.check(_lib.load().lgcn_step_begin(_p(scalars), _p(advance_ctl), int(B_cap), _p(stage_dst), _p(stage_src), n, _stream()), "step_begin")
+
+
 def adam_tick(scalars):
     _lib.check(_lib.load().lgcn_adam_tick(_p(scalars), _stream()), "adam_tick")
 
@@ -418,7 +425,7 @@ def bpr_workspace(B_cap, d, device):
 
 
 def bpr_fwd_bwd(out, users, pos, neg, B_cap, ctl, n_users, m_items, inv_norm, decay, c_bpr, c_reg,
-                loss_out, G, workspace, own=(0, None), deterministic=False):
+                loss_out, G, workspace, own=(0, None), deterministic=False, clear_mask=None, loss_host=None):
     """K2: loss_out[0..2] = (bpr, reg, bpr+decay*reg); G += closed-form gradient (if G is not None)."""
     lib = _lib.load()
     d = out.shape[1]
@@ -430,7 +437,7 @@ def bpr_fwd_bwd(out, users, pos, neg, B_cap, ctl, n_users, m_items, inv_norm, de
     _lib.check(lib.lgcn_bpr_fwd_bwd(_p(out), _p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users, m_items, d,
                                     float(inv_norm), float(decay), float(c_bpr), float(c_reg), _p(loss_out), _p(G),
                                     int(own[0]), int(own_end), int(bool(deterministic)), _p(workspace),
-                                    workspace.numel() * 4, _stream()), "bpr_fwd_bwd")
+                                    workspace.numel() * 4, _p(clear_mask), _p(loss_host), _stream()), "bpr_fwd_bwd")
 
 
 def popgate_param_count(d, pop_hidden, gate_hidden):
@@ -468,10 +475,11 @@ def bpr_clear_rows(G, users, pos, neg, B_cap, ctl, n_users):
                                                G.shape[1], _stream()), "bpr_clear_rows")
 
 
-def batch_masks(users, pos, neg, B_cap, ctl, n_users, g, m0, m1):
-    """Bitmaps of the rows a step needs: m0 = batch rows, m1 (optional) = m0 + their neighbours."""
+def batch_masks(users, pos, neg, B_cap, ctl, n_users, g, m0, m1, clear_first=True):
+    """Bitmaps of the rows a step needs: m0 = batch rows, m1 (optional) = m0 + their neighbours.
+    clear_first=False: m0 is known to be all-zero (the previous step's K2 cleared its bits)."""
     _lib.check(_lib.load().lgcn_batch_masks(_p(users), _p(pos), _p(neg), B_cap, _p(ctl), n_users, g.n_rows, _p(g.indptr),
-                                            _p(g.indices), _p(m0), _p(m1), _stream()), "batch_masks")
+                                            _p(g.indices), _p(m0), _p(m1), int(bool(clear_first)), _stream()), "batch_masks")
 
 
 def batch_masks_rows(users, pos, neg, B_cap, ctl, n_users, row_begin, row_end, m0_local):

@@ -213,7 +213,10 @@ int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const floa
                        float alpha, float beta, const float* const* z_host, int32_t nz,
                        float* P, float* M, float* V, const lgcn_adam_scalars_t* scalars_dev,
                        const lgcn_spmm_plan_t* plan_host, const uint32_t* row_mask, const uint32_t* col_mask,
-                       const lgcn_spmm_peers_t* peers_host, lgcn_stream_t stream);
+                       const lgcn_spmm_peers_t* peers_host,
+                       int32_t clear_first_addend /* != 0: rows of Z_0 that are non-zero are zeroed after they are read — Z_0 = G and
+                                                     this launch is its last reader in the step (replaces lgcn_bpr_clear_rows) */,
+                       lgcn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Adam (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight decay, no amsgrad)
@@ -224,6 +227,11 @@ int lgcn_spmm_adam_f32(const int32_t* indptr, const int32_t* indices, const floa
 int lgcn_adam_init(lgcn_adam_scalars_t* scalars_dev, double lr, double beta1, double beta2, double eps,
                    int32_t step, lgcn_stream_t stream);
 int lgcn_adam_tick(lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream);
+/* The head of a captured training step in one launch: lgcn_adam_tick, plus EITHER lgcn_batch_advance on advance_ctl_dev
+ * (resident epoch; NULL otherwise) OR the pull of a host batch: stage_bytes (multiple of 16) from stage_src (mapped pinned
+ * host memory) to stage_dst (device), as lgcn_copy_words does. */
+int lgcn_step_begin(lgcn_adam_scalars_t* scalars_dev, int32_t* advance_ctl_dev, int32_t B_cap,
+                    void* stage_dst, const void* stage_src, int64_t stage_bytes, lgcn_stream_t stream);
 int lgcn_adam_f32(float* P, float* M, float* V, const float* G, int64_t n,
                   const lgcn_adam_scalars_t* scalars_dev, lgcn_stream_t stream);
 
@@ -253,6 +261,10 @@ int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const int64_t* pos,
                      int32_t d, float inv_norm, float decay, float c_bpr, float c_reg,
                      float* loss_out, float* G, int32_t own_begin, int32_t own_end,
                      int32_t deterministic, void* workspace, size_t workspace_bytes,
+                     uint32_t* clear_mask /* optional: the m0 bitmap of lgcn_batch_masks; the bits of this batch's rows are cleared
+                                             (its last reader, the masked forward layer, ran before), so the next lgcn_batch_masks
+                                             can skip its memset */,
+                     float* loss_host_mapped /* optional: mapped pinned host float[4], receives a copy of loss_out (no D2H memcpy) */,
                      lgcn_stream_t stream);
 /* zero the rows of G a batch touched (cheaper than a full memset when B << N) */
 int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t* pos, const int64_t* neg,
@@ -260,11 +272,11 @@ int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t* pos, cons
                         lgcn_stream_t stream);
 int lgcn_batch_advance(int32_t* batch_ctl_dev, int32_t B_cap, lgcn_stream_t stream);
 /* bitmaps over the N nodes for the current batch window: m0 = the 3B rows the loss reads, m1 = m0 plus their
- * neighbours in the CSR (both cleared first; m1 may be NULL).  uint32[(n_nodes+31)/32] each. */
+ * neighbours in the CSR (m1 is cleared first, m0 if clear_first; m1 may be NULL).  uint32[(n_nodes+31)/32] each. */
 int lgcn_batch_masks(const int64_t* users, const int64_t* pos, const int64_t* neg, int32_t B_cap,
                      const int32_t* batch_ctl_dev, int32_t n_users, int32_t n_nodes,
                      const int32_t* indptr, const int32_t* indices, uint32_t* m0, uint32_t* m1,
-                     lgcn_stream_t stream);
+                     int32_t clear_first /* 0: m0 is known to be all-zero (lgcn_bpr_fwd_bwd cleared it) */, lgcn_stream_t stream);
 
 /* the same m0 restricted to the row block [row_begin,row_end) and indexed by LOCAL row: uint32[(row_end-row_begin+31)/32]
  * (row partition: every rank prunes the last forward layer to the batch rows it owns) */
