@@ -90,13 +90,18 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
         timer.zero()
         return f"loss{aver_loss:.3f}-{time_info}"
     with timer(name="Sample"):
-        S = utils.UniformSample_original(dataset)
+        # the following epoch's sample is drawn in the background while the GPU runs this one (rewound if the next sampler
+        # call turns out to be something else: utils._EpochPrefetch)
+        S = utils.UniformSample_original(dataset, prefetch_next=bool(world.config.get('sampler_prefetch', True)))
     # int64 on the device directly (the reference's torch.Tensor(...).long() float32 round trip,
     # code/Procedure.py:52-54, is exact only below 2^24 — SURVEY.md A16)
-    S_t = torch.from_numpy(np.ascontiguousarray(S[:, :3].T)).to(torch.int64)
-    perm = np.arange(S_t.shape[1])
-    np.random.shuffle(perm)                       # same RNG call as utils.shuffle (code/utils.py:148)
-    S_t = S_t[:, torch.from_numpy(perm)]
+    # Like the reference (code/Procedure.py:52-55) the triples go to the device first and are permuted there; only the
+    # permutation itself is drawn on the host, with the same numpy call as utils.shuffle (code/utils.py:148).
+    dev = world.device if world.device.type == 'cuda' else torch.device('cpu')
+    S_raw = torch.from_numpy(np.ascontiguousarray(S[:, :3])).to(dev, non_blocking=True)      # int32 [n, 3]
+    perm = np.arange(S.shape[0])
+    np.random.shuffle(perm)
+    S_t = S_raw[torch.from_numpy(perm).to(dev)].t().to(torch.int64).contiguous()              # int64 [3, n], shuffled
     n = S_t.shape[1]
     total_batch = n // bs + 1
     if getattr(bpr, 'fused', False):
@@ -105,7 +110,7 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
             eng._alloc_batch(bs)
         eng.set_lr(bpr.opt.param_groups[0]['lr'])
         eng.decay = float(bpr.weight_decay)
-        S_dev = S_t.to(world.device)
+        S_dev = S_t
         if mode == 'rowpart' and nranks > 1:
             # every rank replays the SAME epoch (the batch is replicated, the rows of A are what is split); the loss and
             # the returned string are identical on every rank

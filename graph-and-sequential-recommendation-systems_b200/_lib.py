@@ -99,6 +99,8 @@ _SIGNATURES = {
     "lgcn_rank_metrics": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     "lgcn_sample_bpr": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int64, ctypes.c_uint64, ctypes.c_uint64, _P, _P, _P, _P, _P]),
     "lgcn_sampler_seed": (None, [c_uint32]),
+    "lgcn_sampler_get_state": (None, [_P]),
+    "lgcn_sampler_set_state": (ctypes.c_int, [_P]),
     "lgcn_sample_negative": (c_int64, [c_int32, c_int32, c_int64, _P, _P, c_int32, _P]),
     "lgcn_sample_negative_by_user": (c_int64, [_P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P]),
     "lgcn_randint": (c_int32, [c_int32]),

@@ -84,7 +84,45 @@ extern "C" int lgcn_debug_poke(float* ptr, float value, int32_t n, int32_t* out_
 }
 
 // ---- host sampler: glibc rand() stream, same draw order as sampling.cpp ---------------------
-extern "C" void lgcn_sampler_seed(uint32_t seed) { srand(seed); }
+// The reference's sampler draws from glibc's rand() (srand(seed), code/sources/sampling.cpp:88-91).  The generator is restated
+// here — glibc's TYPE_3 additive feedback generator: degree 31, separation 3, seeded by the Lehmer LCG 16807 mod 2^31-1, first
+// 310 outputs discarded, output = state word >> 1 — so that the stream (i) is the same on any C library, (ii) costs no lock per
+// draw, and (iii) can be snapshotted and rewound (lgcn_sampler_get/set_state: the epoch prefetch in utils.py rewinds when the
+// next call turns out not to be the epoch sample it ran ahead for).  tests/test_host.py checks it against this machine's libc
+// rand() and against a recording of the reference's compiled module.
+namespace lgcn {
+struct GlibcRand {
+    int32_t r[31]; int f, b;            // f = "front" index (starts at 3), b = "rear" index (starts at 0)
+    void seed(uint32_t s) {
+        if (s == 0) s = 1;
+        r[0] = (int32_t)s;
+        for (int i = 1; i < 31; ++i) {
+            const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+            long word = 16807 * lo - 2836 * hi;
+            if (word < 0) word += 2147483647;
+            r[i] = (int32_t)word;
+        }
+        f = 3; b = 0;
+        for (int i = 0; i < 310; ++i) next();
+    }
+    inline int next() {
+        const uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
+        r[f] = (int32_t)v;
+        if (++f >= 31) { f = 0; ++b; } else if (++b >= 31) b = 0;
+        return (int)(v >> 1);
+    }
+};
+static GlibcRand g_rand = [] { GlibcRand g; g.seed(1); return g; }();     // an unseeded program behaves like srand(1)
+}  // namespace lgcn
+
+extern "C" void lgcn_sampler_seed(uint32_t seed) { g_rand.seed(seed); }
+// state = 33 int32 words (31 ring words, front index, rear index)
+extern "C" void lgcn_sampler_get_state(int32_t* state33_host) { if (state33_host) { memcpy(state33_host, g_rand.r, 31 * 4); state33_host[31] = g_rand.f; state33_host[32] = g_rand.b; } }
+extern "C" int lgcn_sampler_set_state(const int32_t* state33_host) {
+    if (!state33_host || state33_host[31] < 0 || state33_host[31] >= 31 || state33_host[32] < 0 || state33_host[32] >= 31) { set_error("sampler_set_state: bad state"); return 1; }
+    memcpy(g_rand.r, state33_host, 31 * 4); g_rand.f = state33_host[31]; g_rand.b = state33_host[32];
+    return 0;
+}
 
 extern "C" int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_num,
                                         const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
@@ -102,10 +140,10 @@ extern "C" int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int6
         for (int64_t pair = 0; pair < per_user; ++pair) {
             int32_t* o = out_host + ((int64_t)user * per_user + pair) * row;
             o[0] = user;
-            o[1] = pos[rand() % npos];
+            o[1] = pos[g_rand.next() % npos];
             for (int idx = 2; idx < row; ++idx) {
                 int neg;
-                do { neg = rand() % item_num; } while (std::find(pos, pos + npos, neg) != pos + npos);
+                do { neg = g_rand.next() % item_num; } while (std::find(pos, pos + npos, neg) != pos + npos);
                 o[idx] = neg;
             }
         }
@@ -130,10 +168,10 @@ extern "C" int64_t lgcn_sample_negative_by_user(const int32_t* users_host, int64
         if (npos >= item_num) { set_error("sample_negative_by_user: user %d interacted with every item", user); return -3; }
         int32_t* o = out_host + k * row;
         o[0] = user;
-        o[1] = pos[rand() % npos];
+        o[1] = pos[g_rand.next() % npos];
         for (int idx = 2; idx < row; ++idx) {
             int neg;
-            do { neg = rand() % item_num; } while (std::find(pos, pos + npos, neg) != pos + npos);
+            do { neg = g_rand.next() % item_num; } while (std::find(pos, pos + npos, neg) != pos + npos);
             o[idx] = neg;
         }
     }
@@ -143,7 +181,7 @@ extern "C" int64_t lgcn_sample_negative_by_user(const int32_t* users_host, int64
 // randint (code/sources/sampling.cpp:22-25, exported to Python at :100): next value of the same rand() stream
 extern "C" int32_t lgcn_randint(int32_t end) {
     if (end <= 0) { set_error("randint: end must be positive"); return -1; }
-    return rand() % end;
+    return g_rand.next() % end;
 }
 
 // ---- ingest: the reference's interaction files --------------------------------------------------

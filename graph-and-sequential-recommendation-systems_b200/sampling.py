@@ -29,11 +29,18 @@ def _vp(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _cancel_prefetch():
+    from . import utils
+    utils._prefetch.cancel()            # an epoch sample drawn ahead of time is rewound: this call sees the stream position it expects
+
+
 def seed(s):
+    _cancel_prefetch()
     _lib.load().lgcn_sampler_seed(ctypes.c_uint32(int(s) & 0xffffffff))
 
 
 def randint(end):
+    _cancel_prefetch()
     r = _lib.load().lgcn_randint(int(end))
     if r < 0:
         raise RuntimeError(_lib.load().lgcn_last_error().decode())
@@ -41,6 +48,7 @@ def randint(end):
 
 
 def sample_negative(user_num, item_num, train_num, allPos, neg_num):
+    _cancel_prefetch()
     indptr, items = _csr(allPos)
     out = np.empty((int(user_num) * (int(train_num) // int(user_num)), 2 + int(neg_num)), dtype=np.int32)
     rows = _lib.load().lgcn_sample_negative(int(user_num), int(item_num), int(train_num), _vp(indptr), _vp(items), int(neg_num), _vp(out))
@@ -50,6 +58,7 @@ def sample_negative(user_num, item_num, train_num, allPos, neg_num):
 
 
 def sample_negative_ByUser(users, item_num, allPos, neg_num):
+    _cancel_prefetch()
     indptr, items = _csr(allPos)
     users = np.ascontiguousarray(users, dtype=np.int32)
     out = np.empty((users.size, 2 + int(neg_num)), dtype=np.int32)

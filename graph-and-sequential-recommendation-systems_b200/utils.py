@@ -120,13 +120,74 @@ class BPRLoss:
 sample_ext = True     # the C sampler ships inside liblgcn_b200.so
 
 
+class _EpochPrefetch:
+    """The NEXT epoch's sample, drawn by a background thread while the GPU runs the current epoch (the ctypes call releases
+    the GIL; the C sampler is ~30 ms per gowalla epoch, a quarter of a BPR_train_original call).  Exactness: the sampler's
+    generator state is snapshotted before the prefetch; if the next sampler call is not the epoch sample it ran ahead for
+    (another dataset, sample_negative_ByUser, randint, a reseed ...), the state is rewound and the prefetch dropped — every
+    interleaving of calls sees the stream the reference's module would have produced."""
+
+    def __init__(self):
+        self.thread, self.key, self.result, self.snapshot, self.error = None, None, None, None, None
+
+    def cancel(self):
+        if self.thread is None:
+            return
+        self.thread.join()
+        _lib.load().lgcn_sampler_set_state(self.snapshot.ctypes.data_as(ctypes.c_void_p))       # rewind: as if it never ran
+        self.thread, self.key, self.result, self.snapshot, self.error = None, None, None, None, None
+
+    def take(self, key):
+        if self.thread is None:
+            return None
+        if key != self.key:
+            self.cancel()
+            return None
+        self.thread.join()
+        res, err = self.result, self.error
+        self.thread, self.key, self.result, self.snapshot, self.error = None, None, None, None, None
+        if err is not None:
+            raise err
+        return res
+
+    def start(self, key, fn):
+        import threading
+        self.snapshot = np.empty(33, dtype=np.int32)
+        _lib.load().lgcn_sampler_get_state(self.snapshot.ctypes.data_as(ctypes.c_void_p))
+        self.key, self.result, self.error = key, None, None
+
+        def run():
+            try:
+                self.result = fn()
+            except Exception as e:                  # noqa: BLE001 — re-raised by take()
+                self.error = e
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+
+
+_prefetch = _EpochPrefetch()
+
+
 def sampler_seed(seed):
+    _prefetch.cancel()
     _lib.load().lgcn_sampler_seed(ctypes.c_uint32(int(seed) & 0xffffffff))
 
 
-def UniformSample_original(dataset, neg_ratio=1):
+def _epoch_sample(indptr, items, n_users, m_items, train_size, neg_ratio):
+    per_user = train_size // n_users
+    out = np.empty((n_users * per_user, 2 + neg_ratio), dtype=np.int32)
+    rows = _lib.load().lgcn_sample_negative(n_users, m_items, train_size,
+                                           indptr.ctypes.data_as(ctypes.c_void_p), items.ctypes.data_as(ctypes.c_void_p),
+                                           neg_ratio, out.ctypes.data_as(ctypes.c_void_p))
+    if rows < 0:
+        raise RuntimeError(_lib.load().lgcn_last_error().decode())
+    return out
+
+
+def UniformSample_original(dataset, neg_ratio=1, prefetch_next=False):
     """One epoch of (user, pos, neg) triples, int32 [n_users * (trainDataSize // n_users), 2+neg_ratio],
-    with the draw order of the reference's C++ sampler (code/sources/sampling.cpp:27-56)."""
+    with the draw order of the reference's C++ sampler (code/sources/sampling.cpp:27-56).
+    prefetch_next (used by Procedure.BPR_train_original): start drawing the following epoch's sample in the background."""
     if hasattr(dataset, 'allPos_csr'):
         indptr, items = dataset.allPos_csr()
     else:
@@ -136,13 +197,13 @@ def UniformSample_original(dataset, neg_ratio=1):
         items = np.concatenate([np.asarray(a, dtype=np.int32) for a in ap]) if len(ap) else np.zeros(0, np.int32)
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
     items = np.ascontiguousarray(items, dtype=np.int32)
-    per_user = dataset.trainDataSize // dataset.n_users
-    out = np.empty((dataset.n_users * per_user, 2 + neg_ratio), dtype=np.int32)
-    rows = _lib.load().lgcn_sample_negative(dataset.n_users, dataset.m_items, dataset.trainDataSize,
-                                           indptr.ctypes.data_as(ctypes.c_void_p), items.ctypes.data_as(ctypes.c_void_p),
-                                           neg_ratio, out.ctypes.data_as(ctypes.c_void_p))
-    if rows < 0:
-        raise RuntimeError(_lib.load().lgcn_last_error().decode())
+    args = (indptr, items, int(dataset.n_users), int(dataset.m_items), int(dataset.trainDataSize), int(neg_ratio))
+    key = (id(dataset), args[2], args[3], args[4], args[5], int(items.size))
+    out = _prefetch.take(key)
+    if out is None:
+        out = _epoch_sample(*args)
+    if prefetch_next:
+        _prefetch.start(key, lambda: _epoch_sample(*args))
     return out
 
 

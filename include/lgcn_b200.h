@@ -386,6 +386,11 @@ int lgcn_rank_metrics(const int64_t* topk_idx, int32_t Bt, int32_t k_max,
  * out int32[user_num*(train_num/user_num)*(2+neg_num)].  Returns rows written or <0.
  * -------------------------------------------------------------------------------------------*/
 void lgcn_sampler_seed(uint32_t seed);
+/* The generator behind the sampler is glibc's rand() restated inside the library (same stream as srand/rand on glibc, on any
+ * platform); its state (int32[33]) can be saved and restored, which is what lets an epoch's sample be drawn ahead of time and
+ * rewound if the next call turns out to be something else. */
+void lgcn_sampler_get_state(int32_t* state33_host);
+int lgcn_sampler_set_state(const int32_t* state33_host);
 int64_t lgcn_sample_negative(int32_t user_num, int32_t item_num, int64_t train_num,
                              const int64_t* allpos_indptr_host, const int32_t* allpos_items_host,
                              int32_t neg_num, int32_t* out_host);

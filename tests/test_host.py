@@ -102,6 +102,41 @@ def test_sampling_module_abi_matches_reference_cpp():
         lg.sampling.sample_negative_ByUser([nu + 3], ni, all_pos, 1)
 
 
+def test_sampler_generator_is_glibc_rand():
+    """The library carries its own copy of glibc's rand() (TYPE_3 additive feedback generator): same stream as this machine's
+    libc for several seeds, so the reference's sampler stream no longer depends on the platform's C library."""
+    import ctypes
+    import lgcn_b200 as lg
+    lib = lg._lib.load()
+    libc = ctypes.CDLL(None)
+    libc.rand.restype = ctypes.c_int
+    for seed in (0, 1, 2020, 123456789, 0xffffffff):
+        libc.srand(ctypes.c_uint(seed)); lg.sampling.seed(seed)
+        assert [libc.rand() % 1000003 for _ in range(3000)] == [lg.sampling.randint(1000003) for _ in range(3000)]
+
+
+def test_epoch_prefetch_keeps_the_sampler_stream_exact():
+    """Procedure.BPR_train_original draws the NEXT epoch's sample in the background.  Whatever is called next, the stream is
+    the one the reference's module would have produced: the same dataset gets the prefetched sample (= what a direct call
+    would have drawn), anything else rewinds the generator first."""
+    import lgcn_b200 as lg
+    ds = lg.synth.make_dataset('tiny')
+    ds2 = lg.synth.make_dataset('tiny', seed=5)
+    lg.utils.sampler_seed(11)
+    ref = [lg.utils.UniformSample_original(ds) for _ in range(3)]                      # plain sequential draws
+    ref_ri = lg.sampling.randint(1000)
+    ref_other = lg.utils.UniformSample_original(ds2)
+    lg.utils.sampler_seed(11)
+    a = lg.utils.UniformSample_original(ds, prefetch_next=True)
+    b = lg.utils.UniformSample_original(ds, prefetch_next=True)                        # served by the prefetch
+    c = lg.utils.UniformSample_original(ds, prefetch_next=True)
+    assert all(np.array_equal(x, y) for x, y in zip(ref, (a, b, c)))
+    assert lg.sampling.randint(1000) == ref_ri                                         # pending prefetch rewound before the draw
+    assert np.array_equal(lg.utils.UniformSample_original(ds2, prefetch_next=True), ref_other)
+    lg.utils.sampler_seed(11)                                                          # reseeding drops a pending prefetch as well
+    assert np.array_equal(lg.utils.UniformSample_original(ds), ref[0])
+
+
 def test_oracle_c_sampler_matches_reference_cpp():
     """oracle/c/sampler_ref.c (what bench.py --impl reference draws its triples with) against the same recording."""
     from oracle import lightgcn_oracle as orc
