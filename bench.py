@@ -397,6 +397,20 @@ def resident_step_fn(eng, S_host):
     return step
 
 
+def rank_record(lg, tm, ds, model):
+    """The ranking alone (K3: score GEMM on tcgen05 + mask + top-k), CUDA events, warm tables: the tensor roofline of §8d."""
+    _, tc_peak, _ = peaks()
+    n_test = int(ds.test_csr()[0].numel())
+    lg.Procedure.rank_all(ds, model, 20, user_tile=65536)
+    rank_us = tm.median_us(lambda: lg.Procedure.rank_all(ds, model, 20, user_tile=65536), reps=7, flush=False)
+    score_flop = 2.0 * n_test * ds.m_items * D
+    return {"rank_all_ms": rank_us / 1e3, "users": n_test, "items": ds.m_items, "rank_useful_tflops": score_flop / (rank_us * 1e-6) / 1e12,
+            "rank_frac_of_bf16_dense_peak": score_flop / (rank_us * 1e-6) / 1e12 / tc_peak if tc_peak else None,
+            "rows_redone_by_exact_kernel": int(getattr(model, 'last_rank_redone', 0)),
+            "rank_note": "useful flops 2*U*M*d counted once; the kernel runs the TF32 GEMM 1.5x (sampled pass + full pass) and TF32 peaks at half the bf16 rate; "
+                         "ncu tensor-pipe activity of the two passes: profiles/r2_evaltc_launches_ncu.csv"}
+
+
 def shape_record(lg, tm, name, cfg, peak, K, R):
     """extra.<shape>: step, cold K1 layer + roofline fraction, eval — one GPU."""
     import torch
@@ -417,6 +431,7 @@ def shape_record(lg, tm, name, cfg, peak, K, R):
         torch.cuda.synchronize(); ev.append(1e3 * (time.perf_counter() - t0))
     n_test = int(ds.test_csr()[0].numel())
     rec = {"workload": bench_config(name, graph)["workload"], "step_ms": step_ms, "samples_per_s": B / (step_ms * 1e-3),
+           **{k: v for k, v in rank_record(lg, tm, ds, model).items() if k in ("rank_all_ms", "rank_useful_tflops", "rank_frac_of_bf16_dense_peak")},
            "spmm_launch_us": roof["launch_us"], "spmm_frac": roof["frac"], "spmm_cold_launch_us": roof["cold_launch_us"],
            "spmm_cold_frac": roof["cold_frac"], "spmm_alg_gbs": roof["achieved"], "spmm_l2_gather_gbs": roof["l2_gather_gbs"],
            "spmm_share_of_step": roof["spmm_share_of_step"], "propagation_L3_cold_us": prop_us,
@@ -711,12 +726,22 @@ def run_ours(args):
                     "wall_no_flush_note": "host clock over a back-to-back stageOne loop, no flush: what a training loop sees"},
             "gpu_launches": K * launches_per_step, "gpu_launches_per_step": launches_per_step,
             "clocks": clk, "loss": last_loss}
+    nnz_full = 2 * int(__import__('numpy').unique(graph['train_user'] * graph['m_items'] + graph['train_item']).size)
+    n_nodes = graph['n_users'] + graph['m_items']
+    step_bytes = 2 * L_LAYERS * (8 * nnz_full + 4 * (n_nodes + 1) + 8 * n_nodes * D) + 28 * n_nodes * D + 24 * B * D
+    hbm_ms = step_bytes / (peak * 1e9 * world) * 1e3
+    line["step_roofline"] = {"algorithmic_bytes_per_step": step_bytes, "formula": "2L*B_spmm + 28*N*d + 24*B*d (SURVEY.md §8d)",
+                             "hbm_ms_at_peak": hbm_ms, "frac": hbm_ms / (ms_dev / K), "peak_gbs": peak * world,
+                             "epoch_ms_at_peak": None, "note": "fraction of the memory roofline of the whole step on the %d GPU(s) used" % world}
     if replicated:
         line["setup"]["note"] = "replicated_throughput: N replicas each run the full-graph step on the all-gathered global batch — NOT a scaling measurement"
 
     # ---- procedures at any N: epoch and evaluation through the reference-facing API -----------------------
     if not replicated:
         guarded("procedures", lambda: procedures_record(lg, ds, model, bpr, dist), line)
+        if isinstance(line.get("procedures"), dict) and "epoch_steps" in line["procedures"]:
+            line["step_roofline"]["epoch_ms_at_peak"] = hbm_ms * line["procedures"]["epoch_steps"]
+            line["procedures"]["epoch_frac_of_hbm_roofline"] = line["step_roofline"]["epoch_ms_at_peak"] / line["procedures"]["epoch_ms"]
 
     if world == 1:
         csr = ds.getCSRGraph()
@@ -727,6 +752,7 @@ def run_ours(args):
             r.update(k1_gather_gbs=line["roofline"]["l2_gather_gbs"], k1_frac_of_gather_ceiling=line["roofline"]["l2_gather_gbs"] / r["gather_ceiling_gbs"])
             return r
         guarded("roofline_l2", _l2, line)
+        guarded("eval", lambda: rank_record(lg, tm, ds, model), line)
         # ---- the library bar: the reference's own calls with tensors on the GPU (cuSPARSE / ATen) -------------
         if not args.no_baselines:
             try:
