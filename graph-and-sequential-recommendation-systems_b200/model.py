@@ -169,7 +169,7 @@ class LightGCN(nn.Module):
                               use_graph=config.get('cuda_graph', True),
                               dist_mode=config.get('dist_mode', None), prune=config.get('prune_dead_rows', True),
                               p2p=config.get('rowpart_p2p', True), row_cost=config.get('rowpart_row_cost', None),
-                              multicast=config.get('rowpart_multicast', True), rebalance=config.get('rowpart_rebalance', 2))
+                              multicast=config.get('rowpart_multicast', True), rebalance=config.get('rowpart_rebalance', 3))
         self._cache_key = None
         self._pack_params()
         seg_len = int(config.get('spmm_seg_len', ops.DEFAULT_SEG_LEN))
