@@ -4,14 +4,16 @@ What the reference does with torch ops per step (code/utils.py:53-64 -> code/mod
 cat -> L x sparse.mm -> stack -> mean -> 3 gathers -> ~10 elementwise kernels -> autograd backward
 (L more sparse.mm on a transposed COO, index_put, stack/mean/cat backward) -> Adam.  Here a step is
 
+    head         Adam step scalars + (advance of the resident batch window | pull of a pinned HOST batch)   [1 kernel]
+    masks        bitmap of the <= 3B batch rows (dead-row pruning of the last forward layer)
     K1 x (L-1)   X_k = A X_{k-1}
-    K1           out = (A X_{L-1} + X_0 + ... + X_{L-1}) / (L+1)        (layer mean fused)
-    K2           loss, reg, G = d(loss + decay*reg)/d(out)              (closed form, scatter-add)
+    K1           out = (A X_{L-1} + X_0 + ... + X_{L-1}) / (L+1)        (layer mean fused; batch rows only)
+    K2           loss, reg, G = d(loss + decay*reg)/d(out)              (closed form, scatter-add; clears the bitmap,
+                                                                         writes the loss record to pinned host memory)
     K1 x (L-1)   g_{L-1} = s (G + A G);  g_k = s G + A g_{k+1}           (s = 1/(L+1); A symmetric)
-    K1 + Adam    g_0 = s G + A g_1  consumed by the Adam epilogue, never written
-    clear        the <= 3B rows of G the batch touched
+    K1 + Adam    g_0 = s G + A g_1  consumed by the Adam epilogue, never written; zeroes the rows of G as it reads them
 
-all on one stream, optionally captured in a CUDA graph.  Buffers: E0 (parameters, [users;items]),
+= 2L + 3 kernels on one stream, captured in a CUDA graph (under the row partition: + 2L rank barriers + clear_rows).  Buffers: E0 (parameters, [users;items]),
 L-1 layer buffers (re-used as backward ping-pong), out, G, Adam M/V — (L+4) * N * d * 4 bytes.
 
 Multi-GPU (one process per GPU, torch.distributed):
