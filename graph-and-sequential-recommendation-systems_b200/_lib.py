@@ -19,6 +19,7 @@ class SpmmPlan(Structure):
         ("seg_len", c_int32), ("n_long", c_int32), ("n_segs", c_int32), ("n_items", c_int32),
         ("d_max", c_int32), ("pad", c_int32),
         ("items", c_void_p), ("seginfo", c_void_p), ("counters", c_void_p), ("partials", c_void_p), ("acc", c_void_p),
+        ("hinted_indices", c_void_p),
     ]
 
 
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "lgcn_copy_words": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P]),
     "lgcn_coo_to_csr": (ctypes.c_int, [_P, _P, c_int64, c_int32, _P, _P, _P]),
     "lgcn_spmm_plan_count": (ctypes.c_int, [_P, c_int32, c_int32, _P, _P]),
+    "lgcn_spmm_hint_indices": (ctypes.c_int, [_P, c_int64, _P, c_int32, _P, _P]),
     "lgcn_spmm_plan_count_slab": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "lgcn_spmm_plan_fill_slab": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, c_size_t, _P]),
     "lgcn_spmm_plan_workspace_bytes": (c_size_t, [c_int32]),

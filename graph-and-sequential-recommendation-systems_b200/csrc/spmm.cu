@@ -57,6 +57,7 @@ struct SpmmArgs {
     // (and of P in the Adam epilogue) over NVLink, so no separate all-gather pass re-reads and re-sends it
     int n_peers; float4* peerY[LGCN_MAX_PEERS]; float4* peerP[LGCN_MAX_PEERS];
     int multicast;      // peerY[0] / peerP[0] are NVSwitch multimem addresses: ONE store reaches every replica
+    int hinted;         // a.indices is the hinted copy (bit 31 = hot column): spmm_kernel<..., HINTED>
     int clear_z0;       // Adam epilogue: z[0] (= G, the batch gradient: zero except <= 3B rows) is zeroed where it was non-zero — this
                         // launch is its last reader in the step, so no separate clear_rows kernel is needed
     // column-slab blocking: items carry flags (bit0 = not the row's first segment: start from acc[row]; bit1 = not its last:
@@ -102,6 +103,14 @@ __device__ __forceinline__ float4 gather_f4(const float4* p) {
     return v;
 }
 
+__device__ __forceinline__ float4 gather_f4_policy(const float4* p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 __device__ __forceinline__ unsigned long long policy_evict_normal() {
     unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
 }
@@ -112,15 +121,18 @@ __device__ __forceinline__ float ld_stream_f32_policy(const float* p, unsigned l
     float v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v;
 }
 
-// HINT (blocked plans): the (col,val) stream carries an L2 evict-first policy so that it does not displace the slab of X
+// HINT (gathered table larger than L2, BASELINE config 5): a.indices is the HINTED copy of the column indices — bit 31 set
+// for a hot column (one of the highest-degree columns whose rows together fill ~half of L2).  Hot rows are gathered with an
+// L2 evict-last policy, the others with evict-first, and so is the (col,val) stream: the rows that are re-read most stay
+// resident instead of being displaced by rows that are read once (plain LRU keeps ~6 % of the gathers in L2 on config 5).
 template <int D, int LANES, int UNROLL, bool HINT>
 __device__ __forceinline__ void accumulate_item(const SpmmArgs& a, int start, int end, int lane,
                                                 unsigned gmask, float4 (&acc)[D / 4 / LANES]) {
     constexpr int VEC = D / 4, VPL = VEC / LANES;
     static_assert(LANES % UNROLL == 0, "UNROLL must divide the group width");
     if (start >= end) return;
-    unsigned long long pol = 0;
-    if constexpr (HINT) pol = policy_evict_first();
+    unsigned long long pol = 0, pol_hot = 0;
+    if constexpr (HINT) { pol = policy_evict_first(); pol_hot = policy_evict_last(); }
     auto ld_c = [&](const int* p) { if constexpr (HINT) return ld_stream_i32_policy(p, pol); else return ld_stream_i32(p); };
     auto ld_v = [&](const float* p) { if constexpr (HINT) return ld_stream_f32_policy(p, pol); else return ld_stream_f32(p); };
     int cnt = min(LANES, end - start);
@@ -144,9 +156,16 @@ __device__ __forceinline__ void accumulate_item(const SpmmArgs& a, int start, in
             for (int u = 0; u < UNROLL; ++u) {
                 const int cc = __shfl_sync(gmask, c, t + u, LANES);
                 w[u] = __shfl_sync(gmask, v, t + u, LANES);
-                const float4* src = a.X + (size_t)cc * VEC + lane;
+                if constexpr (HINT) {
+                    const float4* src = a.X + (size_t)(cc & 0x7fffffff) * VEC + lane;
+                    const unsigned long long pg = cc < 0 ? pol_hot : pol;
 #pragma unroll
-                for (int p = 0; p < VPL; ++p) x[u][p] = gather_f4(src + p * LANES);
+                    for (int p = 0; p < VPL; ++p) x[u][p] = gather_f4_policy(src + p * LANES, pg);
+                } else {
+                    const float4* src = a.X + (size_t)cc * VEC + lane;
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p) x[u][p] = gather_f4(src + p * LANES);
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
@@ -306,7 +325,7 @@ __device__ __forceinline__ void finish_item(const SpmmArgs& a, int row, int lane
     if (lane == 0) a.counters[long_id] = 0;                  // ready for the next launch
 }
 
-template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB, bool MASKED = false>
+template <int D, int LANES, int UNROLL, bool ADAM, int THREADS, int MINB, bool MASKED = false, bool HINTED = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_kernel(const __grid_constant__ SpmmArgs a) {
     constexpr int VEC = D / 4, VPL = VEC / LANES;
@@ -338,7 +357,7 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
 #pragma unroll
     for (int p = 0; p < VPL; ++p) acc[p] = f4_zero();
     if constexpr (MASKED) { griddep_wait(); accumulate_item_masked<D, LANES, UNROLL>(a, start, end, lane, gmask, (threadIdx.x & 31) / LANES * LANES, acc); }
-    else accumulate_item<D, LANES, UNROLL, false>(a, start, end, lane, gmask, acc);
+    else accumulate_item<D, LANES, UNROLL, HINTED>(a, start, end, lane, gmask, acc);
     griddep_wait();                                                       // (empty items skip the wait inside accumulate_item)
     griddep_launch_dependents();
     finish_item<D, LANES, ADAM, false>(a, row, lane, gmask, seg_ref, acc);
@@ -531,6 +550,12 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
         LGCN_CHECK_LAUNCH("spmm_kernel<masked>");
         return 0;
     }
+    if (a.hinted) {
+        constexpr int UH = UNROLL < 4 ? UNROLL : 4;
+        spmm_kernel<D, LANES, UH, ADAM, THREADS, MINB, false, true><<<(unsigned)blocks, THREADS, 0, st>>>(a);
+        LGCN_CHECK_LAUNCH("spmm_kernel<hinted>");
+        return 0;
+    }
     if (pdl_enabled()) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -608,7 +633,7 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
     LGCN_CHECK_ARG(nz >= 0 && nz <= LGCN_MAX_Z, "spmm: nz=%d out of range (max %d)", nz, LGCN_MAX_Z);
     LGCN_CHECK_ARG(nz == 0 || z_host, "spmm: nz>0 but z_host is null");
     LGCN_CHECK_ARG(((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0, "spmm: X/Y must be 16-byte aligned");
-    a.indptr = indptr; a.indices = indices; a.vals = vals;
+    a.indptr = indptr; a.indices = indices; a.vals = vals; a.hinted = 0;
     a.X = reinterpret_cast<const float4*>(X); a.Y = reinterpret_cast<float4*>(Y);
     a.alpha = alpha; a.beta = beta; a.nz = nz;
     for (int t = 0; t < LGCN_MAX_Z; ++t) {
@@ -625,6 +650,10 @@ static int fill_args(SpmmArgs& a, const int32_t* indptr, const int32_t* indices,
         a.counters = plan->counters; a.partials = reinterpret_cast<float4*>(plan->partials);
         LGCN_CHECK_ARG(((uintptr_t)plan->acc % 16) == 0, "spmm: plan.acc must be 16-byte aligned");
         a.acc = reinterpret_cast<float4*>(plan->acc);
+        if (plan->hinted_indices) {
+            LGCN_CHECK_ARG(!plan->acc && !col_mask, "spmm: hinted indices go with the whole-row plan only");
+            a.indices = plan->hinted_indices; a.hinted = 1;
+        }
     } else {
         LGCN_CHECK_ARG(indptr || n_rows == 0, "spmm: indptr is null and no plan was given");
         a.items = nullptr; a.n_items = n_rows; a.seginfo = nullptr; a.counters = nullptr; a.partials = nullptr; a.acc = nullptr;
@@ -688,9 +717,27 @@ gather_probe_kernel(const float4* __restrict__ X, const int* __restrict__ idx, l
     for (int p = 0; p < VPL; ++p) out[(size_t)g * VEC + lane + p * LANES] = acc[p];
 }
 
+// hinted copy of the column indices: bit 31 set where the column's weight (degree) reaches the threshold
+__global__ void hint_indices_kernel(const int* __restrict__ indices, long long nnz, const int* __restrict__ col_weight, int threshold,
+                                    int* __restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    const int c = indices[j];
+    out[j] = (__ldg(col_weight + c) >= threshold) ? (c | (int)0x80000000u) : c;
+}
+
 }  // namespace lgcn
 
 using namespace lgcn;
+
+extern "C" int lgcn_spmm_hint_indices(const int32_t* indices, int64_t nnz, const int32_t* col_weight, int32_t threshold,
+                                      int32_t* hinted_out, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(indices && col_weight && hinted_out && nnz >= 0, "spmm_hint_indices: bad arguments");
+    if (nnz == 0) return 0;
+    hint_indices_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, as_stream(stream)>>>(indices, nnz, col_weight, threshold, hinted_out);
+    LGCN_CHECK_LAUNCH("hint_indices_kernel");
+    return 0;
+}
 
 extern "C" int lgcn_debug_gather_rows(const float* X, const int32_t* idx, int64_t n_idx, int32_t d, int32_t run,
                                       int32_t variant, float* out, lgcn_stream_t stream) {

@@ -20,6 +20,8 @@ DEFAULT_SEG_LEN = 128
 SLAB_BYTES = int(os.environ.get('LGCN_SLAB_MB', '64')) << 20
 BLOCK_THRESHOLD_BYTES = int(os.environ.get('LGCN_BLOCK_THRESHOLD_MB', '112')) << 20
 BLOCKING_DEFAULT = os.environ.get('LGCN_BLOCKING', '0') == '1'
+XX
+HOT_BYTES = int(os.environ.get('LGCN_HOT_MB', '48')) << 20
 
 
 def _stream():
@@ -51,7 +53,10 @@ def device_info():
 class CSRGraph:
     """int32 CSR on the device + the SpMM segment plan for its long rows."""
 
-    def __init__(self, indptr, indices, vals, n_cols, deg=None, dinv=None, seg_len=DEFAULT_SEG_LEN):
+    def __init__(self, indptr, indices, vals, n_cols, deg=None, dinv=None, seg_len=DEFAULT_SEG_LEN, col_weight=None):
+        self.col_weight = col_weight          # optional int32[n_cols]: how often a column is gathered (its degree) — L2 hints
+        self._hinted = None
+        self._hint_bytes = None
         self.indptr = _need(indptr, torch.int32, "indptr", 1)
         self.indices = _need(indices, torch.int32, "indices", 1)
         self.vals = _need(vals, torch.float32, "vals", 1)
@@ -136,6 +141,28 @@ class CSRGraph:
     def clear_blocking(self):
         self._blocks = None
 
+    def hint_indices(self, d, hot_bytes=None):
+        """Hinted copy of the column indices for gathers from an (n_cols, d) table that does not fit L2 (bit 31 = hot column),
+        or None.  hot_bytes forces it (and its size) regardless of the table size."""
+        if hot_bytes is None:
+            if not HINTS_DEFAULT or self.col_weight is None or self.n_cols * d * 4 <= BLOCK_THRESHOLD_BYTES or self.nnz == 0:
+                return None
+            hot_bytes = HOT_BYTES
+        if self.col_weight is None:
+            raise RuntimeError("hint_indices: this graph carries no column weights")
+        if self._hinted is not None and self._hint_bytes == (int(hot_bytes), d):
+            return self._hinted
+        k = max(1, min(self.n_cols, int(hot_bytes) // (4 * d)))
+        thr = int(torch.topk(self.col_weight, k).values[-1].item())          # setup: degree of the k-th hottest column
+        thr = max(thr, 2)                                                      # a column read once has nothing to keep
+        out = torch.empty_like(self.indices)
+        _lib.check(_lib.load().lgcn_spmm_hint_indices(_p(self.indices), self.nnz, _p(self.col_weight), thr, _p(out), _stream()), "spmm_hint_indices")
+        self._hinted, self._hint_bytes, self._plan = out, (int(hot_bytes), d), None
+        return out
+
+    def clear_hints(self):
+        self._hinted, self._hint_bytes, self._plan = None, None, None
+
     def plan(self, d):
         if not self.use_plan:
             return None
@@ -147,6 +174,8 @@ class CSRGraph:
             pl.seginfo = self._seginfo.data_ptr()
             pl.counters = self._counters.data_ptr()
             pl.partials = self._partials.data_ptr()
+            h = self.hint_indices(d) if self._hinted is None else self._hinted
+            pl.hinted_indices = h.data_ptr() if h is not None else None
             self._plan = pl
         return self._plan
 
@@ -159,7 +188,7 @@ class CSRGraph:
         ip = (self.indptr[begin:end + 1] - self.indptr[begin]).contiguous()
         lo, hi = int(self.indptr[begin]), int(self.indptr[end])
         return CSRGraph(ip, self.indices[lo:hi], self.vals[lo:hi], self.n_cols,
-                        seg_len=self.seg_len if seg_len is None else seg_len)
+                        seg_len=self.seg_len if seg_len is None else seg_len, col_weight=self.col_weight)
 
     def to_torch_sparse_csr(self):
         return torch.sparse_csr_tensor(self.indptr, self.indices, self.vals, size=(self.n_rows, self.n_cols),
@@ -196,7 +225,8 @@ def csr_build(train_user, train_item, n_users, m_items, seg_len=DEFAULT_SEG_LEN)
     if status_h != 0:
         raise RuntimeError("csr_build: a user or item id is outside [0,n_users) x [0,m_items)")
     del ws
-    return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], N, deg=deg, dinv=dinv, seg_len=seg_len)
+    return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], N, deg=deg, dinv=dinv, seg_len=seg_len,
+                    col_weight=deg.to(torch.int32) if N * 64 * 4 > BLOCK_THRESHOLD_BYTES else None)
 
 
 class RowBlockBuilder:
@@ -255,7 +285,7 @@ class RowBlockBuilder:
         del ws
         if nnz_h < int(0.9 * n_keys):           # many duplicates: do not keep the slack alive
             indices, vals = indices[:nnz_h].clone(), vals[:nnz_h].clone()
-        return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], self.N, seg_len=self.seg_len)
+        return CSRGraph(indptr, indices[:nnz_h], vals[:nnz_h], self.N, seg_len=self.seg_len, col_weight=self.counts)
 
 
 class RankBarrier:

@@ -126,6 +126,9 @@ typedef struct {
     float* partials;          /* float32[n_segs*d_max]                                             */
     float* acc;               /* column-slab blocking (lgcn_spmm_plan_*_slab): float32[n_rows*d_max] running sums carried from one
                                  slab's launch to the next; NULL for a whole-row plan                                      */
+    const int32_t* hinted_indices; /* optional (whole-row plans, gathered table larger than L2): copy of `indices` with bit 31 set
+                                 for HOT columns (lgcn_spmm_hint_indices); their rows are gathered with an L2 evict-last
+                                 policy, all other gathers and the (col,val) stream with evict-first                         */
 } lgcn_spmm_plan_t;
 
 /* Fused SpMM + all-gather for the row partition: pointers to the PEER GPUs' copies of Y (and of P for
@@ -157,6 +160,10 @@ int lgcn_rank_barrier(uint32_t* flags_local, void* const* peer_flags_host, int32
  * so one step through the public API is "fill the pinned staging block, replay one graph, wait".  dst_is_host != 0 adds a
  * system-scope fence after the stores. */
 int lgcn_copy_words(void* dst, const void* src, int64_t n_bytes, int32_t dst_is_host, lgcn_stream_t stream);
+
+/* hinted_out[j] = indices[j] | (col_weight[indices[j]] >= threshold ? 1 << 31 : 0); col_weight int32[n_cols] (e.g. degrees) */
+int lgcn_spmm_hint_indices(const int32_t* indices, int64_t nnz, const int32_t* col_weight, int32_t threshold,
+                           int32_t* hinted_out, lgcn_stream_t stream);
 
 /* counts_out int32[4] = {n_long, n_segs, longest item, rows with an item} (device).  A row is cut into at most 2048 segments. */
 int lgcn_spmm_plan_count(const int32_t* indptr, int32_t n_rows, int32_t seg_len,

@@ -172,6 +172,22 @@ def test_spmm_column_slab_blocking_equals_unblocked(lg, orc, seg_len, slab_rows)
         assert rel_err(M1.cpu().numpy(), M0.cpu().numpy()) < 2e-6 and rel_err(P1.cpu().numpy(), P0.cpu().numpy()) < 1e-4
 
 
+def test_spmm_l2_hinted_gathers_are_bit_identical(lg):
+    """K1 with L2 eviction hints (hot columns evict-last, the rest evict-first: a cache policy, not arithmetic)."""
+    rng = np.random.default_rng(3)
+    nu, ni, d = 800, 1100, 64
+    tu, ti = random_edges(rng, nu, ni, 15000, dup=20)
+    g0, g1 = build(lg, tu, ti, nu, ni), build(lg, tu, ti, nu, ni)
+    g1.col_weight = g1.deg.to(torch.int32)
+    h = g1.hint_indices(d, hot_bytes=100 * d * 4)
+    assert h is not None and int((h < 0).sum()) > 0 and torch.equal(h & 0x7fffffff, g1.indices)
+    N = nu + ni
+    X = torch.randn(N, d, device='cuda'); Z = torch.randn(N, d, device='cuda')
+    Y0, Y1 = torch.empty(N, d, device='cuda'), torch.empty(N, d, device='cuda')
+    lg.ops.spmm(g0, X, Y0, 0.5, 0.25, [Z]); lg.ops.spmm(g1, X, Y1, 0.5, 0.25, [Z])
+    assert torch.equal(Y0, Y1)
+
+
 def test_training_step_with_blocked_graph_matches_unblocked(lg):
     """The whole fused step (forward, K2, backward, Adam) with K1 column-blocked == unblocked, bit for bit (tiny graph, no
     row long enough to be segmented inside a slab), through the reference-facing API in deterministic mode."""
