@@ -20,7 +20,12 @@ DEFAULT_SEG_LEN = 128
 SLAB_BYTES = int(os.environ.get('LGCN_SLAB_MB', '64')) << 20
 BLOCK_THRESHOLD_BYTES = int(os.environ.get('LGCN_BLOCK_THRESHOLD_MB', '112')) << 20
 BLOCKING_DEFAULT = os.environ.get('LGCN_BLOCKING', '0') == '1'
-XX
+# L2 eviction hints for K1's gathers when the gathered table does not fit L2 (csrc/spmm.cu, HINTED): the rows of the hottest
+# columns — as many as fill HOT_BYTES — are gathered evict-last, everything else evict-first.  OFF by default (LGCN_L2_HINTS=1,
+# or CSRGraph.hint_indices(d, hot_bytes=...)): measured on BASELINE config 5 it changes nothing — 36.2 ms per layer without,
+# 35.9-36.4 ms with hot sets of 16-96 MB covering 13-28 % of the non-zeros (profiles/r2_hint_probe.jsonl): the hardware's own
+# replacement already keeps the frequently re-read rows, and what misses are the rows that are read once.
+HINTS_DEFAULT = os.environ.get('LGCN_L2_HINTS', '0') == '1'
 HOT_BYTES = int(os.environ.get('LGCN_HOT_MB', '48')) << 20
 
 
