@@ -56,6 +56,26 @@ B = 2048
 L_LAYERS, D = 3, 64
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep file descriptor 1 for the ONE JSON line: everything else that writes to stdout (the procedures' own prints of
+    the metric dicts — the reference prints them too, code/Procedure.py:205 —, NCCL's version banner) goes to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -253,7 +273,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ measurement helpers (our arm)
@@ -789,7 +809,7 @@ def run_ours(args):
             return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         guarded("cpu_baseline", _cpu, line)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -811,6 +831,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
