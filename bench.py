@@ -139,14 +139,22 @@ class ClockSampler:
             pass
         return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
-    def _poll(self):
+    def sample_now(self):
+        """One NVML reading from the calling thread (Timing.loop calls it after a loop's steps are enqueued and before it
+        waits for them, i.e. with the GPU under load — the polling thread alone was seen to get a single reading in when
+        the loop enqueues 100 steps without a host-side wait in between)."""
+        if self.nvml is None or self.thread is None:
+            return
         nv, h = self.nvml
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-            except Exception:
-                pass
+            self.sample_now()
             time.sleep(0.001)
 
     def start(self):
@@ -280,6 +288,7 @@ def run_reference(args):
 class Timing:
     def __init__(self, dist, flush_buf):
         self.dist, self.flush_buf = dist, flush_buf
+        self.clocks = None              # a started ClockSampler: read once per loop while the loop's steps are executing
 
     def flush_l2(self):
         # read 512 MiB (4x the 126 MB L2): everything the step touched is evicted and the lines left behind are
@@ -304,6 +313,8 @@ class Timing:
             evs[i][0].record()
             step_fn(i)
             evs[i][1].record()
+        if self.clocks is not None:
+            self.clocks.sample_now()
         self.barrier()
         wall = time.perf_counter() - wall0
         ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -722,7 +733,9 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        tm.clocks = clocks
     ms_dev, _, all_ms = tm.repeats(step1, K, R)
+    tm.clocks = None
     clk = clocks.stop() if rank == 0 else None
     samples_per_step = B * (world if replicated else 1)
     value = samples_per_step * K / (ms_dev * 1e-3)
