@@ -64,7 +64,7 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
     bs = world.config['bpr_batch_size']
     mode, rank, nranks, group = _dist_info(Recmodel)
     if mode in ('dp', 'dp_idx'):
-        raise NotImplementedError("BPR_train_original drives one GPU or the row partition (dist_mode='rowpart'); the "
+        raise NotImplementedError("BPR_train_original drives one GPU, the row partition ('rowpart') or the feature partition ('featpart'); the "
                                   "replicated modes 'dp'/'dp_idx' are driven per rank through Engine.step")
     if world.config.get('device_sampler', False) and getattr(bpr, 'fused', False):
         # K5: sample + shuffle on the device, straight into the layout the step reads (no host phase, no H2D)
@@ -111,7 +111,7 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
         eng.set_lr(bpr.opt.param_groups[0]['lr'])
         eng.decay = float(bpr.weight_decay)
         S_dev = S_t
-        if mode == 'rowpart' and nranks > 1:
+        if mode in ('rowpart', 'featpart') and nranks > 1:
             # every rank replays the SAME epoch (the batch is replicated, the rows of A are what is split); the loss and
             # the returned string are identical on every rank
             _assert_same_on_every_rank(S_dev, group, "the epoch's sampled triples")

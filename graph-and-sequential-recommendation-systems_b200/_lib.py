@@ -27,6 +27,11 @@ class SpmmPeers(Structure):
     _fields_ = [("n_peers", c_int32), ("multicast", c_int32), ("y", c_void_p * 7), ("p", c_void_p * 7)]
 
 
+class BprFeat(Structure):
+    _fields_ = [("n_parts", c_int32), ("part", c_int32), ("scalars_dev", c_void_p), ("records_local", c_void_p),
+                ("records_peer", c_void_p * 8)]
+
+
 class AdamScalars(Structure):
     _fields_ = [
         ("step_size", c_float), ("bc2_sqrt", c_float), ("beta1", c_float), ("beta2", c_float),
@@ -72,6 +77,10 @@ _SIGNATURES = {
     "lgcn_bpr_fwd_bwd": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32,
                                         c_float, c_float, c_float, c_float, _P, _P, c_int32, c_int32,
                                         c_int32, _P, c_size_t, _P, _P, _P]),
+    "lgcn_bpr_feat_partial": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, POINTER(BprFeat), _P, c_size_t, _P]),
+    "lgcn_bpr_feat_finish": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, c_int32,
+                                            c_float, c_float, c_float, c_float, _P, _P, c_int32, POINTER(BprFeat),
+                                            _P, c_size_t, _P, _P, _P]),
     "lgcn_bpr_clear_rows": (ctypes.c_int, [_P, _P, _P, _P, c_int32, _P, c_int32, c_int32, _P]),
     "lgcn_batch_advance": (ctypes.c_int, [_P, c_int32, _P]),
     "lgcn_batch_masks": (ctypes.c_int, [_P, _P, _P, c_int32, _P, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P]),

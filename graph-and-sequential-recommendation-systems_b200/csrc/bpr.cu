@@ -39,7 +39,22 @@ struct BprArgs {
     unsigned* clear_mask;       // optional: the batch-row bitmap of lgcn_batch_masks — its bits are cleared here (its last reader
                                 // ran before this kernel), so the next step's batch_masks needs no memset
     float* loss_host;           // optional: mapped pinned host float[4] that receives a copy of loss_out
+    // feature partition (dist_mode='featpart': every rank holds d/P COLUMNS of all tables, `out` here is this rank's (N, D)
+    // slice): the five dot products of a triple are sums over the ranks' partial dot products.  n_parts > 1:
+    //   bpr_feat_partial_kernel  stores this rank's partials into slot `part` of EVERY rank's record buffer (peer stores),
+    //   [lgcn_rank_barrier]
+    //   bpr_kernel               replaces its local sums by the sum of the n_parts records in rank order — every rank gets
+    //                            the same bits — and carries on: loss, coefficients, gradient rows of ITS columns.
+    // Records are double-buffered by the parity of the Adam step counter (sc->step, device-resident): a rank can only
+    // overwrite a buffer two steps later, i.e. after a barrier every rank reached having finished reading it.
+    int n_parts, part;
+    const lgcn_adam_scalars_t* sc;
+    float4* xchg_local; float4* xchg_peer[LGCN_MAX_PEERS + 1];      // [2][n_parts][B_cap][2] float4: {pu,nu,uu,pp},{nn,0,0,0}
 };
+
+__device__ __forceinline__ size_t feat_record(const BprArgs& a, int part, int t) {
+    return (((size_t)(a.sc->step & 1) * a.n_parts + part) * a.B_cap + t) * 2;
+}
 
 // 1/B of the means: explicit when > 0, else from the device-resident batch descriptor
 // (ctl[3] = global batch size when the batch is sharded over ranks, else ctl[1])
@@ -82,8 +97,18 @@ bpr_kernel(const __grid_constant__ BprArgs a) {
             pu += f4_dot(U[q], P[q]); nu += f4_dot(U[q], Nn[q]);
             uu += f4_dot(U[q], U[q]); pp += f4_dot(P[q], P[q]); nn += f4_dot(Nn[q], Nn[q]);
         }
-        pu = group_sum(pu, gmask, LANES); nu = group_sum(nu, gmask, LANES);
-        uu = group_sum(uu, gmask, LANES); pp = group_sum(pp, gmask, LANES); nn = group_sum(nn, gmask, LANES);
+        if (a.n_parts > 1) {
+            // the ranks' partial dot products, added in rank order (written by peers: L2-coherent loads, not the L1)
+            pu = 0.f; nu = 0.f; uu = 0.f; pp = 0.f; nn = 0.f;
+            for (int q = 0; q < a.n_parts; ++q) {
+                const float4 r0 = ld_cg_f4(a.xchg_local + feat_record(a, q, t));
+                const float4 r1 = ld_cg_f4(a.xchg_local + feat_record(a, q, t) + 1);
+                pu += r0.x; nu += r0.y; uu += r0.z; pp += r0.w; nn += r1.x;
+            }
+        } else {
+            pu = group_sum(pu, gmask, LANES); nu = group_sum(nu, gmask, LANES);
+            uu = group_sum(uu, gmask, LANES); pp = group_sum(pp, gmask, LANES); nn = group_sum(nn, gmask, LANES);
+        }
         const float z = pu - nu;
         const float ez = expf(-fabsf(z));
         loss_t = fmaxf(-z, 0.f) + log1pf(ez);                 // softplus(-z) = -logsigmoid(z)
@@ -147,6 +172,39 @@ bpr_kernel(const __grid_constant__ BprArgs a) {
             }
             *a.counter = 0;
         }
+    }
+}
+
+// Feature partition, first half of K2: this rank's share of the five dot products of every triple, stored into every rank.
+template <int D>
+__global__ void __launch_bounds__(kBprThreads)
+bpr_feat_partial_kernel(const __grid_constant__ BprArgs a) {
+    constexpr int LANES = BGeo<D>::LANES, VPL = BGeo<D>::VPL, VEC = BGeo<D>::VEC;
+    constexpr int GROUPS = kBprThreads / LANES;
+    const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu
+                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+    const int off = a.ctl[0];
+    const int B = min(a.ctl[1], a.B_cap);
+    const int t = blockIdx.x * GROUPS + grp;
+    if (t >= B) return;
+    const long long u = a.users[off + t], p = a.pos[off + t] + a.n_users, n = a.neg[off + t] + a.n_users;
+    const float4* ur = a.out + (size_t)u * VEC + lane;
+    const float4* pr = a.out + (size_t)p * VEC + lane;
+    const float4* nr = a.out + (size_t)n * VEC + lane;
+    float pu = 0.f, nu = 0.f, uu = 0.f, pp = 0.f, nn = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+        const float4 U = __ldg(ur + q * LANES), P = __ldg(pr + q * LANES), Nn = __ldg(nr + q * LANES);
+        pu += f4_dot(U, P); nu += f4_dot(U, Nn);
+        uu += f4_dot(U, U); pp += f4_dot(P, P); nn += f4_dot(Nn, Nn);
+    }
+    pu = group_sum(pu, gmask, LANES); nu = group_sum(nu, gmask, LANES);
+    uu = group_sum(uu, gmask, LANES); pp = group_sum(pp, gmask, LANES); nn = group_sum(nn, gmask, LANES);
+    if (lane == 0) {
+        const size_t at = feat_record(a, a.part, t);
+        const float4 r0 = make_float4(pu, nu, uu, pp), r1 = make_float4(nn, 0.f, 0.f, 0.f);
+        for (int q = 0; q < a.n_parts; ++q) { st_stream_f4(a.xchg_peer[q] + at, r0); st_stream_f4(a.xchg_peer[q] + at + 1, r1); }
     }
 }
 
@@ -306,17 +364,17 @@ static int launch_bpr(BprArgs& a, int deterministic, cudaStream_t st) {
 using namespace lgcn;
 
 extern "C" size_t lgcn_bpr_workspace_bytes(int32_t B_cap, int32_t d) {
-    if (B_cap <= 0 || d < 16) return 0;
+    if (B_cap <= 0 || d < 8) return 0;
     // [counter:16 B][partials: 2 floats per CTA][coef: B_cap floats]
     return 16 + align_up(2 * sizeof(float) * bpr_blocks(B_cap, d), 16) + align_up(sizeof(float) * (size_t)B_cap, 16);
 }
 
-extern "C" int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const int64_t* pos, const int64_t* neg,
-                                int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items,
-                                int32_t d, float inv_norm, float decay, float c_bpr, float c_reg,
-                                float* loss_out, float* G, int32_t own_begin, int32_t own_end,
-                                int32_t deterministic, void* workspace, size_t workspace_bytes,
-                                uint32_t* clear_mask, float* loss_host_mapped, lgcn_stream_t stream) {
+static int bpr_run(const float* out, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                   int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items,
+                   int32_t d, float inv_norm, float decay, float c_bpr, float c_reg,
+                   float* loss_out, float* G, int32_t own_begin, int32_t own_end,
+                   int32_t deterministic, void* workspace, size_t workspace_bytes,
+                   uint32_t* clear_mask, float* loss_host_mapped, const lgcn_bpr_feat_t* feat, int feat_phase, lgcn_stream_t stream) {
     LGCN_CHECK_ARG(out && users && pos && neg && batch_ctl_dev && loss_out, "bpr: null argument");
     LGCN_CHECK_ARG(B_cap > 0, "bpr: B_cap must be > 0");
     LGCN_CHECK_ARG(workspace && workspace_bytes >= lgcn_bpr_workspace_bytes(B_cap, d), "bpr: workspace too small");
@@ -330,19 +388,74 @@ extern "C" int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const in
     a.inv_norm = inv_norm; a.decay = decay; a.c_bpr = c_bpr; a.c_reg = c_reg;
     a.loss_out = loss_out; a.G = reinterpret_cast<float4*>(G); a.own_begin = own_begin; a.own_end = own_end;
     a.clear_mask = clear_mask; a.loss_host = loss_host_mapped;
+    a.n_parts = 1; a.part = 0; a.sc = nullptr; a.xchg_local = nullptr;
+    for (int q = 0; q <= LGCN_MAX_PEERS; ++q) a.xchg_peer[q] = nullptr;
+    if (feat) {
+        LGCN_CHECK_ARG(feat->n_parts >= 1 && feat->n_parts <= LGCN_MAX_PEERS + 1 && feat->part >= 0 && feat->part < feat->n_parts,
+                       "bpr_feat: part %d of %d out of range", feat->part, feat->n_parts);
+        LGCN_CHECK_ARG(feat->scalars_dev && feat->records_local && ((uintptr_t)feat->records_local % 16) == 0, "bpr_feat: scalars / record buffer missing or misaligned");
+        a.n_parts = feat->n_parts; a.part = feat->part; a.sc = feat->scalars_dev;
+        a.xchg_local = reinterpret_cast<float4*>(feat->records_local);
+        for (int q = 0; q < feat->n_parts; ++q) {
+            LGCN_CHECK_ARG(feat_phase != 1 || (feat->records_peer[q] && ((uintptr_t)feat->records_peer[q] % 16) == 0), "bpr_feat: record buffer of rank %d not mapped", q);
+            a.xchg_peer[q] = reinterpret_cast<float4*>(feat->records_peer[q]);
+        }
+    }
     char* w = static_cast<char*>(workspace);
     a.counter = reinterpret_cast<int*>(w);
     a.partials = reinterpret_cast<float*>(w + 16);
     a.coef = reinterpret_cast<float*>(w + 16 + align_up(2 * sizeof(float) * bpr_blocks(B_cap, d), 16));
     cudaStream_t st = as_stream(stream);
+    if (feat_phase == 1) {
+#define LGCN_FEAT1(DD) { constexpr int GR = kBprThreads / BGeo<DD>::LANES; \
+        bpr_feat_partial_kernel<DD><<<(unsigned)((B_cap + GR - 1) / GR), kBprThreads, 0, st>>>(a); } break
+        switch (d) {
+            case 8: LGCN_FEAT1(8); case 16: LGCN_FEAT1(16); case 32: LGCN_FEAT1(32); case 64: LGCN_FEAT1(64);
+            default: return fail("bpr_feat_partial: local width %d unsupported (8,16,32,64)", d);
+        }
+#undef LGCN_FEAT1
+        LGCN_CHECK_LAUNCH("bpr_feat_partial_kernel");
+        return 0;
+    }
     switch (d) {
+        case 8:   return launch_bpr<8>(a, deterministic, st);
         case 16:  return launch_bpr<16>(a, deterministic, st);
         case 32:  return launch_bpr<32>(a, deterministic, st);
         case 64:  return launch_bpr<64>(a, deterministic, st);
         case 128: return launch_bpr<128>(a, deterministic, st);
         case 256: return launch_bpr<256>(a, deterministic, st);
-        default:  return fail("bpr: d=%d unsupported (16,32,64,128,256)", d);
+        default:  return fail("bpr: d=%d unsupported (8,16,32,64,128,256)", d);
     }
+}
+
+extern "C" int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                                int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items,
+                                int32_t d, float inv_norm, float decay, float c_bpr, float c_reg,
+                                float* loss_out, float* G, int32_t own_begin, int32_t own_end,
+                                int32_t deterministic, void* workspace, size_t workspace_bytes,
+                                uint32_t* clear_mask, float* loss_host_mapped, lgcn_stream_t stream) {
+    return bpr_run(out, users, pos, neg, B_cap, batch_ctl_dev, n_users, m_items, d, inv_norm, decay, c_bpr, c_reg, loss_out, G,
+                   own_begin, own_end, deterministic, workspace, workspace_bytes, clear_mask, loss_host_mapped, nullptr, 0, stream);
+}
+
+extern "C" int lgcn_bpr_feat_partial(const float* out_slice, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                                     int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items, int32_t d_local,
+                                     const lgcn_bpr_feat_t* feat, void* workspace, size_t workspace_bytes, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(feat, "bpr_feat_partial: feat is null");
+    float dummy_loss;      // never dereferenced by the partial kernel
+    return bpr_run(out_slice, users, pos, neg, B_cap, batch_ctl_dev, n_users, m_items, d_local, 0.f, 0.f, 0.f, 0.f, &dummy_loss, nullptr,
+                   0, 0, 0, workspace, workspace_bytes, nullptr, nullptr, feat, 1, stream);
+}
+
+extern "C" int lgcn_bpr_feat_finish(const float* out_slice, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                                    int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items,
+                                    int32_t d_local, float inv_norm, float decay, float c_bpr, float c_reg,
+                                    float* loss_out, float* G_slice, int32_t deterministic, const lgcn_bpr_feat_t* feat,
+                                    void* workspace, size_t workspace_bytes,
+                                    uint32_t* clear_mask, float* loss_host_mapped, lgcn_stream_t stream) {
+    LGCN_CHECK_ARG(feat, "bpr_feat_finish: feat is null");
+    return bpr_run(out_slice, users, pos, neg, B_cap, batch_ctl_dev, n_users, m_items, d_local, inv_norm, decay, c_bpr, c_reg, loss_out, G_slice,
+                   0, n_users + m_items, deterministic, workspace, workspace_bytes, clear_mask, loss_host_mapped, feat, 2, stream);
 }
 
 extern "C" int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t* pos, const int64_t* neg,
@@ -357,7 +470,7 @@ extern "C" int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t
 #define LGCN_CLR(DD) { constexpr int GR = kBprThreads / BGeo<DD>::LANES; \
         bpr_clear_rows_kernel<DD><<<(unsigned)((3LL * B_cap + GR - 1) / GR), kBprThreads, 0, st>>>(g4, u, p, n, B_cap, batch_ctl_dev, n_users); } break
     switch (d) {
-        case 16: LGCN_CLR(16); case 32: LGCN_CLR(32); case 64: LGCN_CLR(64); case 128: LGCN_CLR(128); case 256: LGCN_CLR(256);
+        case 8: LGCN_CLR(8); case 16: LGCN_CLR(16); case 32: LGCN_CLR(32); case 64: LGCN_CLR(64); case 128: LGCN_CLR(128); case 256: LGCN_CLR(256);
         default: return fail("bpr_clear_rows: d=%d unsupported", d);
     }
 #undef LGCN_CLR

@@ -363,6 +363,92 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
     finish_item<D, LANES, ADAM, false>(a, row, lane, gmask, seg_ref, acc);
 }
 
+// ---- narrow tables (d = 8 / 16 / 32: the column slices of the feature partition, dist_mode='featpart') ---------------------
+// With a 32..128-byte row the lane layout of spmm_kernel (a group of lanes shares ONE row, the (col,val) pairs go round by
+// shuffle) pays two shuffles, an address and a request per lane for 16 useful bytes: measured on the gowalla shape a d = 8
+// layer took 29-49 us against 35 us at d = 64 — no faster for an eighth of the bytes
+// (profiles/r2_feat_probe_row_per_group_kernel.jsonl).  Here a
+// lane owns whole NON-ZEROS: the GL lanes of a group stride over the item's entries (their (col,val) loads are coalesced, no
+// shuffles), each lane gathers the whole row of its entry with 256-bit loads (one request per 32 bytes: LDG.E.256) and keeps a
+// full-width partial sum; the group's partial sums meet in a fixed xor tree at the end.  Deterministic, but the summation
+// order differs from spmm_kernel's (entry j goes to lane j mod GL), so the two agree to rounding, not bit for bit.
+// What bounds it: one L2 request per non-zero — ~2 SM cycles per non-zero on both shapes, whatever the row width; wider slices
+// (d = 16, 32) are served by spmm_kernel, whose cooperating lanes fetch a 64/128-byte row with one request.
+__device__ __forceinline__ void ld_row256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+template <int D, int GL, int UNROLL, bool ADAM, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+spmm_narrow_kernel(const __grid_constant__ SpmmArgs a) {
+    constexpr int VEC = D / 4, GROUPS = 128 / GL;
+    static_assert(VEC >= 2 && VEC <= GL && VEC % 2 == 0 && GL <= 32, "narrow kernel: 8 <= d <= 4 * GL, d a multiple of 8");
+    const int lane = threadIdx.x % GL;
+    const int gshift = (threadIdx.x & 31) / GL * GL;
+    const unsigned gmask = (GL == 32) ? 0xffffffffu : (((1u << GL) - 1u) << gshift);
+    const long long gidx = (long long)blockIdx.x * GROUPS + threadIdx.x / GL;
+    if (gidx >= a.n_items) return;
+    int row, start, end, seg_ref;
+    if (a.items != nullptr) {
+        const int4 it = __ldg(a.items + gidx);
+        row = it.x; start = it.y; end = it.z; seg_ref = it.w;
+    } else {
+        row = (int)gidx; start = __ldg(a.indptr + row); end = __ldg(a.indptr + row + 1); seg_ref = -1;
+    }
+    if (a.row_mask != nullptr) {
+        griddep_wait();
+        if (!mask_bit(a.row_mask, row)) return;
+    }
+    float4 acc[VEC];
+#pragma unroll
+    for (int p = 0; p < VEC; ++p) acc[p] = f4_zero();
+    // entries start + lane, + GL, + 2 GL, ...: UNROLL of them per round; entries past the end re-read the last one with weight 0
+    int c[UNROLL]; float v[UNROLL];
+    auto fetch = [&](int base) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int j = base + u * GL + lane;
+            const bool ok = j < end;
+            c[u] = ld_stream_i32(a.indices + (ok ? j : end - 1));
+            v[u] = ok ? ld_stream_f32(a.vals + j) : 0.f;
+        }
+    };
+    if (start < end) fetch(start);                          // static data: before the wait for the previous kernel
+    griddep_wait();
+    for (int base = start; base < end; base += GL * UNROLL) {
+        float4 x[UNROLL][VEC]; float w[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const float4* src = a.X + (size_t)c[u] * VEC;
+            w[u] = v[u];
+#pragma unroll
+            for (int p = 0; p < VEC; p += 2) ld_row256(src + p, x[u][p], x[u][p + 1]);
+        }
+        if (base + GL * UNROLL < end) fetch(base + GL * UNROLL);     // next round's (col,val) while the rows are in flight
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int p = 0; p < VEC; ++p) f4_fma(acc[p], w[u], x[u][p]);
+    }
+    griddep_launch_dependents();
+#pragma unroll
+    for (int o = GL >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int p = 0; p < VEC; ++p) {
+            acc[p].x += __shfl_xor_sync(gmask, acc[p].x, o, GL); acc[p].y += __shfl_xor_sync(gmask, acc[p].y, o, GL);
+            acc[p].z += __shfl_xor_sync(gmask, acc[p].z, o, GL); acc[p].w += __shfl_xor_sync(gmask, acc[p].w, o, GL);
+        }
+    }
+    // the first VEC lanes of the group finish the row, one float4 each (finish_item / epilogue in their VEC-lane layout)
+    if (lane >= VEC) return;
+    float4 mine[1] = {acc[0]};
+#pragma unroll
+    for (int p = 1; p < VEC; ++p) if (lane == p) mine[0] = acc[p];
+    const unsigned emask = ((1u << VEC) - 1u) << gshift;
+    finish_item<D, VEC, ADAM, false>(a, row, lane, emask, seg_ref, mine);
+}
+
 // ---- column-slab blocked launches --------------------------------------------------------------------------------
 // The items of a slab launch are SHORT (a row's entries inside one 64 MB slab of columns: ~3-40) and each one is a dependent
 // chain  descriptor -> (columns, values, running sum) -> gathers -> store.  With one item per group (spmm_kernel) a slab launch
@@ -572,6 +658,28 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
     return 0;
 }
 
+template <int D, int GL, int UNROLL, bool ADAM, int MINB>
+static int launch_narrow(const SpmmArgs& a, cudaStream_t st) {
+    constexpr int GROUPS = 128 / GL;
+    if (a.n_items == 0) return 0;
+    const long long blocks = ((long long)a.n_items + GROUPS - 1) / GROUPS;
+    if (blocks > 0x7fffffffLL) return fail("spmm: grid too large");
+    if (pdl_enabled()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, spmm_narrow_kernel<D, GL, UNROLL, ADAM, MINB>, a);
+        if (e != cudaSuccess) return fail("spmm_narrow_kernel (programmatic dependent launch): %s", cudaGetErrorString(e));
+        return 0;
+    }
+    spmm_narrow_kernel<D, GL, UNROLL, ADAM, MINB><<<(unsigned)blocks, 128, 0, st>>>(a);
+    LGCN_CHECK_LAUNCH("spmm_narrow_kernel");
+    return 0;
+}
+
 template <int D, int LANES, int UNROLL, bool ADAM>
 static int launch_blocked(const SpmmArgs& a, cudaStream_t st) {
     if (a.n_items == 0) return 0;
@@ -595,7 +703,14 @@ static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
         case 256: return launch_blocked<256, 32, 2, ADAM>(a, st);
         default:  return fail("spmm: d=%d unsupported (16,32,64,128,256)", d);
     }
+    // 32-byte rows (d = 8, the slices of an 8-way feature partition): a lane per non-zero (spmm_narrow_kernel) unless a column mask,
+    // hints or a fused exchange ask for the row-per-group kernel (variant 50 forces that kernel: measurement).  Measured per layer
+    // inside a captured graph (profiles/r2_feat_probe_k1_slice_widths.jsonl, gowalla / amazon-book shape): 13.8 / 34.3 us against
+    // 25-39 / 47-56 us; at d = 16 and 32 the row-per-group kernel is the faster one (18.8 / 35.3 and 29.7 / 53.6 us) and is kept.
+    if (d == 8 && a.col_mask == nullptr && !a.hinted && a.n_peers == 0 && g_variant != 50 && ((uintptr_t)a.X % 32) == 0)
+        return launch_narrow<8, 8, 2, ADAM, 8>(a, st);
     switch (d) {
+        case 8:   return launch_cfg<8, 2, 2, ADAM, 128, 8>(a, st);       // feature partition over 8 ranks: 32-byte rows
         case 16:  return launch_cfg<16, 4, 4, ADAM, 128, 8>(a, st);
         case 32:  return launch_cfg<32, 4, 4, ADAM, 128, 8>(a, st);
         case 64:
@@ -620,7 +735,7 @@ static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
             if (!ADAM && g_variant == 1) return launch_cfg<256, 16, 2, false, 128, 8>(a, st);
             if (!ADAM && g_variant == 2) return launch_cfg<256, 32, 2, false, 128, 8>(a, st);
             return launch_cfg<256, 32, 4, ADAM, 128, 8>(a, st);
-        default:  return fail("spmm: d=%d unsupported (16,32,64,128,256)", d);
+        default:  return fail("spmm: d=%d unsupported (8,16,32,64,128,256)", d);
     }
 }
 

@@ -36,6 +36,13 @@ Multi-GPU (one process per GPU, torch.distributed):
                   issues ONE NVSwitch multicast store (multimem.st) per 16 bytes instead of world-1 unicast stores.
                   rebalance=3 (default, rounds): the block boundaries are moved to equal measured time at start-up —
                   item rows gather from the larger table, so equal nnz (+ row cost) is not equal time.
+  mode 'featpart' COLUMNS of the embedding tables partitioned: rank p holds columns [p*d/P, (p+1)*d/P) of E0, X_k, out, G, M, V
+                  and the whole CSR.  A CSR SpMM is independent per column, so the 2L products of a step need NO exchange; the
+                  only cross-rank dependence is K2's five dot products per triple: every rank stores its partial sums into all
+                  ranks (40 KB per step, peer stores), ONE device barrier, then K2 runs on the slice with the summed records
+                  (ops.FeatExchange, csrc/bpr.cu).  This is the mode for graphs that FIT one GPU (the three named shapes), where
+                  the row partition is bound by the NVLink ingest of every layer's table; it does not partition the CSR.
+                  Every other line of the step is the single-GPU step at width d/P, captured in one CUDA graph per rank.
 """
 import torch
 
@@ -151,11 +158,40 @@ def shard_batch(n, rank, world):
     return lo, min(n, lo + per)
 
 
+def link_feat_engines(engines, timeout_ms=20000):
+    """Wire together feature-partition ranks emulated in ONE process (Engine(..., dist_mode='featpart', feat=(rank, world)),
+    one CUDA stream per engine): the 'peer' buffers are plain tensors of the same device.  The step sequence, the record
+    exchange and the device barrier are the ones the multi-process mode runs."""
+    world = len(engines)
+    engines = sorted(engines, key=lambda e: e.rank)
+    if [e.rank for e in engines] != list(range(world)) or any(e.world != world or not e._feat_virtual for e in engines):
+        raise RuntimeError("link_feat_engines: need exactly one emulated engine per rank")
+    # Load every kernel of the step first (a throw-away step per engine on a one-rank exchange): with lazy module loading the
+    # first launch of a kernel can wait for the device to go idle — while another emulated rank's barrier is spinning on it and
+    # this host thread, the only one, has not yet enqueued the rank it waits for.  (Separate processes cannot block each other.)
+    for e in engines:
+        rec1 = torch.zeros(2 * e.B_cap * 8, dtype=torch.float32, device=e.device)
+        flg1 = torch.zeros(64, dtype=torch.int32, device=e.device)
+        e.xchg = ops.FeatExchange(rec1, [rec1], flg1, [flg1], 0, 1, e.B_cap, e.scalars)
+        e._warm_kernels(e.bu, e.bp, e.bn, e.ctl)
+    torch.cuda.synchronize()
+    recs, flags = [e._feat_records for e in engines], [e._feat_flags for e in engines]
+    for e in engines:
+        e.xchg = ops.FeatExchange(e._feat_records, recs, e._feat_flags, flags, e.rank, world, e.B_cap, e.scalars, timeout_ms=timeout_ms)
+        e._barrier = e.xchg.barrier
+        e._graphs = {}
+
+
 class Engine:
     def __init__(self, csr, n_users, m_items, d, n_layers, device, *, lr=1e-3, decay=1e-4, B_cap=2048,
-                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True, row_cost=None, multicast=True, rebalance=3):
+                 deterministic=False, use_graph=True, dist_mode=None, group=None, prune=True, p2p=True, row_cost=None, multicast=True, rebalance=3,
+                 feat=None):
+        """feat=(rank, world): dist_mode='featpart' WITHOUT a process group — several ranks emulated in one process (one
+        engine and one CUDA stream each; tests): the caller wires them together with link_feat_engines()."""
         if n_layers > 8:
             raise RuntimeError("lightGCN_n_layers > 8 is not supported (LGCN_MAX_Z)")
+        if feat is not None and dist_mode != 'featpart':
+            raise RuntimeError("feat=(rank, world) goes with dist_mode='featpart' only")
         self.builder = csr if isinstance(csr, ops.RowBlockBuilder) else None
         if self.builder is not None and dist_mode != 'rowpart':
             raise RuntimeError("a RowBlockBuilder is the graph source of dist_mode='rowpart' only")
@@ -170,12 +206,28 @@ class Engine:
         self.dist_mode = dist_mode
         self.group = group
         self.rank, self.world = 0, 1
-        if dist_mode is not None:
+        self._feat_virtual = feat is not None
+        if feat is not None:
+            self.rank, self.world = int(feat[0]), int(feat[1])
+        elif dist_mode is not None:
             import torch.distributed as dist
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.d_full, self.c0 = d, 0
+        self.xchg = None
+        self.pre_step_hook = None           # set by the model under the feature partition: push externally written parameters into the slice
+        self.full_param_sync = None         #   "    : refresh the model's full parameter table from the ranks' slices (collective)
+        if dist_mode == 'featpart':
+            if d % self.world or (d // self.world) not in (8, 16, 32, 64):
+                raise RuntimeError(f"dist_mode='featpart': latent_dim {d} over {self.world} ranks gives a slice of {d / self.world:g} columns; supported slices: 8, 16, 32, 64")
+            if isinstance(csr, ops.RowBlockBuilder) or csr is None:
+                raise RuntimeError("dist_mode='featpart' replicates the CSR: hand it the whole CSRGraph (use 'rowpart' for graphs beyond one GPU)")
+            d = d // self.world                       # everything below is the single-GPU engine at the slice width
+            self.d, self.c0 = d, self.rank * d
+            if d == 16:                               # 4-lane groups walk 4 non-zeros per round trip: shorter segments bound the longest item
+                self.csr = self.csr.rows(0, self.csr.n_rows, seg_len=min(self.csr.seg_len, 64))     # (18.8 vs 24.1 us per layer, gowalla shape)
         # fused exchange (K1 stores into the peers + device-side barrier): one NVSwitch box, CUDA only
         self.p2p = bool(p2p) and dist_mode == 'rowpart' and self.world > 1 and self.world - 1 <= 7 and torch.device(device).type == 'cuda'
-        self.use_graph = bool(use_graph) and (dist_mode in (None, 'dp_idx') or (dist_mode == 'rowpart' and (self.p2p or self.world == 1)))
+        self.use_graph = bool(use_graph) and (dist_mode in (None, 'dp_idx', 'featpart') or (dist_mode == 'rowpart' and (self.p2p or self.world == 1)))
         if dist_mode == 'dp_idx':
             self.B_cap = self.B_cap * self.world          # the static batch buffers hold the GLOBAL batch
             self.deterministic = True                     # replicas are never re-synchronised: they must not drift in rounding
@@ -198,7 +250,7 @@ class Engine:
         self.param_epoch = 0
         # dead-row pruning of the training step (see _enqueue_step): bitmaps over the N nodes
         # (row partition: the bitmap covers the rank's own rows, indexed by local row; (re)allocated in _take_block)
-        self.prune = bool(prune) and dist_mode in (None, 'dp_idx', 'rowpart')
+        self.prune = bool(prune) and dist_mode in (None, 'dp_idx', 'rowpart', 'featpart')
         words = (N + 31) // 32
         self.m0 = torch.zeros(words, dtype=torch.int32, device=device)
         # row partition
@@ -278,6 +330,8 @@ class Engine:
 
     def adam_state_full(self):
         """Full (N,d) Adam moments on every rank (collective in the memory-partitioned row partition: checkpoints)."""
+        if self.dist_mode == 'featpart' and self.world > 1:
+            return self.gather_columns(self.M), self.gather_columns(self.V)
         if not self._mv_local:
             if self.dist_mode == 'rowpart' and self.world > 1:
                 M, V = self.M.clone(), self.V.clone()
@@ -293,7 +347,10 @@ class Engine:
         return full[0], full[1]
 
     def load_adam_state(self, M_full, V_full):
-        if self._mv_local:
+        if self.dist_mode == 'featpart' and self.world > 1:
+            c0, c1 = self.c0, self.c0 + self.d
+            self.M.copy_(M_full[:, c0:c1]); self.V.copy_(V_full[:, c0:c1])
+        elif self._mv_local:
             self.M.copy_(M_full[self.r0:self.r1]); self.V.copy_(V_full[self.r0:self.r1])
         else:
             self.M.copy_(M_full); self.V.copy_(V_full)
@@ -334,6 +391,8 @@ class Engine:
         self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.bpr_ws = ops.bpr_workspace(self.B_cap, self.d, self.device)
         self._graphs = {}
+        if self.dist_mode == 'featpart' and self.world > 1:
+            self._setup_feat_exchange()
         # zero-copy staging: a host batch is read straight out of the pinned block by a kernel at the head of the captured
         # step, and the loss is written into pinned memory by a kernel at its tail (no copy-engine hops, one graph launch)
         self._zc_slot = None
@@ -341,6 +400,39 @@ class Engine:
         if self.zero_copy:
             ops.copy_words(self._loss_host, self.loss_out, 16, dst_is_host=True)      # loads the kernel before any capture
             torch.cuda.current_stream().synchronize()
+
+    def _setup_feat_exchange(self):
+        """Feature partition: this rank's record buffer and barrier flags, and (between processes) the peers' mappings.
+        Collective when a process group is used — _alloc_batch is entered by every rank with the same B_cap."""
+        self._feat_records = torch.zeros(2 * self.world * self.B_cap * 8, dtype=torch.float32, device=self.device)
+        self._feat_flags = torch.zeros(64, dtype=torch.int32, device=self.device)
+        self.xchg, self._barrier = None, None
+        if self._feat_virtual:
+            return                                  # link_feat_engines() wires the emulated ranks together
+        import torch.distributed as dist
+        from . import _lib
+        if self.world - 1 > 7:
+            raise RuntimeError("dist_mode='featpart' serves the <= 8 GPUs of one NVSwitch box")
+        for p_dev in range(torch.cuda.device_count()):
+            _lib.load().lgcn_enable_peer_access(p_dev)
+        torch.cuda.synchronize()
+        self.xchg = ops.FeatExchange(self._feat_records, map_peer_buffers(self._feat_records, self.group), self._feat_flags,
+                                     map_peer_buffers(self._feat_flags, self.group), self.rank, self.world, self.B_cap, self.scalars)
+        self._barrier = self.xchg.barrier
+        dist.barrier(self.group)
+
+    def gather_columns(self, local, out_full=None):
+        """(N, d) table on every rank from the ranks' (N, d/P) column slices (collective; evaluation and checkpoints)."""
+        if self.dist_mode != 'featpart' or self.world == 1:
+            return local
+        import torch.distributed as dist
+        n = local.shape[0]
+        parts = torch.empty((self.world, n, self.d), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(parts, local.contiguous(), group=self.group)
+        if out_full is None:
+            out_full = torch.empty((n, self.d_full), dtype=local.dtype, device=local.device)
+        out_full.view(n, self.world, self.d).copy_(parts.permute(1, 0, 2))
+        return out_full
 
     def _stage_batch(self, users, pos, neg, B_global=0):
         """Put the batch where the step reads it.  Device tensors: device-side copies into the staging block.  Host tensors:
@@ -516,7 +608,7 @@ class Engine:
         if only_spmm:
             return self._enqueue_spmm_only()
         zc, fuse = self._zc_slot, self.fuse_small
-        local_g = self.dist_mode in (None, 'dp_idx')                       # G, m0 are whole-graph and every row is visited by this rank
+        local_g = self.dist_mode in (None, 'dp_idx', 'featpart')           # G, m0 are whole-graph and every row is visited by this rank
         if fuse:
             ops.step_begin(self.scalars, self.B_cap, advance_ctl=ctl if advance else None,
                            stage_dst=self._blk if zc is not None else None, stage_src=self._stage[zc][0] if zc is not None else None)
@@ -560,6 +652,15 @@ class Engine:
             pg = self.pg
             ops.popgate_bpr_fwd_bwd(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, pg['pop'], pg['params'], pg['H1'], pg['H2'],
                                     pg['temp'], pg['coeff'], self.decay, self.loss_out, self.G, pg['grad'], pg['ws'])
+        elif self.dist_mode == 'featpart' and self.world > 1:
+            if self.xchg is None:
+                raise RuntimeError("featpart: the emulated ranks were not linked (link_feat_engines)")
+            # the one exchange of the step: partial dot products into every rank, barrier, K2 on the slice with the sums
+            ops.bpr_feat_partial(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, self.xchg, self.bpr_ws)
+            self.xchg.barrier()
+            ops.bpr_feat_finish(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0, self.decay,
+                                self.loss_out, self.G, self.xchg, self.bpr_ws, deterministic=self.deterministic,
+                                clear_mask=self.m0 if k2_clears_mask else None, loss_host=self._loss_host if k2_writes_host else None)
         else:
             ops.bpr_fwd_bwd(out, users, pos, neg, self.B_cap, ctl, self.nu, self.ni, 0.0, self.decay, 1.0,
                             self.decay, self.loss_out, self.G, self.bpr_ws, deterministic=self.deterministic,
@@ -619,7 +720,7 @@ class Engine:
         step) — bench.py times its replays to get K1's launch duration under the conditions of the captured step.
         Replays run the Adam epilogue on whatever G holds: callers save and restore E0/M/V/scalars around them."""
         self._sync_params_across_ranks()
-        if self.prune and self.dist_mode in (None, 'dp_idx'):
+        if self.prune and self.dist_mode in (None, 'dp_idx', 'featpart'):
             # K2 leaves the batch-row bitmap all-zero after every step: set the bits of the current batch window again
             # (they stay set: these replays have no K2), so that the masked layer does the work it does in a real step
             if self._epoch is not None:
@@ -667,6 +768,8 @@ class Engine:
     def step(self, users, pos, neg, B_global=0):
         """One BPR step on a batch given as host or device int64 tensors. Returns nothing; the loss is
         in self.loss_out (device).  Host batches cost one H2D copy."""
+        if self.pre_step_hook is not None:
+            self.pre_step_hook()
         if self.dist_mode == 'dp' and not B_global:
             B_global = int(users.numel()) * self.world          # equal shards unless the caller says otherwise
         if self.dist_mode == 'dp_idx':
@@ -697,6 +800,8 @@ class Engine:
     def sync_params_for_read(self):
         """Make this rank's replica of the parameter table complete (collective; no-op when the fused exchange already
         keeps the replicas in step or when nothing is partitioned)."""
+        if self.full_param_sync is not None:
+            self.full_param_sync()
         if self.dist_mode == 'rowpart' and self.world > 1 and not (self.p2p and self._e0_synced):
             self._allgather_rows(self.E0)
             self._e0_synced = self.p2p
@@ -747,6 +852,8 @@ class Engine:
 
     def epoch_step(self):
         S, ctl = self._epoch
+        if self.pre_step_hook is not None:
+            self.pre_step_hook()
         self._sync_params_across_ranks()
         self._zc_slot = None
         self._loss_host_valid = False

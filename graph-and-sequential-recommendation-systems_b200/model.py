@@ -273,31 +273,92 @@ class LightGCN(nn.Module):
         return self._fuse_item_embeddings(all_items).contiguous()
 
     # ------------------------------------------------------------------ parameter storage
+    @property
+    def _feat(self):
+        """Feature partition (dist_mode='featpart', > 1 rank): the engine holds d/P COLUMNS of every table; the two embedding
+        tables of the API are views of a full (N,d) table kept by the model, pushed into the engine's slice when they were
+        written from outside and refreshed from the ranks' slices (collective) when they are read after training steps."""
+        eng = self._engine
+        return eng.dist_mode == 'featpart' and eng.world > 1
+
+    def _param_table(self):
+        if not self._feat:
+            return self._engine.E0
+        if getattr(self, '_E0_full', None) is None:
+            self._E0_full = torch.zeros((self.n_users + self.m_items, self.latent_dim), dtype=torch.float32, device=self.device)
+            self._out_full = None
+            self._engine.pre_step_hook = self._feat_push_params
+            self._engine.full_param_sync = self._feat_pull_params
+        return self._E0_full
+
     def _pack_params(self):
-        """Make both embedding tables views of the engine's contiguous E0 buffer."""
+        """Make both embedding tables views of ONE contiguous (N,d) buffer: the engine's E0 (feature partition: the model's
+        full table, whose column slice the engine trains)."""
         eng = self._engine
         nu = self.n_users
+        tab = self._param_table()
         with torch.no_grad():
-            eng.E0[:nu].copy_(self.embedding_user.weight.data)
-            eng.E0[nu:].copy_(self.embedding_item.weight.data)
-        self.embedding_user.weight.data = eng.E0[:nu]
-        self.embedding_item.weight.data = eng.E0[nu:]
+            tab[:nu].copy_(self.embedding_user.weight.data)
+            tab[nu:].copy_(self.embedding_item.weight.data)
+        self.embedding_user.weight.data = tab[:nu]
+        self.embedding_item.weight.data = tab[nu:]
         self._cache_key = None
         self._engine._e0_synced = False
+        if self._feat:
+            self._feat_pushed = None
+            self._feat_push_params()
 
     def _params_packed(self, user_w=None, item_w=None):
-        eng = self._engine
+        tab = self._param_table()
         uw = self.embedding_user.weight if user_w is None else user_w
         iw = self.embedding_item.weight if item_w is None else item_w
-        return (uw.data_ptr() == eng.E0.data_ptr()
-                and iw.data_ptr() == eng.E0.data_ptr() + self.n_users * self.latent_dim * 4)
+        return (uw.data_ptr() == tab.data_ptr()
+                and iw.data_ptr() == tab.data_ptr() + self.n_users * self.latent_dim * 4)
 
     def _sync_params_into_engine(self, user_w, item_w):
         if not self._params_packed(user_w, item_w):
-            eng = self._engine
+            tab = self._param_table()
             with torch.no_grad():
-                eng.E0[:self.n_users].copy_(user_w)
-                eng.E0[self.n_users:].copy_(item_w)
+                tab[:self.n_users].copy_(user_w)
+                tab[self.n_users:].copy_(item_w)
+            if self._feat:
+                self._feat_pushed = None
+        if self._feat:
+            self._feat_push_params()
+
+    def _feat_versions(self):
+        return (self.embedding_user.weight._version, self.embedding_item.weight._version, self.embedding_user.weight.data_ptr())
+
+    def _feat_push_params(self):
+        """Full table -> the engine's column slice, when the parameters were written from outside since the last push
+        (initialisation, load_state_dict, an external optimiser).  Engine.step / epoch_step / forward call it first."""
+        eng = self._engine
+        if not self._params_packed():
+            return self._pack_params()
+        key = self._feat_versions()
+        if getattr(self, '_feat_pushed', None) == key:
+            return
+        with torch.no_grad():
+            eng.E0.copy_(self._E0_full[:, eng.c0:eng.c0 + eng.d])
+        self._feat_pushed = key
+        self._feat_pulled_epoch = eng.param_epoch
+        self._cache_key = None
+
+    def _feat_pull_params(self):
+        """The ranks' trained column slices -> the full table behind embedding_user/embedding_item (collective: every rank)."""
+        eng = self._engine
+        self._feat_push_params()
+        if getattr(self, '_feat_pulled_epoch', None) == eng.param_epoch:
+            return
+        with torch.no_grad():
+            eng.gather_columns(eng.E0, out_full=self._E0_full)
+        self._feat_pulled_epoch = eng.param_epoch
+        self._feat_pushed = self._feat_versions()
+
+    def state_dict(self, *args, **kwargs):
+        if self._feat:
+            self._feat_pull_params()                    # collective under the feature partition: every rank calls state_dict()
+        return super().state_dict(*args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
         # .to(device)/.cuda()/.float() re-create parameter storage; re-pack afterwards
@@ -323,6 +384,9 @@ class LightGCN(nn.Module):
         uw, iw = self.embedding_user.weight, self.embedding_item.weight
         nu = self.n_users
         if torch.is_grad_enabled() and (uw.requires_grad or iw.requires_grad):
+            if self._feat:
+                raise NotImplementedError("dist_mode='featpart' trains through the fused step (utils.BPRLoss.stageOne / "
+                                          "Procedure.BPR_train_original); call computer() under torch.no_grad()")
             out = _Propagate.apply(uw, iw, self)
             self._cache_key = None
             items = out[nu:]
@@ -333,13 +397,15 @@ class LightGCN(nn.Module):
         if self._cache_key != key:
             self._sync_params_into_engine(uw, iw)
             self._engine.forward()
-            self._cache_key = key
+            if self._feat:      # every rank propagated its columns: all-gather them into the full table the scoring reads (collective)
+                self._out_full = self._engine.gather_columns(self._engine.out, out_full=self._out_full)
+            self._cache_key = self._param_key()
             self._items_smoothed = None
             if self._i2i is not None and self.i2i_alpha > 0.0:
                 x = self._engine.out[nu:]
                 self._items_smoothed = torch.empty_like(x)
                 ops.spmm(self._i2i, x, self._items_smoothed, self.i2i_alpha, 1.0, [x])
-        out = self._engine.out
+        out = self._out_full if self._feat else self._engine.out
         items = out[nu:] if getattr(self, '_items_smoothed', None) is None else self._items_smoothed
         return out[:nu], items
 
@@ -399,6 +465,8 @@ class LightGCN(nn.Module):
                 entropy = -(gates * torch.log(gates) + (1 - gates) * torch.log(1 - gates)).mean()
                 bpr = bpr - self.gate_entropy_coeff * entropy
             return bpr, reg
+        if self._feat:
+            raise NotImplementedError("dist_mode='featpart' has no autograd path: train through utils.BPRLoss.stageOne")
         if torch.is_grad_enabled() and (uw.requires_grad or iw.requires_grad):
             out = _Propagate.apply(uw, iw, self)
             self._cache_key = None

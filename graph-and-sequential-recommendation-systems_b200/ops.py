@@ -475,6 +475,44 @@ def bpr_fwd_bwd(out, users, pos, neg, B_cap, ctl, n_users, m_items, inv_norm, de
                                     workspace.numel() * 4, _p(clear_mask), _p(loss_host), _stream()), "bpr_fwd_bwd")
 
 
+class FeatExchange:
+    """Cross-rank state of the feature partition's K2 (include/lgcn_b200.h, lgcn_bpr_feat_*): this rank's record buffer
+    float32[2 * world * B_cap * 8], every rank's buffer as seen from this process, and the device barrier between the two
+    halves.  `peer_records` / `peer_flags`: lists indexed by rank (own entries included) — CUDA-IPC mappings between
+    processes, or plain tensors of one device when several ranks are emulated on one GPU (tests)."""
+
+    def __init__(self, records, peer_records, flags, peer_flags, rank, world, B_cap, scalars, timeout_ms=20000):
+        if records.numel() != 2 * world * B_cap * 8 or records.dtype != torch.float32:
+            raise ValueError("FeatExchange: records must be float32[2 * world * B_cap * 8]")
+        self.records, self.peer_records = records, list(peer_records)
+        self.rank, self.world, self.B_cap = int(rank), int(world), int(B_cap)
+        self.barrier = RankBarrier(flags, peer_flags, rank, world, timeout_ms=timeout_ms)
+        self.feat = _lib.BprFeat()
+        self.feat.n_parts, self.feat.part = self.world, self.rank
+        self.feat.scalars_dev = scalars.data_ptr()
+        self.feat.records_local = records.data_ptr()
+        for q, t in enumerate(self.peer_records):
+            self.feat.records_peer[q] = t.data_ptr()
+        self._keep = scalars
+
+
+def bpr_feat_partial(out, users, pos, neg, B_cap, ctl, n_users, m_items, xchg, workspace):
+    """First half of K2 under the feature partition: this rank's partial dot products into every rank's record buffer."""
+    _need(out, torch.float32, "out", 2)
+    _lib.check(_lib.load().lgcn_bpr_feat_partial(_p(out), _p(users), _p(pos), _p(neg), int(B_cap), _p(ctl), int(n_users), int(m_items), out.shape[1],
+                                                 ctypes.byref(xchg.feat), _p(workspace), workspace.numel() * 4, _stream()), "bpr_feat_partial")
+
+
+def bpr_feat_finish(out, users, pos, neg, B_cap, ctl, n_users, m_items, inv_norm, decay, c_bpr, c_reg, loss_out, G, xchg, workspace,
+                    deterministic=False, clear_mask=None, loss_host=None):
+    """Second half (after the barrier): K2 on the column slice with the dot products taken from the summed records."""
+    _need(out, torch.float32, "out", 2)
+    _lib.check(_lib.load().lgcn_bpr_feat_finish(_p(out), _p(users), _p(pos), _p(neg), int(B_cap), _p(ctl), int(n_users), int(m_items), out.shape[1],
+                                                float(inv_norm), float(decay), float(c_bpr), float(c_reg), _p(loss_out), _p(G),
+                                                int(bool(deterministic)), ctypes.byref(xchg.feat), _p(workspace), workspace.numel() * 4,
+                                                _p(clear_mask), _p(loss_host), _stream()), "bpr_feat_finish")
+
+
 def popgate_param_count(d, pop_hidden, gate_hidden):
     return int(_lib.load().lgcn_popgate_param_count(int(d), int(pop_hidden), int(gate_hidden)))
 

@@ -8,6 +8,8 @@ every 10th epoch Test + best-NDCG checkpoint, then one BPR epoch, CSV rows, atom
 Under torchrun (WORLD_SIZE > 1) the adjacency is row-partitioned over the ranks (dist_mode='rowpart'): every rank runs the
 same loop on the same sampled triples (same seeds), holds only its block of the CSR and of the Adam moments, evaluates its
 shard of the test users, and rank 0 alone prints and writes checkpoints (the optimizer state is gathered for that).
+`--dist_mode featpart` splits the embedding COLUMNS instead (CSR replicated, no exchange in the propagation): the mode for
+graphs that fit one GPU, where a row-partitioned layer is bound by the NVLink ingest of the exchanged table.
 
 Checkpoint schema = the reference's (code/main.py:56-67): {'epoch','model_state','optimizer_state','best_metric'} with
 parameter keys embedding_user.weight / embedding_item.weight, so files are interchangeable.
@@ -71,6 +73,9 @@ def main(argv=None):
     ap.add_argument('--device_sampler', action='store_true')
     ap.add_argument('--resume', default=None)
     ap.add_argument('--eval_every', type=int, default=10)
+    ap.add_argument('--dist_mode', default='rowpart', choices=['rowpart', 'featpart'],
+                    help="under torchrun: 'rowpart' = rows of the adjacency over the ranks (graphs of any size), 'featpart' = embedding "
+                         "columns over the ranks, CSR replicated, no exchange in the propagation (graphs that fit one GPU)")
     known, rest = ap.parse_known_args(argv)
     a = world.from_args(rest)
     world.configure(device_sampler=known.device_sampler)
@@ -81,7 +86,7 @@ def main(argv=None):
         torch.cuda.set_device(local)
         if not dist.is_initialized():
             dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-        world.configure(device=f'cuda:{local}', dist_mode='rowpart')
+        world.configure(device=f'cuda:{local}', dist_mode=known.dist_mode)
     cfg = world.config
     if known.synthetic:
         ds = synth.make_dataset(known.synthetic, seed=world.seed, config=cfg)

@@ -29,7 +29,7 @@ class _AdamStateView(optim.Adam):
         eng, nu = m._engine, m.n_users
         # single GPU / replicas: the state tensors ALIAS the engine's buffers.  Row partition: a rank holds only its rows of
         # M and V, so the aliases are replaced by gathered full tables whenever a state_dict is asked for.
-        sharded = eng.dist_mode == 'rowpart' and eng.world > 1
+        sharded = eng.dist_mode in ('rowpart', 'featpart') and eng.world > 1
         M, V = full if full is not None else ((None, None) if sharded else (eng.M, eng.V))
         for p, sl in ((m.embedding_user.weight, slice(0, nu)), (m.embedding_item.weight, slice(nu, None))):
             st = self.state[p]
@@ -48,7 +48,7 @@ class _AdamStateView(optim.Adam):
 
     def state_dict(self):
         eng = self._model._engine
-        if eng.dist_mode == 'rowpart' and eng.world > 1:
+        if eng.dist_mode in ('rowpart', 'featpart') and eng.world > 1:
             self._bind(full=eng.adam_state_full())          # collective: every rank must call state_dict()
         for st in self.state.values():
             st['step'] = torch.tensor(float(eng._host_step))

@@ -273,6 +273,33 @@ int lgcn_bpr_fwd_bwd(const float* out, const int64_t* users, const int64_t* pos,
                                              can skip its memset */,
                      float* loss_host_mapped /* optional: mapped pinned host float[4], receives a copy of loss_out (no D2H memcpy) */,
                      lgcn_stream_t stream);
+/* Feature partition (dist_mode='featpart', SURVEY.md §8e for graphs that FIT one GPU): the d embedding columns are split
+ * over the P ranks of one NVSwitch box, every rank holds the (N, d/P) column slice of every table and the whole CSR.  The
+ * propagation then needs NO exchange at all (a CSR SpMM is independent per column) — the only cross-rank dependence of a
+ * training step is the five dot products per triple, 40 KB per rank per step:
+ *   lgcn_bpr_feat_partial  this rank's share of <u,p>, <u,n>, |u|^2, |p|^2, |n|^2 for every triple, stored into record
+ *                          slot `part` of EVERY rank (records_peer[q] = rank q's record buffer mapped into this process)
+ *   lgcn_rank_barrier
+ *   lgcn_bpr_feat_finish   lgcn_bpr_fwd_bwd on the slice with the dot products replaced by the sum of the P records in rank
+ *                          order (every rank computes the same loss bits); gradient rows of this rank's columns only
+ * Record buffer: float32[2 * n_parts * B_cap * 8] per rank (16-byte aligned), double-buffered by the parity of
+ * scalars_dev->step (the device-resident Adam step counter), so one barrier per step orders both the read-after-write and
+ * the write-after-read hazard.  No counterpart in the reference (code/model.py:162-173 runs on one device). */
+typedef struct {
+    int32_t n_parts, part;
+    const lgcn_adam_scalars_t* scalars_dev;
+    float* records_local;
+    float* records_peer[LGCN_MAX_PEERS + 1];     /* indexed by rank, own entry included; only the partial call stores to them */
+} lgcn_bpr_feat_t;
+int lgcn_bpr_feat_partial(const float* out_slice, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                          int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items, int32_t d_local,
+                          const lgcn_bpr_feat_t* feat_host, void* workspace, size_t workspace_bytes, lgcn_stream_t stream);
+int lgcn_bpr_feat_finish(const float* out_slice, const int64_t* users, const int64_t* pos, const int64_t* neg,
+                         int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t m_items,
+                         int32_t d_local, float inv_norm, float decay, float c_bpr, float c_reg,
+                         float* loss_out, float* G_slice, int32_t deterministic, const lgcn_bpr_feat_t* feat_host,
+                         void* workspace, size_t workspace_bytes,
+                         uint32_t* clear_mask, float* loss_host_mapped, lgcn_stream_t stream);
 /* zero the rows of G a batch touched (cheaper than a full memset when B << N) */
 int lgcn_bpr_clear_rows(float* G, const int64_t* users, const int64_t* pos, const int64_t* neg,
                         int32_t B_cap, const int32_t* batch_ctl_dev, int32_t n_users, int32_t d,

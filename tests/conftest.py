@@ -4,6 +4,9 @@ import sys
 import numpy as np
 import pytest
 
+# several CUDA streams that wait for each other on the device (ranks emulated on one GPU) must not share a hardware queue
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

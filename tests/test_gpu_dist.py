@@ -171,6 +171,108 @@ def test_procedures_under_the_row_partition(tmp_path):
     assert all(r[1] and r[2] for r in res), res
 
 
+def _feat_worker(rank, world, port, q, mode):
+    """dist_mode='featpart' through the reference-facing API: stageOne (host or device batches, captured graph or eager),
+    computer(), state_dict() and the optimizer state, against the real reference's golden."""
+    dist, lg = _init(rank, world, port)
+    try:
+        g = load_golden('tiny')
+        cfg, ds, m = _tiny_model(lg, g, dist_mode='featpart', deterministic=(mode == 'deterministic'), cuda_graph=(mode != 'eager'))
+        eng = m._engine
+        d = int(g['d'])
+        assert eng.d == d // world and eng.E0.shape == (eng.N, d // world) and eng.M.shape == (eng.N, d // world)
+        assert eng.use_graph == (mode != 'eager') and eng.csr.nnz == 2 * np.unique(g['train_user'] * int(g['m_items']) + g['train_item']).size
+        bpr = lg.utils.BPRLoss(m, cfg)
+        B = len(g['users'])
+        ok = True
+        losses = []
+        for s in range(3):
+            sh = (s * 17) % B
+            u, p, n = (torch.from_numpy(np.roll(g[k], sh)).long() for k in ('users', 'pos', 'neg'))
+            if mode != 'host_batch':
+                u, p, n = u.cuda(), p.cuda(), n.cuda()
+            losses.append(bpr.stageOne(u, p, n))
+            sd = m.state_dict()                                  # collective: gathers the trained column slices
+            P = torch.cat([sd['embedding_user.weight'], sd['embedding_item.weight']]).cpu().numpy()
+            ok = ok and rel_err(P, g['params_after'][s]) < 1e-4
+        ok = ok and all(abs(a - b) < 1e-5 * abs(b) for a, b in zip(losses, g['step_losses']))
+        with torch.no_grad():
+            out = torch.cat(m.computer()).cpu().numpy()
+        ok = ok and rel_err(out, g['out_after']) < 1e-4
+        osd = bpr.opt.state_dict()
+        m_cat = np.concatenate([osd['state'][0]['exp_avg'].cpu().numpy(), osd['state'][1]['exp_avg'].cpu().numpy()])
+        v_cat = np.concatenate([osd['state'][0]['exp_avg_sq'].cpu().numpy(), osd['state'][1]['exp_avg_sq'].cpu().numpy()])
+        ok = ok and rel_err(m_cat, g['exp_avg']) < 1e-4 and rel_err(v_cat, g['exp_avg_sq']) < 1e-4 and float(osd['state'][0]['step']) == 3.0
+        # parameters written from outside reach the slices: load the step-1 state into a fresh model, one more step -> step 2
+        cfg2, _, m2 = _tiny_model(lg, g, dist_mode='featpart', deterministic=(mode == 'deterministic'), cuda_graph=False)
+        bpr2 = lg.utils.BPRLoss(m2, cfg2)
+        u, p, n = (torch.from_numpy(g[k]).long().cuda() for k in ('users', 'pos', 'neg'))
+        bpr2.stageOne(u, p, n)
+        msd, osd2 = m2.state_dict(), bpr2.opt.state_dict()
+        cfg3, _, m3 = _tiny_model(lg, g, dist_mode='featpart', deterministic=(mode == 'deterministic'), cuda_graph=False)
+        bpr3 = lg.utils.BPRLoss(m3, cfg3)
+        m3.load_state_dict(msd); bpr3.opt.load_state_dict(osd2)
+        sh = 17 % B
+        l2 = bpr3.stageOne(*(torch.from_numpy(np.roll(g[k], sh)).long().cuda() for k in ('users', 'pos', 'neg')))
+        sd3 = m3.state_dict()
+        P3 = torch.cat([sd3['embedding_user.weight'], sd3['embedding_item.weight']]).cpu().numpy()
+        resumed = rel_err(P3, g['params_after'][1]) < 1e-4 and abs(l2 - g['step_losses'][1]) < 1e-5 * abs(g['step_losses'][1])
+        # every rank computes the same loss bits (same records, same order)
+        chk = torch.tensor(losses, device='cuda', dtype=torch.float64)
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        same = all(torch.equal(x, lst[0]) for x in lst)
+        eng._barrier.check()
+        q.put((rank, bool(ok), bool(same), bool(resumed), mode))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager", "deterministic", "host_batch"])
+@pytest.mark.timeout(600)
+def test_feature_partition_matches_reference(mode):
+    res = _spawn(_feat_worker, NRANKS, mode)
+    assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def _feat_procedure_worker(rank, world, port, q, tmp):
+    dist, lg = _init(rank, world, port)
+    try:
+        g, t = load_golden('tiny_epochs'), load_golden('tiny')
+        lg.world.configure(checkpoint_dir=os.path.join(tmp, f'r{rank}'), bpr_batch_size=int(g['batch']), topks=[20])
+
+        def run(dist_mode):
+            cfg = dict(lg.world.config)
+            cfg.update(latent_dim_rec=int(g['d']), lightGCN_n_layers=int(g['L']), decay=float(g['decay']), lr=float(g['lr']),
+                       deterministic=True, dist_mode=dist_mode)
+            ds = lg.InteractionDataset(int(t['n_users']), int(t['m_items']), t['train_user'], t['train_item'],
+                                       t['test_user'], t['test_item'], config=cfg)
+            lg.utils.set_seed(2020); lg.utils.sampler_seed(2020)
+            m = lg.LightGCN(cfg, ds)
+            bpr = lg.utils.BPRLoss(m, cfg)
+            infos = [lg.Procedure.BPR_train_original(ds, m, bpr, e) for e in range(1, int(g['epochs']) + 1)]
+            res = lg.Procedure.Test(ds, m, int(g['epochs']))
+            sd = m.state_dict()
+            return torch.cat([sd['embedding_user.weight'], sd['embedding_item.weight']]).cpu().numpy(), infos, res
+        P, infos, res = run('featpart')
+        P1, infos1, res1 = run(None)                            # the same procedures on this GPU alone
+        close_to_single = (rel_err(P, P1) < 1e-4 and all(abs(float(res[k][0]) - float(res1[k][0])) <= 1e-4 for k in res)
+                           and [s.split('-')[0] for s in infos] == [s.split('-')[0] for s in infos1])
+        vs_ref = (abs(float(res['recall'][0]) - float(g['recall'][0])) <= 1e-4 and abs(float(res['ndcg'][0]) - float(g['ndcg'][0])) <= 1e-4
+                  and rel_err(P, g['params']) < 1e-3)
+        q.put((rank, bool(close_to_single), bool(vs_ref), float(res['recall'][0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_procedures_under_the_feature_partition(tmp_path):
+    """BPR_train_original x 20 epochs + Test under dist_mode='featpart': the reference's fixed-epoch golden to 1e-4, the
+    single-GPU run to rounding (the dot products are summed in a different order, nothing else changes)."""
+    res = _spawn(_feat_procedure_worker, NRANKS, str(tmp_path))
+    assert all(r[1] and r[2] for r in res) and len({r[3] for r in res}) == 1, res
+
+
 def _barrier_worker(rank, world, port, q):
     dist, lg = _init(rank, world, port)
     try:

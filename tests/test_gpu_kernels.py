@@ -234,7 +234,7 @@ def test_coo_to_csr(lg, orc):
 
 
 # ------------------------------------------------------------------------------------ K1
-@pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("d", [8, 16, 32, 64, 128, 256])
 @pytest.mark.parametrize("seg_len", [128, 8, 2])
 def test_spmm_vs_oracle(lg, orc, d, seg_len):
     rng = np.random.default_rng(d + seg_len)
@@ -404,9 +404,10 @@ def test_adam_matches_torch_and_oracle(lg, orc):
     assert rel_err(M.cpu().numpy(), m64) < TOL and rel_err(V.cpu().numpy(), v64) < TOL
 
 
-def test_spmm_adam_epilogue_equals_spmm_then_adam(lg):
+@pytest.mark.parametrize("d", [8, 16, 32, 64])
+def test_spmm_adam_epilogue_equals_spmm_then_adam(lg, d):
     rng = np.random.default_rng(2)
-    nu, ni, d = 300, 200, 64
+    nu, ni = 300, 200
     tu, ti = random_edges(rng, nu, ni, 4000)
     g = build(lg, tu, ti, nu, ni, seg_len=16)
     N = nu + ni
@@ -432,7 +433,7 @@ def _bpr_case(rng, nu, ni, d, B):
     return out, users.astype(np.int64), pos.astype(np.int64), neg.astype(np.int64)
 
 
-@pytest.mark.parametrize("d", [16, 64, 256])
+@pytest.mark.parametrize("d", [8, 16, 64, 256])
 @pytest.mark.parametrize("B", [1, 37, 2048])
 @pytest.mark.parametrize("deterministic", [False, True])
 def test_bpr_vs_oracle(lg, orc, d, B, deterministic):

@@ -428,3 +428,51 @@ def test_gowalla_one_epoch_matches_the_reference_procedure(lg, gowalla, tmp_path
             assert abs(float(res[k][0]) - float(g[k][0])) <= 1e-4, (k, res[k], g[k])
     finally:
         lg.world.configure(checkpoint_dir='./checkpoints', bpr_batch_size=2048)
+
+
+@pytest.mark.parametrize("deterministic", [False, True])
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_feature_partition_emulated_ranks_match_reference(lg, golden, P, deterministic):
+    """dist_mode='featpart' with P ranks emulated on ONE GPU (an engine and a CUDA stream per rank; the record exchange, the
+    device barrier and the double-buffered records are the multi-process ones): column slices of width 32 / 16 / 8 trained
+    for 3 steps reproduce the reference's losses and parameters (code/utils.py:53-64), every rank sees the same loss bits."""
+    from lgcn_b200.engine import Engine, link_feat_engines
+    g = golden
+    nu, ni, d, L = int(g['n_users']), int(g['m_items']), int(g['d']), int(g['L'])
+    if d // P < 8:
+        pytest.skip("slices narrower than 8 columns are not supported")
+    csr = lg.ops.csr_build(torch.from_numpy(g['train_user']).cuda(), torch.from_numpy(g['train_item']).cuda(), nu, ni)
+    E0 = torch.from_numpy(g['E0']).cuda()
+    B = len(g['users'])
+    batches = [tuple(t.cuda() for t in triples(g, (s * 17) % B)) for s in range(3)]
+    streams = [torch.cuda.Stream() for _ in range(P)]
+    engines = []
+    for p in range(P):
+        with torch.cuda.stream(streams[p]):
+            e = Engine(csr.rows(0, csr.n_rows), nu, ni, d, L, torch.device('cuda'), lr=float(g['lr']), decay=float(g['decay']), B_cap=B,
+                       deterministic=deterministic, use_graph=False, dist_mode='featpart', feat=(p, P))
+            assert e.d == d // P and e.E0.shape == (nu + ni, d // P)
+            e.E0.copy_(E0[:, e.c0:e.c0 + e.d])
+        engines.append(e)
+    torch.cuda.synchronize()
+    link_feat_engines(engines, timeout_ms=3000)
+    for s in range(3):
+        for p in range(P):                       # nothing in step() waits on the host, so the P ranks' steps overlap on the device
+            with torch.cuda.stream(streams[p]):
+                engines[p].step(*batches[s])
+        torch.cuda.synchronize()
+        for e in engines:
+            e.xchg.barrier.check()
+        losses = [e.loss_out.cpu().numpy() for e in engines]
+        assert all(np.array_equal(x, losses[0]) for x in losses)
+        assert abs(float(losses[0][2]) - g['step_losses'][s]) < TOL * abs(g['step_losses'][s])
+        P_all = torch.cat([e.E0 for e in engines], dim=1).cpu().numpy()
+        assert rel_err(P_all, g['params_after'][s]) < 1e-4
+    M_all = torch.cat([e.M for e in engines], dim=1).cpu().numpy()
+    V_all = torch.cat([e.V for e in engines], dim=1).cpu().numpy()
+    assert rel_err(M_all, g['exp_avg']) < 1e-4 and rel_err(V_all, g['exp_avg_sq']) < 1e-4
+    for p in range(P):
+        with torch.cuda.stream(streams[p]):
+            engines[p].forward()
+    torch.cuda.synchronize()
+    assert rel_err(torch.cat([e.out for e in engines], dim=1).cpu().numpy(), g['out_after']) < 1e-4
