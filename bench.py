@@ -9,14 +9,19 @@ graph (29,858 x 40,981, ~810 k train edges — the real file is reference data a
 triples from the reference's sampler stream (C sampler seeded 2020, numpy shuffle seeded 2020).
 
 N = 1            one GPU, the whole graph.
-N > 1 (torchrun) the SAME step on the SAME workload with the adjacency ROW-PARTITIONED over the N GPUs (north_star):
-                 strong scaling — each rank holds only its CSR block and its rows of the Adam moments, K1's epilogue
-                 stores every finished row into all replicas over NVLink (multimem.st), layers are ordered by a
-                 device-side flag barrier, the whole step is one CUDA graph per rank, no collective launch on the path.
-                 `value` stays B / step time: what N GPUs buy is a shorter step, not more samples per step.  On the
-                 three small shapes the step is latency-bound (SURVEY.md §7 predicts communication-bound); the config
-                 the partition exists for is BASELINE config 5 -> `large_graph` (one-GPU step timed on rank 0 first).
-                 `--parallel dp_idx` (replicas, NOT a scaling measurement) is kept as a labelled side mode.
+N > 1 (torchrun) the SAME step on the SAME workload split over the N GPUs — strong scaling: `value` stays B / step time, what
+                 N GPUs buy is a shorter step, not more samples per step.  Two decompositions:
+                 * `large_graph` (BASELINE config 5, and anything beyond one GPU): the adjacency ROW-PARTITIONED (north_star) —
+                   each rank holds only its CSR block and its rows of the Adam moments, K1's epilogue stores every finished row
+                   into all replicas over NVLink (multimem.st), layers are ordered by a device-side flag barrier, one CUDA graph
+                   per rank, no collective launch on the path; the one-GPU step is timed on rank 0 first.
+                 * the headline and amazon-book-shape (graphs that fit one GPU; `--parallel auto`): the FEATURE partition — every
+                   rank holds d/N embedding columns of every table and the whole CSR; a CSR SpMM is independent per column, so
+                   the propagation exchanges NOTHING and the only cross-rank traffic of a step is K2's five dot products per
+                   triple (40 KB, peer stores) around ONE device barrier.  The row partition of the same step is reported
+                   beside it (`extra.headline_under_row_partition`): there every rank must ingest (N-1)/N of the table per
+                   layer over NVLink, which makes a layer slower than the whole graph on one GPU.
+                 `--parallel rowpart|featpart` force one; `--parallel dp_idx` (replicas, NOT a scaling measurement) is a side mode.
 
 value    : samples/s, epoch's triples resident in HBM; R repeats of a K-step loop, every step bracketed by CUDA events
            on the launching stream, L2 flushed before every step, max over ranks per repeat, MEDIAN over repeats.
@@ -494,8 +499,9 @@ def shape_record_partitioned(lg, tm, name, cfg, K, R, dist, world):
             "eval_ms": float(t[1].item()), "rows_per_rank": eng.r1 - eng.r0, "adjacency_nnz": csr_nnz, "mem_gb_max_over_ranks": float(t[2].item()),
             "how": "step: median over repeats of the K-step loop, CUDA events, L2 flushed, max over ranks; epoch/eval: wall clock around "
                    "Procedure.BPR_train_original / Procedure.Test, best of 2, max over ranks",
-            "note": "an L2-resident graph: the exchanged layer is latency/NVLink-ingest bound (DESIGN.md §5), so the partition does not "
-                    "shorten this step; the one-GPU numbers are in the N=1 line's extra.amazon_book"}
+            "note": ("feature partition: d/N columns per rank, no exchange in the propagation; " if eng.dist_mode == 'featpart' else
+                     "row partition of an L2-resident graph: the exchanged layer is latency/NVLink-ingest bound (DESIGN.md §5); ")
+                    + "the one-GPU numbers are in the N=1 line's extra.amazon_book"}
 
 
 def sweep_record(lg, tm, graph, peak):
@@ -699,6 +705,10 @@ def run_ours(args):
     cfg = dict(lg.world.config)
     cfg.update(lightGCN_n_layers=L_LAYERS, latent_dim_rec=D, bpr_batch_size=B)
     mode = args.parallel if world > 1 else None
+    if mode == 'auto':
+        # graphs that fit one GPU (every --workload here): the feature partition — embedding columns over the ranks, no exchange in
+        # the propagation; the row partition is what the large_graph record (and anything beyond one GPU's memory) runs
+        mode = 'featpart' if (D % world == 0 and D // world in (8, 16, 32)) else 'rowpart'
     cfg.update(dist_mode=mode)
     peak, tc_peak, peak_src = peaks()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda").view(torch.int64)
@@ -762,7 +772,11 @@ def run_ours(args):
     # + 2L x K1 + [2L x rank_barrier: fused exchange]
     # step_begin (Adam tick + window advance | host-batch pull) + [batch_masks] + K2 + 2L x K1 + [2L x rank_barrier]
     # + [clear_rows: only when the Adam-epilogue K1 cannot zero G itself, i.e. under the row partition]
-    launches_per_step = 1 + (1 if eng.prune else 0) + 1 + n_k1 + (n_k1 if eng._barrier is not None else 0) + (1 if mode == 'rowpart' else 0)
+    # feature partition: K2 is two kernels around ONE rank_barrier, nothing else is exchanged
+    if mode == 'featpart':
+        launches_per_step = 1 + (1 if eng.prune else 0) + 3 + n_k1
+    else:
+        launches_per_step = 1 + (1 if eng.prune else 0) + 1 + n_k1 + (n_k1 if eng._barrier is not None else 0) + (1 if mode == 'rowpart' else 0)
     launches_per_step_e2e = launches_per_step
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True,
@@ -772,7 +786,7 @@ def run_ours(args):
                       "l2": "flushed before every timed step (512 MiB read outside the event brackets)",
                       "repeats": R, "statistic": "median over repeats of the K-step loop (each: sum of per-step CUDA-event times, max over ranks)",
                       "ms_per_step_all_repeats": [round(m / K, 5) for m in all_ms],
-                      "rows_per_rank": (eng.r1 - eng.r0), "partition_memory": bool(eng._mv_local),
+                      "rows_per_rank": (eng.r1 - eng.r0), "columns_per_rank": eng.d, "partition_memory": bool(eng._mv_local) or mode == 'featpart',
                       "device_barrier": eng._barrier is not None, "multicast": bool(eng._mc),
                       "model_and_graph_setup_s": t_setup},
             "e2e": {"value": samples_per_step * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 16 + 3 * B * 8, "d2h_bytes_per_step": 16,
@@ -839,12 +853,28 @@ def run_ours(args):
             guarded("sweep_amazon_book", lambda: sweep_record(lg, tm, ab.get("graph") or workload_graph("amazon-book"), peak), extra)
             line["extra"] = extra
             torch.cuda.empty_cache()
-    if world > 1 and mode == 'rowpart' and not args.no_extra:
+    if world > 1 and mode in ('rowpart', 'featpart') and not args.no_extra:
         # BASELINE config 3: amazon-book-shape at N GPUs, through the same partition (collective section, same code path as the headline)
         del model, bpr, eng, ds
         torch.cuda.empty_cache()
         extra = {}
         guarded("amazon_book", lambda: shape_record_partitioned(lg, tm, "amazon-book", cfg, K, 5, dist, world), extra)
+        if mode == 'featpart':
+            # the same headline step under the ROW partition (north_star's decomposition), for comparison: on graphs whose table
+            # is L2-resident every rank must ingest (N-1)/N of the table per layer over NVLink, which bounds it
+            def _rowpart():
+                c2 = dict(cfg); c2.update(dist_mode='rowpart')
+                _, ds2, model2, _, S2 = setup_workload(lg, args.workload, c2, graph)
+                e2 = model2._engine
+                st2 = resident_step_fn(e2, S2)
+                for i in range(5):
+                    st2(i)
+                ms2, _, _ = tm.repeats(st2, K, 5)
+                if e2._barrier is not None:
+                    e2._barrier.check()
+                return {"parallelism": "rowpart", "ms_per_step": ms2 / K, "samples_per_s": B * K / (ms2 * 1e-3), "rows_per_rank": e2.r1 - e2.r0,
+                        "multicast": bool(e2._mc), "device_barrier": e2._barrier is not None}
+            guarded("headline_under_row_partition", _rowpart, extra)
         line["extra"] = extra
         torch.cuda.empty_cache()
     if not args.no_large_graph and not replicated:
@@ -869,7 +899,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gowalla", choices=["gowalla", "yelp2018", "amazon-book", "tiny"])
-    ap.add_argument("--parallel", default="rowpart", choices=["rowpart", "dp_idx", "dp"])
+    ap.add_argument("--parallel", default="auto", choices=["auto", "featpart", "rowpart", "dp_idx", "dp"],
+                    help="N > 1: auto = featpart (embedding columns over the ranks) for the workloads here, which fit one GPU; rowpart = rows of "
+                         "the adjacency over the ranks (always used for large_graph); dp/dp_idx = replicas (not a scaling measurement)")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline and gpu_library_baseline")
     ap.add_argument("--no-extra", action="store_true", help="skip the yelp2018 / amazon-book / sweep records")
     ap.add_argument("--no-large-graph", action="store_true", help="skip the BASELINE config-5 record")

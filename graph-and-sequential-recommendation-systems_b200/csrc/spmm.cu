@@ -712,7 +712,12 @@ static int dispatch_spmm(int d, const SpmmArgs& a, cudaStream_t st) {
     switch (d) {
         case 8:   return launch_cfg<8, 2, 2, ADAM, 128, 8>(a, st);       // feature partition over 8 ranks: 32-byte rows
         case 16:  return launch_cfg<16, 4, 4, ADAM, 128, 8>(a, st);
-        case 32:  return launch_cfg<32, 4, 4, ADAM, 128, 8>(a, st);
+        case 32:
+            // 8 lanes x one float4: a 128-byte row is ONE request (4 lanes x 2 float4 made it two): 18.9 / 43.1 us per layer inside a
+            // captured graph on the gowalla / amazon-book shape against 29.8 / 54.3 (profiles/r2_feat_probe_k1_d32_lane_configs.jsonl)
+            if (!ADAM && g_variant == 51) return launch_cfg<32, 8, 4, false, 128, 8>(a, st);
+            if (!ADAM && g_variant == 54) return launch_cfg<32, 4, 4, false, 128, 8>(a, st);
+            return launch_cfg<32, 8, 8, ADAM, 128, 8>(a, st);
         case 64:
             if (!ADAM) switch (g_variant) {                       // tuning variants, same results
                 case 1:  return launch_cfg<64, 16, 8, false, 128, 8>(a, st);

@@ -427,11 +427,11 @@ class Engine:
             return local
         import torch.distributed as dist
         n = local.shape[0]
-        parts = torch.empty((self.world, n, self.d), dtype=local.dtype, device=local.device)
+        parts = torch.empty((self.world * n, self.d), dtype=local.dtype, device=local.device)     # rank blocks stacked along dim 0 (NCCL and gloo)
         dist.all_gather_into_tensor(parts, local.contiguous(), group=self.group)
         if out_full is None:
             out_full = torch.empty((n, self.d_full), dtype=local.dtype, device=local.device)
-        out_full.view(n, self.world, self.d).copy_(parts.permute(1, 0, 2))
+        out_full.view(n, self.world, self.d).copy_(parts.view(self.world, n, self.d).permute(1, 0, 2))
         return out_full
 
     def _stage_batch(self, users, pos, neg, B_global=0):

@@ -169,3 +169,76 @@ def test_procedure_sharding_host_logic_world2():
         assert p.exitcode == 0
     res = sorted(q.get(timeout=10) for _ in range(2))
     assert res == [(0, True, True), (1, True, True)]
+
+
+class _FeatStub:
+    """The attributes Engine.gather_columns reads (dist_mode='featpart' on `world` ranks, slices of d columns)."""
+    def __init__(self, rank, world, d_full):
+        self.dist_mode, self.rank, self.world, self.group = 'featpart', rank, world, None
+        self.d_full, self.d, self.c0 = d_full, d_full // world, rank * (d_full // world)
+
+
+def _feat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import lgcn_b200 as lg
+        from oracle import lightgcn_oracle as orc
+        g = lg.synth.make_graph('tiny', seed=1)
+        nu, ni = g['n_users'], g['m_items']
+        indptr, indices, vals, _, _ = orc.build_norm_adj(g['train_user'], g['train_item'], nu, ni)
+        N, d, L = nu + ni, 16, 3
+        rng = np.random.default_rng(0)
+        E0 = rng.normal(0, 0.1, (N, d))
+        st = _FeatStub(rank, world, d)
+        c0, c1 = st.c0, st.c0 + st.d
+        # (1) the propagation of a column slice needs nothing from the other ranks and equals the slice of the full propagation
+        x = E0[:, c0:c1].copy(); acc = x.copy()
+        for _ in range(L):
+            x = orc.spmm(indptr, indices, vals, x); acc += x
+        out_slice = acc / (L + 1)
+        full = E0.copy(); acc_full = full.copy()
+        for _ in range(L):
+            full = orc.spmm(indptr, indices, vals, full); acc_full += full
+        out_full = acc_full / (L + 1)
+        ok_prop = np.array_equal(out_slice, out_full[:, c0:c1])
+        # (2) Engine.gather_columns: every rank ends with the full table, columns in rank order
+        got = lg.engine.Engine.gather_columns(st, torch.from_numpy(out_slice))
+        ok_gather = got.shape == (N, d) and np.array_equal(got.numpy(), out_full)
+        # (3) K2 split: the dot products are sums of the ranks' partial dot products; given the sums, the gradient rows of a
+        #     slice are the slice of the full gradient
+        users = rng.integers(0, nu, 64); pos = rng.integers(0, ni, 64); neg = rng.integers(0, ni, 64)
+        U, P, Nn = out_slice[users], out_slice[nu + pos], out_slice[nu + neg]
+        part = torch.from_numpy(np.stack([(U * P).sum(1), (U * Nn).sum(1), (U * U).sum(1), (P * P).sum(1), (Nn * Nn).sum(1)]))
+        dist.all_reduce(part)
+        pu, nuu, uu, pp, nn = part.numpy()
+        z = pu - nuu
+        bpr = float(np.mean(np.logaddexp(0.0, -z))); reg = float(0.5 * (uu + pp + nn).sum() / 64)
+        bpr_ref, reg_ref, Gb, Gr = orc.bpr_loss(out_full, users, pos, neg, nu)
+        ok_loss = abs(bpr - bpr_ref) < 1e-12 and abs(reg - reg_ref) < 1e-12
+        sg = 1.0 / (1.0 + np.exp(z))                                  # sigmoid(-z)
+        G = np.zeros((N, st.d))
+        np.add.at(G, users, (sg[:, None] * (Nn - P) + 1e-4 * U) / 64)
+        np.add.at(G, nu + pos, (-sg[:, None] * U + 1e-4 * P) / 64)
+        np.add.at(G, nu + neg, (sg[:, None] * U + 1e-4 * Nn) / 64)
+        ok_grad = np.allclose(G, (Gb + 1e-4 * Gr)[:, c0:c1], rtol=1e-10, atol=1e-15)
+        q.put((rank, bool(ok_prop), bool(ok_gather), bool(ok_loss), bool(ok_grad)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_feature_partition_host_logic_world2():
+    """dist_mode='featpart' over gloo, no GPU: a column slice propagates on its own, Engine.gather_columns reassembles the table,
+    and the BPR loss/gradient follow from the all-reduced partial dot products (the algebra csrc/bpr.cu's split K2 relies on)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_feat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert res == [(0, True, True, True, True), (1, True, True, True, True)], res
