@@ -372,8 +372,9 @@ spmm_kernel(const __grid_constant__ SpmmArgs a) {
 // shuffles), each lane gathers the whole row of its entry with 256-bit loads (one request per 32 bytes: LDG.E.256) and keeps a
 // full-width partial sum; the group's partial sums meet in a fixed xor tree at the end.  Deterministic, but the summation
 // order differs from spmm_kernel's (entry j goes to lane j mod GL), so the two agree to rounding, not bit for bit.
-// What bounds it: one L2 request per non-zero — ~2 SM cycles per non-zero on both shapes, whatever the row width; wider slices
-// (d = 16, 32) are served by spmm_kernel, whose cooperating lanes fetch a 64/128-byte row with one request.
+// What bounds it (ncu, profiles/r2_k1_slice_widths_ncu_raw.csv): per-NON-ZERO costs, not bytes — the L1 data pipe is 65-74 % busy at every
+// width (a wavefront per gathered row + the (col,val) stream), ~2 SM cycles per non-zero; wider slices (d = 16, 32) are served by
+// spmm_kernel, whose cooperating lanes fetch a 64/128-byte row with one request.
 __device__ __forceinline__ void ld_row256(const float4* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
