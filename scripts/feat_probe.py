@@ -27,7 +27,7 @@ def med_us(fn, reps=11, flush=True, per=1):
     return statistics.median(ts)
 
 
-VARIANTS = {64: [0], 32: [0, 51, 52, 53], 16: [0], 8: [50, 0]}
+VARIANTS = {64: [0], 32: [0, 51, 54], 16: [0], 8: [50, 0]}      # 0 = shipped; 51/54: d = 32 with 8 lanes x 4 in flight / the 4-lane layout; 50: row-per-group kernel at d = 8
 for name in sys.argv[1:] or ["gowalla", "amazon-book"]:
     gr = lg.synth.make_graph(name, seed=2020)
     nu, ni = gr['n_users'], gr['m_items']
