@@ -121,3 +121,9 @@ def main(argv=None):
 
 if __name__ == '__main__':
     main(sys.argv[1:])
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch.distributed as _dist
+        if _dist.is_initialized():
+            torch.cuda.synchronize()
+            _dist.barrier()
+            _dist.destroy_process_group()
