@@ -58,6 +58,40 @@ def test_ctypes_signatures_match_the_header_arity_and_kinds():
                     assert want64 == (ctypes.sizeof(at) == 8), f"{name} arg {i}: '{decl}' vs {at}"
 
 
+def test_ctypes_structs_have_the_headers_layout(tmp_path):
+    """The structs that cross the C ABI by pointer (plan, peers, Adam scalars, feature-partition exchange): sizeof and every
+    offsetof of the ctypes mirrors in _lib.py equal what a C compiler makes of include/lgcn_b200.h."""
+    import ctypes
+    import shutil
+    import subprocess
+    import lgcn_b200  # noqa: F401  (registers the package under its importable name)
+    from lgcn_b200 import _lib
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if cc is None:
+        pytest.skip("no C compiler")
+    pairs = {'lgcn_spmm_plan_t': _lib.SpmmPlan, 'lgcn_spmm_peers_t': _lib.SpmmPeers, 'lgcn_adam_scalars_t': _lib.AdamScalars,
+             'lgcn_bpr_feat_t': _lib.BprFeat}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lgcn_b200.h"', 'int main(void) {']
+    for cname, st in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include')
+    subprocess.run([cc, '-std=c99', '-I', inc, str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line in out:
+        cname, *nums = line.split()
+        st = pairs[cname]
+        want = [ctypes.sizeof(st)] + [getattr(st, f).offset for f, _ in st._fields_]
+        assert [int(x) for x in nums] == want, f"{cname}: header {nums} vs ctypes {want}"
+
+
 def test_host_side_queries_without_gpu():
     import lgcn_b200 as lg
     lib = lg._lib.load()
