@@ -79,6 +79,8 @@ def BPR_train_original(dataset, recommend_model, loss_class, epoch, neg_k=1, w=N
             eng._alloc_batch(bs)
         eng.set_lr(bpr.opt.param_groups[0]['lr'])
         eng.decay = float(bpr.weight_decay)
+        if mode in ('rowpart', 'featpart') and nranks > 1:
+            _assert_same_on_every_rank(S_dev, group, "the epoch's device-sampled triples")      # same (seed, epoch) key on every rank
         steps = eng.begin_epoch(S_dev)
         for _ in range(steps):
             eng.epoch_step()
