@@ -536,7 +536,7 @@ tc_select_kernel(int Bt, int n_item_tiles, const float* __restrict__ tile_max, i
 // rescore: warp per row — exact rescoring of every candidate, top-k by rank counting, certificate
 constexpr int RS_WARPS = 4;
 constexpr int RS_CAP = 192;
-constexpr int RS_BATCH = 16;         // item rows staged per step
+constexpr int RS_BATCH = 16;         // item rows staged per step (32 was measured: +8 % on the whole call — fewer resident warps — profiles/r2_eval_probe_rescore_batch32.jsonl)
 __global__ void __launch_bounds__(RS_WARPS * 32)
 rescore_kernel(const float* __restrict__ U, const float* __restrict__ V, const long long* __restrict__ users, int Bt, int n_lists, int k, TcOrder order,
                const float4* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt,
