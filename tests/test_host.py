@@ -468,3 +468,23 @@ def test_tensor_core_threshold_rule_on_the_host(kind):
     assert max(hits_all) <= 160 and worst_list <= 32, (max(hits_all), worst_list)
     if kind == "popular_adjacent_ids":
         assert in_order_worst > 32                                    # what the layout is for
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver's contract for `bench.py --impl reference` (runs on the host cores, no GPU): stdout is ONE JSON line with the
+    same metric/unit/config keys as the GPU arm, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e block;
+    everything else (library banners, prints) goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'tiny', '--steps', '3', '--warmup', '3'],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'samples/s' and d['higher_is_better'] is True and d['n_gpus'] == 1
+    assert d['steps'] == 3 and d['warmup'] == 3 and d['value'] > 0 and d['ms_per_step'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and 'model' not in d['config'] and d['gpu_launches'] == 0
